@@ -1,0 +1,112 @@
+"""ctypes binding for ``csrc/host_runtime.cpp``."""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).parent / "_host_runtime.so"
+_lib: Optional[ctypes.CDLL] = None
+_tried = False
+
+
+def _load() -> Optional[ctypes.CDLL]:
+    global _lib, _tried
+    if _tried:
+        return _lib
+    _tried = True
+    if os.environ.get("SRB_DISABLE_NATIVE") == "1" or not _LIB_PATH.exists():
+        return None
+    try:
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        lib.srb_featurize.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+        lib.srb_featurize.restype = None
+        lib.srb_collate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        lib.srb_collate.restype = ctypes.c_int64
+        lib.srb_collate_gold.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        lib.srb_collate_gold.restype = ctypes.c_int64
+        lib.srb_abi_version.restype = ctypes.c_int
+        if lib.srb_abi_version() != 1:
+            return None
+        _lib = lib
+    except OSError:
+        _lib = None
+    return _lib
+
+
+def available() -> bool:
+    return _load() is not None
+
+
+def featurize_words(words: Sequence[str]) -> np.ndarray:
+    lib = _load()
+    assert lib is not None
+    n = len(words)
+    enc = [w.encode("utf8") for w in words]
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum([len(b) for b in enc], out=offsets[1:])
+    buf = b"".join(enc)
+    out = np.empty((n, 4), dtype=np.uint64)
+    flags = np.zeros(n, dtype=np.uint8)
+    lib.srb_featurize(buf, offsets.ctypes.data, n, out.ctypes.data, flags.ctypes.data)
+    if flags.any():
+        from ..pipeline.doc import lex_attrs
+
+        for i in np.nonzero(flags)[0]:
+            a = lex_attrs(words[int(i)])
+            out[i, 0], out[i, 1], out[i, 2], out[i, 3] = a[0], a[1], a[2], a[3]
+    return out
+
+
+def collate(store: np.ndarray, doc_off: np.ndarray, ids: np.ndarray, out_attrs: np.ndarray,
+            out_mask: np.ndarray, out_starts: np.ndarray, out_lens: np.ndarray) -> int:
+    """Gather docs ``ids`` from the corpus-wide ``store`` into padded staging
+    buffers (may be pinned-tensor-backed numpy views).  Returns rows used."""
+    lib = _load()
+    cap = out_attrs.shape[0]
+    n_attr = store.shape[1]
+    if lib is not None:
+        used = lib.srb_collate(store.ctypes.data, doc_off.ctypes.data, n_attr, ids.ctypes.data, len(ids),
+                               out_attrs.ctypes.data, out_mask.ctypes.data, out_starts.ctypes.data,
+                               out_lens.ctypes.data, cap)
+        if used < 0:
+            raise ValueError("collate: staging buffer too small")
+        return int(used)
+    out_attrs[:] = 0
+    out_mask[:] = 0
+    row = 1
+    for d, i in enumerate(ids):
+        a, b = int(doc_off[i]), int(doc_off[i + 1])
+        n = b - a
+        if row + n + 1 > cap:
+            raise ValueError("collate: staging buffer too small")
+        out_starts[d] = row
+        out_lens[d] = n
+        out_attrs[row:row + n] = store[a:b]
+        out_mask[row:row + n] = 1.0
+        row += n + 1
+    return row
+
+
+def collate_gold(store: np.ndarray, doc_off: np.ndarray, ids: np.ndarray, out: np.ndarray, out_off: np.ndarray) -> int:
+    lib = _load()
+    if lib is not None:
+        used = lib.srb_collate_gold(store.ctypes.data, doc_off.ctypes.data, ids.ctypes.data, len(ids),
+                                    out.ctypes.data, out_off.ctypes.data, out.shape[0])
+        if used < 0:
+            raise ValueError("collate_gold: staging buffer too small")
+        return int(used)
+    pos = 0
+    for d, i in enumerate(ids):
+        a, b = int(doc_off[i]), int(doc_off[i + 1])
+        n = b - a
+        out_off[d] = pos
+        out[pos:pos + n] = store[a:b]
+        pos += n
+    return pos

@@ -1,0 +1,407 @@
+"""Trainable pipeline components: tok2vec, tagger, ner, parser.
+
+These are the pipes the reference trains through spaCy's
+``nlp.update`` (``/root/reference/spacy_ray/worker.py:176-189`` ->
+``train_while_improving`` -> ``pipe.update``).  Factories are registered under
+spaCy's factory names so ``[components.ner] factory = "ner"`` resolves.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..config import registry
+from ..models.transition_model import TransitionGold
+from ..nn.batch import TokenBatch
+from ..nn.layers import set_dropout_rate
+from ..nn.model import Model
+from . import scorer as S
+from .doc import Doc, Example
+from .transitions import (
+    ArcEagerSystem, BiluoSystem, biluo_actions_to_spans, is_projective, spans_to_biluo_actions,
+)
+
+
+class TrainablePipe:
+    is_trainable = True
+    default_score_weights: Dict[str, Any] = {}
+
+    def __init__(self, name: str, model: Model, **cfg):
+        self.name = name
+        self.model = model
+        self.cfg = dict(cfg)
+        self._labels: List[str] = []
+
+    # ---- labels ----------------------------------------------------------
+    @property
+    def labels(self) -> List[str]:
+        return list(self._labels)
+
+    def add_label(self, label: str) -> int:
+        if label in self._labels:
+            return 0
+        self._labels.append(label)
+        return 1
+
+    # ---- lifecycle -------------------------------------------------------
+    def initialize(self, get_examples: Callable[[], Iterable[Example]], *, nlp=None, labels=None) -> None:
+        raise NotImplementedError
+
+    def update(self, examples, *, batch: TokenBatch, drop: float = 0.0, sgd=None, losses=None):
+        raise NotImplementedError
+
+    def predict(self, docs: Sequence[Doc], batch: TokenBatch):
+        raise NotImplementedError
+
+    def set_annotations(self, docs: Sequence[Doc], preds) -> None:
+        raise NotImplementedError
+
+    def finish_update(self, sgd) -> None:
+        self.model.finish_update(sgd)
+
+    def score(self, examples) -> Dict[str, Any]:
+        return {}
+
+    @property
+    def listening_to(self) -> List[Model]:
+        return [n for n in self.model.walk() if n.name == "tok2vec_listener"]
+
+    # ---- serialisation ---------------------------------------------------
+    def to_disk(self, path: Path) -> None:
+        path = Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        (path / "cfg").write_text(json.dumps({"labels": self._labels, **self._json_cfg()}, indent=1))
+        (path / "model").write_bytes(self.model.to_bytes())
+
+    def from_disk(self, path: Path) -> "TrainablePipe":
+        path = Path(path)
+        meta = json.loads((path / "cfg").read_text())
+        self._labels = list(meta.get("labels", []))
+        self._after_labels()
+        self.model.initialize()
+        self.model.from_bytes((path / "model").read_bytes())
+        return self
+
+    def _json_cfg(self) -> Dict[str, Any]:
+        return {k: v for k, v in self.cfg.items() if isinstance(v, (int, float, str, bool, list, type(None)))}
+
+    def _after_labels(self) -> None:
+        pass
+
+
+# ============================================================================
+class Tok2VecComponent(TrainablePipe):
+    """Shared embedding/encoding layer.  Downstream components that use a
+    ``Tok2VecListener`` get this component's output and send gradients back."""
+
+    def __init__(self, name: str, model: Model):
+        super().__init__(name, model)
+        self.listeners: List[Model] = []
+        self._pending = None
+
+    def add_listener(self, listener: Model) -> None:
+        if listener not in self.listeners:
+            self.listeners.append(listener)
+
+    def find_listeners(self, component: TrainablePipe) -> None:
+        for node in component.listening_to:
+            up = node.attrs.get("upstream", "*")
+            if up in ("*", self.name):
+                self.add_listener(node)
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        self.model.initialize()
+
+    def predict(self, docs, batch):
+        out = self.model.predict(batch)
+        for l in self.listeners:
+            l.attrs["receive"](batch, out, None)
+        return out
+
+    def set_annotations(self, docs, preds) -> None:
+        pass
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        """Run the forward pass now; the backward pass runs when the *last*
+        listener has handed its gradient back (spaCy's listener protocol)."""
+        set_dropout_rate(self.model, drop)
+        outputs, bp = self.model.begin_update(batch)
+        n_listeners = len(self.listeners)
+        state = {"d": None, "count": 0}
+
+        def accumulate(dY):
+            state["d"] = dY.clone() if state["d"] is None else state["d"].add_(dY)
+            state["count"] += 1
+            if state["count"] == n_listeners:
+                bp(state["d"])
+                if sgd not in (None, False):
+                    self.finish_update(sgd)
+
+        for l in self.listeners:
+            l.attrs["receive"](batch, outputs, accumulate)
+        if losses is not None:
+            losses.setdefault(self.name, 0.0)
+        return losses
+
+
+# ============================================================================
+class Tagger(TrainablePipe):
+    default_score_weights = {"tag_acc": 1.0}
+
+    def _after_labels(self) -> None:
+        if self.model.has_dim("nO") is None and self._labels:
+            self.model.set_dim("nO", len(self._labels))
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                for t in (eg.reference.tags or []):
+                    if t:
+                        seen.add(t)
+            for t in sorted(seen):
+                self.add_label(t)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no tag labels found in the training data")
+        self._after_labels()
+        self.model.initialize()
+
+    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
+        index = {l: i for i, l in enumerate(self._labels)}
+        arr = np.full((batch.n_rows,), -1, dtype=np.int64)
+        for eg, s in zip(examples, batch.starts):
+            ref = eg.reference
+            ids = ref.user_data.get(("tag_ids", self.name))
+            if ids is None:
+                tags = ref.tags or [None] * len(ref)
+                ids = np.array([index.get(t, -1) if t else -1 for t in tags], dtype=np.int64)
+                ref.user_data[("tag_ids", self.name)] = ids
+            arr[s:s + len(ids)] = ids
+        return torch.from_numpy(arr).to(batch.device)
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        set_dropout_rate(self.model, drop)
+        labels = self._gold_labels(examples, batch)
+        loss, _guesses = self.model.attrs["update_with_labels"](batch, labels)
+        if sgd not in (None, False):
+            self.finish_update(sgd)
+        if losses is not None:
+            losses[self.name] = losses.get(self.name, 0.0) + float(loss)
+        return losses
+
+    def predict(self, docs, batch):
+        P = self.model.predict(batch)
+        return P.argmax(dim=1)
+
+    def set_annotations(self, docs, preds) -> None:
+        host = preds.to("cpu").tolist()
+        row = 1
+        for doc in docs:
+            n = len(doc)
+            doc.tags = [self._labels[i] for i in host[row:row + n]]
+            row += n + 1
+
+    def score(self, examples):
+        return S.score_tags(examples)
+
+
+# ============================================================================
+class EntityRecognizer(TrainablePipe):
+    default_score_weights = {"ents_f": 1.0, "ents_p": 0.0, "ents_r": 0.0, "ents_per_type": None}
+
+    def __init__(self, name, model, **cfg):
+        super().__init__(name, model, **cfg)
+        self.system: Optional[BiluoSystem] = None
+
+    def _after_labels(self) -> None:
+        self.system = BiluoSystem(self._labels)
+        if self.model.has_dim("nO") is None:
+            self.model.set_dim("nO", self.system.n_actions)
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                for (_s, _e, lab) in eg.reference.ents:
+                    seen.add(lab)
+            for l in sorted(seen):
+                self.add_label(l)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no entity labels found in the training data")
+        self._after_labels()
+        self.model.initialize()
+
+    def gold_actions(self, ref: Doc) -> np.ndarray:
+        key = ("ner_actions", self.name)
+        acts = ref.user_data.get(key)
+        if acts is None:
+            if not ref.has_ents_annotation:
+                acts = np.full((len(ref),), -1, dtype=np.int64)
+            else:
+                index = {l: i for i, l in enumerate(self._labels)}
+                spans = [(s, e, index[l]) for (s, e, l) in ref.ents if l in index]
+                acts = np.array(spans_to_biluo_actions(len(ref), spans), dtype=np.int64)
+            ref.user_data[key] = acts
+        return acts
+
+    def _make_gold(self, examples, batch: TokenBatch) -> TransitionGold:
+        per_doc = [self.gold_actions(eg.reference) for eg in examples]
+        flat = np.concatenate(per_doc) if per_doc else np.zeros((0,), dtype=np.int64)
+        offs = np.zeros(len(per_doc), dtype=np.int64)
+        if len(per_doc) > 1:
+            offs[1:] = np.cumsum([len(a) for a in per_doc])[:-1]
+        dev = batch.device
+        return TransitionGold(actions=torch.from_numpy(flat).to(dev), offsets=torch.from_numpy(offs).to(dev))
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        set_dropout_rate(self.model, drop)
+        gold = self._make_gold(examples, batch)
+        out = self.model.attrs["run"](batch, self.system, gold, True)
+        if sgd not in (None, False):
+            self.finish_update(sgd)
+        if losses is not None:
+            losses[self.name] = losses.get(self.name, 0.0) + float(out.loss)
+        return losses
+
+    def predict(self, docs, batch):
+        return self.model.attrs["run"](batch, self.system, None, False)
+
+    def set_annotations(self, docs, out) -> None:
+        host = out.actions_flat.to("cpu").tolist()
+        pos = 0
+        for doc in docs:
+            n = len(doc)
+            spans = biluo_actions_to_spans(host[pos:pos + n])
+            doc.ents = [(s, e, self._labels[l]) for (s, e, l) in spans]
+            doc.has_ents_annotation = True
+            pos += n
+
+    def score(self, examples):
+        return S.score_ents(examples)
+
+
+# ============================================================================
+class DependencyParser(TrainablePipe):
+    default_score_weights = {"dep_uas": 0.5, "dep_las": 0.5}
+
+    def __init__(self, name, model, **cfg):
+        super().__init__(name, model, **cfg)
+        self.system: Optional[ArcEagerSystem] = None
+
+    def _after_labels(self) -> None:
+        self.system = ArcEagerSystem(self._labels)
+        if self.model.has_dim("nO") is None:
+            self.model.set_dim("nO", self.system.n_actions)
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                for d in (eg.reference.deps or []):
+                    if d:
+                        seen.add(d)
+            for l in sorted(seen):
+                self.add_label(l)
+        if not self._labels:
+            self.add_label("dep")
+        self._after_labels()
+        self.model.initialize()
+
+    def _gold(self, ref: Doc):
+        key = ("dep_gold", self.name)
+        g = ref.user_data.get(key)
+        if g is None:
+            n = len(ref)
+            if ref.heads is None:
+                g = ([-1] * n, [-1] * n)
+            else:
+                index = {l: i for i, l in enumerate(self._labels)}
+                heads = [h if (h is not None and 0 <= h < n) else -1 for h in ref.heads]
+                if not is_projective([h if h >= 0 else t for t, h in enumerate(heads)]):
+                    heads = [-1] * n           # non-projective trees can't be reached: treat as unannotated
+                deps = ref.deps or [None] * n
+                g = (heads, [index.get(d, -1) if d else -1 for d in deps])
+            ref.user_data[key] = g
+        return g
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        set_dropout_rate(self.model, drop)
+        golds = [self._gold(eg.reference) for eg in examples]
+        gold = TransitionGold(heads=[g[0] for g in golds], labels=[g[1] for g in golds])
+        out = self.model.attrs["run"](batch, self.system, gold, True)
+        if sgd not in (None, False):
+            self.finish_update(sgd)
+        if losses is not None:
+            losses[self.name] = losses.get(self.name, 0.0) + float(out.loss)
+        return losses
+
+    def predict(self, docs, batch):
+        return self.model.attrs["run"](batch, self.system, None, False)
+
+    def set_annotations(self, docs, out) -> None:
+        for doc, st in zip(docs, out.states):
+            heads, labs = self.system.finalize(st)
+            doc.heads = heads
+            doc.deps = [self._labels[l] if l >= 0 else "ROOT" for l in labs]
+
+    def score(self, examples):
+        return S.score_deps(examples)
+
+
+# ---- factories ----------------------------------------------------------------
+@registry.factories("tok2vec")
+def make_tok2vec(nlp, name: str, model: Model) -> Tok2VecComponent:
+    return Tok2VecComponent(name, model)
+
+
+@registry.factories("tagger")
+def make_tagger(nlp, name: str, model: Model, **cfg) -> Tagger:
+    return Tagger(name, model, **cfg)
+
+
+@registry.factories("ner")
+def make_ner(nlp, name: str, model: Model, **cfg) -> EntityRecognizer:
+    return EntityRecognizer(name, model, **cfg)
+
+
+@registry.factories("parser")
+def make_parser(nlp, name: str, model: Model, **cfg) -> DependencyParser:
+    return DependencyParser(name, model, **cfg)
+
+
+DEFAULT_MODEL_CONFIGS: Dict[str, Dict[str, Any]] = {
+    "tok2vec": {
+        "@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+        "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None,
+    },
+    "tagger": {
+        "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "ner": {
+        "@architectures": "spacy.TransitionBasedParser.v2", "state_type": "ner", "extra_state_tokens": False,
+        "hidden_width": 64, "maxout_pieces": 2, "use_upper": True,
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "parser": {
+        "@architectures": "spacy.TransitionBasedParser.v2", "state_type": "parser", "extra_state_tokens": False,
+        "hidden_width": 128, "maxout_pieces": 3, "use_upper": True,
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+}

@@ -1,0 +1,106 @@
+"""Checkpoint / resume.
+
+The reference defines ``Worker.save_checkpoint`` but never calls it and drops
+``--output``.  Here: rank 0 writes the pipeline directory
+(``model-best`` / ``model-last``: ``config.cfg``, ``meta.json``, ``<pipe>/model``,
+``<pipe>/cfg``); every rank additionally writes the optimizer state of the
+parameter keys it *owns* to ``optim/rank{r}-of{n}.pt`` keyed by *structural*
+key (component name, node index in ``walk()`` order, param name), so a resumed
+run re-derives ownership with the same ``divide_params`` and refuses a
+world-size mismatch unless told to re-shard."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+KeyT = Tuple[int, str]
+
+
+def structural_keys(nlp) -> Dict[KeyT, Tuple[str, int, str]]:
+    """``(node.id, name) -> (component, walk_index, name)``; stable across
+    processes regardless of the absolute id values."""
+    out: Dict[KeyT, Tuple[str, int, str]] = {}
+    for cname, comp in nlp.components:
+        model = getattr(comp, "model", None)
+        if model is None:
+            continue
+        for i, node in enumerate(model.walk()):
+            for pname in node.param_names:
+                out.setdefault((node.id, pname), (cname, i, pname))
+    return out
+
+
+def save_optimizer_shard(path: Path, nlp, optimizer, owned_keys: Iterable[KeyT], *, rank: int, world_size: int,
+                         extra: Optional[Dict[str, Any]] = None) -> Path:
+    path = Path(path) / "optim"
+    path.mkdir(parents=True, exist_ok=True)
+    skeys = structural_keys(nlp)
+    state = optimizer.state_dict(keys=list(owned_keys))
+
+    def conv(d):
+        return None if d is None else {skeys[k]: v for k, v in d.items() if k in skeys}
+
+    blob = {
+        "rank": rank, "world_size": world_size,
+        "mom1": conv(state["mom1"]), "mom2": conv(state["mom2"]), "nr_update": conv(state["nr_update"]),
+        "averages": conv(state["averages"]), "step": state["step"], "hyper": state["hyper"],
+        "extra": extra or {},
+    }
+    out = path / f"rank{rank}-of{world_size}.pt"
+    torch.save(blob, out)
+    return out
+
+
+def load_optimizer_shards(path: Path, nlp, optimizer, owned_keys: Iterable[KeyT], *, rank: int, world_size: int,
+                          allow_reshard: bool = True) -> Dict[str, Any]:
+    """Load the optimizer state for ``owned_keys``.  With the same world size only
+    this rank's file is read; otherwise (``allow_reshard``) all shards are scanned
+    and the keys this rank now owns are picked out."""
+    path = Path(path) / "optim"
+    files = sorted(path.glob("rank*-of*.pt"))
+    if not files:
+        raise FileNotFoundError(f"No optimizer shards under {path}")
+    saved_ws = int(files[0].stem.split("-of")[1])
+    if saved_ws != world_size and not allow_reshard:
+        raise ValueError(f"Checkpoint was written with world_size={saved_ws}, now {world_size}")
+    wanted = [path / f"rank{rank}-of{world_size}.pt"] if saved_ws == world_size else files
+    by_struct = {v: k for k, v in structural_keys(nlp).items()}
+    owned = set(owned_keys)
+    state = {"mom1": {}, "mom2": {}, "nr_update": {}, "averages": None, "step": 0}
+    extra: Dict[str, Any] = {}
+    for f in wanted:
+        blob = torch.load(f, map_location="cpu", weights_only=False)
+        state["step"] = max(state["step"], int(blob.get("step", 0)))
+        extra = blob.get("extra", {}) or extra
+        for field in ("mom1", "mom2", "nr_update"):
+            for skey, v in (blob[field] or {}).items():
+                key = by_struct.get(tuple(skey))
+                if key is not None and key in owned:
+                    state[field][key] = v
+        if blob.get("averages"):
+            state["averages"] = state["averages"] or {}
+            for skey, v in blob["averages"].items():
+                key = by_struct.get(tuple(skey))
+                if key is not None and key in owned:
+                    state["averages"][key] = v
+    optimizer.load_state_dict(state)
+    return extra
+
+
+def save_pipeline(nlp, path: Path, *, training_cfg: Optional[Dict[str, Any]] = None, info: Optional[Dict[str, Any]] = None,
+                  before_to_disk=None) -> None:
+    from .loop import update_meta
+
+    path = Path(path)
+    if training_cfg is not None and info is not None:
+        frozen = training_cfg.get("frozen_components", []) or []
+        with nlp.select_pipes(disable=frozen):
+            update_meta(training_cfg, nlp, info)
+    target = before_to_disk(nlp) if before_to_disk else nlp
+    target.to_disk(path)
+    if info is not None:
+        slim = {k: v for k, v in info.items() if k in ("epoch", "step", "score", "words", "seconds")}
+        (path / "training_state.json").write_text(json.dumps(slim, default=str))

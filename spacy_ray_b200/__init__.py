@@ -13,3 +13,6 @@ from .config import Config, registry, load_config  # noqa: F401
 from . import models as _models  # noqa: F401  (registers architectures)
 from . import training as _training  # noqa: F401  (registers optimizers, batchers, loggers, readers)
 from .pipeline import Language, Doc, Example, blank, load  # noqa: F401
+from .worker import Worker, Evaluator, FakeOptimizer, thread_training  # noqa: F401,E402
+from .train_cli import ray_train, ray_cli  # noqa: F401,E402
+from .parallel.proxies import RayPeerProxy, RayOptimizer, PeerProxy  # noqa: F401,E402

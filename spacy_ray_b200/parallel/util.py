@@ -1,0 +1,123 @@
+"""Parameter-ownership partitioning, proxy installation, timers.
+
+API-compatible with ``/root/reference/spacy_ray/util.py`` (``KeyT``,
+``make_key``, ``divide_params``, ``set_params_proxy``, ``Timer``,
+``ManyTimer``).  ``divide_params`` reproduces the reference partition exactly
+(SURVEY.md 2.1 #6): keys grouped per node so a layer's params share an owner,
+``max(1, n_groups // num_workers)`` consecutive groups per rank, all leftovers
+to the last rank, trailing ranks empty if there are fewer groups than ranks.
+``divide_params_balanced`` is the opt-in byte-balanced alternative.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, Iterable, List, Sequence, Tuple
+
+KeyT = Tuple[int, str]
+
+
+def make_key(model_id: int, name: str) -> KeyT:
+    return (model_id, name)
+
+
+def _key_groups(model) -> List[List[KeyT]]:
+    groups: Dict[int, List[KeyT]] = {}
+    for node in model.walk():
+        for name in node.param_names:
+            groups.setdefault(node.id, []).append(make_key(node.id, name))
+    return [g for g in groups.values() if g]
+
+
+def divide_params(model, num_workers: int) -> List[List[KeyT]]:
+    """Owner partition of a component model's parameter keys (reference layout)."""
+    groups = _key_groups(model)
+    per_rank = max(1, len(groups) // num_workers)
+    shares: List[List[KeyT]] = [[] for _ in range(num_workers)]
+    for gi, group in enumerate(groups):
+        owner = min(gi // per_rank, num_workers - 1)
+        shares[owner].extend(group)
+    return shares
+
+
+def divide_params_balanced(model, num_workers: int) -> List[List[KeyT]]:
+    """Contiguous partition of node groups minimising the largest shard (by
+    element count) greedily: keeps a layer's params together like
+    ``divide_params`` but evens out bytes (the reference counts nodes, so the
+    embedding tables make rank 0 ~2x heavier than the rest)."""
+    groups = _key_groups(model)
+    sizes = []
+    by_key = {}
+    for node in model.walk():
+        for name in node.param_names:
+            if node.has_param(name):
+                by_key[make_key(node.id, name)] = int(node.get_param(name).numel())
+    for g in groups:
+        sizes.append(sum(by_key.get(k, 0) for k in g))
+    total = sum(sizes)
+    shares: List[List[KeyT]] = [[] for _ in range(num_workers)]
+    rank, acc = 0, 0
+    remaining = total
+    for gi, (g, sz) in enumerate(zip(groups, sizes)):
+        groups_left = len(groups) - gi
+        ranks_left = num_workers - rank
+        target = remaining / max(1, ranks_left)
+        if shares[rank] and rank < num_workers - 1 and (acc + sz / 2.0 > target or groups_left <= ranks_left - 1):
+            remaining -= acc
+            rank += 1
+            acc = 0
+        shares[rank].extend(g)
+        acc += sz
+    return shares
+
+
+def set_params_proxy(model, proxy) -> None:
+    """Install ``proxy`` on every node of ``model``: existing parameter values
+    are handed to ``proxy.set_param`` first, then the node's ``ParamServer``
+    routes all further reads/grad writes through the proxy."""
+    for node in model.walk():
+        node._params.proxy = None
+        for name in node.param_names:
+            if node.has_param(name):
+                proxy.set_param(node.id, name, node.get_param(name))
+        node._params.proxy = proxy
+
+
+def clear_params_proxy(model) -> None:
+    for node in model.walk():
+        node._params.proxy = None
+
+
+class Timer:
+    """Accumulating wall-clock timer (context manager)."""
+
+    def __init__(self, state: str):
+        self.state = state
+        self.sum = 0.0
+        self.n = 0
+        self.start = 0.0
+
+    def __enter__(self) -> "Timer":
+        self.start = time.time()
+        self.n += 1
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.sum += time.time() - self.start
+
+    @property
+    def mean(self) -> float:
+        return self.sum / self.n if self.n else 0.0
+
+
+class ManyTimer:
+    def __init__(self):
+        self.timers: Dict[str, Timer] = {}
+
+    def __call__(self, key: str) -> Timer:
+        timer = self.timers.get(key)
+        if timer is None:
+            timer = self.timers[key] = Timer(key)
+        return timer
+
+    def report(self) -> Dict[str, Dict[str, float]]:
+        return {k: {"sum": t.sum, "n": t.n, "mean": t.mean} for k, t in self.timers.items()}

@@ -96,8 +96,10 @@ class SyntheticCorpus:
 
     def __init__(self, n_docs: int = 2000, seed: int = 0, min_len: int = 8, max_len: int = 40,
                  vocab_size: int = 20000, n_tags: int = 17, n_ent_labels: int = 4, n_dep_labels: int = 8,
-                 ent_rate: float = 0.12, noise: float = 0.02, tasks: Sequence[str] = ("tagger", "ner", "parser")):
+                 ent_rate: float = 0.12, noise: float = 0.02, tasks: Sequence[str] = ("tagger", "ner", "parser"),
+                 vocab_seed: int = 0):
         self.n_docs, self.seed = int(n_docs), int(seed)
+        self.vocab_seed = int(vocab_seed)       # shared by train/dev corpora so word types (and their tags) agree
         self.min_len, self.max_len = int(min_len), int(max_len)
         self.vocab_size = int(vocab_size)
         self.n_tags = min(int(n_tags), len(TAGS))
@@ -111,7 +113,7 @@ class SyntheticCorpus:
     # ---- vocabulary --------------------------------------------------------
     def vocab(self) -> Dict[str, Any]:
         if self._vocab is None:
-            rng = np.random.default_rng(self.seed * 7919 + 13)
+            rng = np.random.default_rng(self.vocab_seed * 7919 + 13)
             V = self.vocab_size
             words = []
             seen = set()
@@ -225,6 +227,6 @@ def itertools_cycle(seq):
 def create_synthetic_corpus(n_docs: int = 2000, seed: int = 0, min_len: int = 8, max_len: int = 40,
                             vocab_size: int = 20000, n_tags: int = 17, n_ent_labels: int = 4,
                             n_dep_labels: int = 8, ent_rate: float = 0.12, noise: float = 0.02,
-                            tasks: Sequence[str] = ("tagger", "ner", "parser")) -> SyntheticCorpus:
+                            tasks: Sequence[str] = ("tagger", "ner", "parser"), vocab_seed: int = 0) -> SyntheticCorpus:
     return SyntheticCorpus(n_docs, seed, min_len, max_len, vocab_size, n_tags, n_ent_labels, n_dep_labels,
-                           ent_rate, noise, tasks)
+                           ent_rate, noise, tasks, vocab_seed)

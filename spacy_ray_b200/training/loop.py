@@ -111,7 +111,7 @@ def update_meta(training: Dict[str, Any], nlp, info: Dict[str, Any]) -> None:
     nlp.meta["performance"] = {}
     for metric in (training.get("score_weights") or {}):
         if metric is not None:
-            nlp.meta["performance"][metric] = info.get("other_scores", {}).get(metric, 0.0)
+            nlp.meta["performance"][metric] = (info.get("other_scores") or {}).get(metric, 0.0)
     for pipe_name in nlp.pipe_names:
         if pipe_name in info.get("losses", {}):
             nlp.meta["performance"][f"{pipe_name}_loss"] = info["losses"][pipe_name]

@@ -1,0 +1,101 @@
+"""Device-side timing + clock sampling (the reference has only an
+unused wall-clock ``Timer``).  Every throughput number is measured with CUDA
+events on the launching stream; ``ClockSampler`` records SM clocks / throttle
+reasons during the timed region (B200_PROFILING.md recipe)."""
+from __future__ import annotations
+
+import subprocess
+import threading
+import time
+from typing import Any, Dict, List, Optional
+
+import torch
+
+
+class CudaStepTimer:
+    """Start/stop CUDA events around a region; ``elapsed_ms`` synchronises."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
+        if self.cuda:
+            self._start = torch.cuda.Event(enable_timing=True)
+            self._stop = torch.cuda.Event(enable_timing=True)
+        self._t0 = 0.0
+        self._t1 = 0.0
+
+    def start(self) -> None:
+        if self.cuda:
+            self._start.record()
+        else:
+            self._t0 = time.perf_counter()
+
+    def stop(self) -> None:
+        if self.cuda:
+            self._stop.record()
+        else:
+            self._t1 = time.perf_counter()
+
+    def elapsed_ms(self) -> float:
+        if self.cuda:
+            self._stop.synchronize()
+            return float(self._start.elapsed_time(self._stop))
+        return (self._t1 - self._t0) * 1e3
+
+
+class ClockSampler:
+    """Polls ``nvidia-smi`` in a background thread while a region is timed."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0, period_s: float = 0.2):
+        self.gpu_index = gpu_index
+        self.period_s = period_s
+        self.samples: List[Dict[str, Any]] = []
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+
+    def _poll(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip().splitlines()
+                for line in out:
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 9:
+                        self.samples.append({
+                            "sm": float(f[1]), "sm_max": float(f[2]), "power": float(f[3]) if f[3] not in ("[N/A]", "N/A") else 0.0,
+                            "active": f[4], "hw_slowdown": f[5], "hw_thermal": f[6], "sw_thermal": f[7], "sw_power_cap": f[8],
+                        })
+            except Exception:
+                pass
+            self._stop.wait(self.period_s)
+
+    def __enter__(self) -> "ClockSampler":
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=6)
+
+    def summary(self) -> Dict[str, Any]:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sms = sorted(s["sm"] for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for key, name in (("hw_slowdown", "hw_slowdown"), ("hw_thermal", "hw_thermal_slowdown"),
+                              ("sw_thermal", "sw_thermal_slowdown"), ("sw_power_cap", "sw_power_cap")):
+                if str(s[key]).lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": sms[len(sms) // 2], "sm_max_mhz": self.samples[0]["sm_max"],
+            "power_w_max": max(s["power"] for s in self.samples), "reasons": sorted(reasons),
+            "samples": len(self.samples),
+        }

@@ -1,0 +1,319 @@
+"""``B200Ops``: the sm_100a backend (hand-written kernels in ``ops/csrc``).
+
+Same interface as ``TorchOps`` (which is its numerics reference), bf16
+parameters/activations, fp32 gradients.  GEMM-shaped work runs on the
+tcgen05/TMEM kernels of ``gemm_tcgen05.cu`` (``use_tc=True``); with
+``use_tc=False`` GEMMs go to cuBLAS via ``torch.matmul`` and only the fused
+elementwise kernels are ours - that configuration is the "library GEMM"
+baseline arm used to quantify what the fusion buys.
+
+There is no silent fallback: constructing ``B200Ops`` without the built
+extension raises (``python -m spacy_ray_b200.build`` builds it in-tree).
+"""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .torch_ops import TorchOps
+
+_LIB = Path(__file__).parent / "_srb_cuda.so"
+_loaded = False
+
+MODE_KK, MODE_MNMN = 0, 1
+EPI_STORE, EPI_MAXOUT3, EPI_ATOMIC_F32 = 0, 1, 2
+
+
+def load_extension() -> None:
+    global _loaded
+    if _loaded:
+        return
+    if not _LIB.exists():
+        raise RuntimeError(
+            f"sm_100a extension not built: {_LIB} is missing. Run `python -m spacy_ray_b200.build` "
+            "(or __graft_entry__.build()). Refusing to fall back to PyTorch ops on a GPU run."
+        )
+    torch.ops.load_library(str(_LIB))
+    _loaded = True
+
+
+def extension_available() -> bool:
+    return _LIB.exists()
+
+
+def _mask1d(mask: torch.Tensor) -> torch.Tensor:
+    return mask.reshape(-1)
+
+
+class B200Ops(TorchOps):
+    name = "b200"
+    fused = True
+    param_dtype = torch.bfloat16
+
+    def __init__(self, device: str = "cuda:0", *, use_tc: Optional[bool] = None, tc_dw: Optional[bool] = None):
+        super().__init__(device=device, dtype=torch.bfloat16)
+        if self.device.type != "cuda":
+            raise ValueError("B200Ops needs a CUDA device")
+        load_extension()
+        self.k = torch.ops.srb
+        env_tc = os.environ.get("SRB_USE_TC")
+        self.use_tc = (env_tc != "0") if use_tc is None else use_tc
+        env_dw = os.environ.get("SRB_TC_DW")
+        self.tc_dw = (env_dw != "0") if tc_dw is None else tc_dw
+        self.launches = 0            # our kernels launched (bench.py reports this)
+        self._wt_cache: Dict[int, Tuple[int, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------ GEMM helpers
+    def _tc_ok(self, *dims: int) -> bool:
+        return self.use_tc and all(d % 64 == 0 and d > 0 for d in dims)
+
+    def tc_gemm(self, A, B, out, *, mode, epi, block_n, M, N, K, a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,),
+                b_col_off=(0,), splits=1, win_w=0, bias=None, which=None, add_src=None, row_scale=None, m_dev=None,
+                max_ctas=0) -> None:
+        self.k.tc_gemm(A, B, out, mode, epi, block_n, M, N, K, list(a_row_shift), list(a_col_off), list(b_row_off),
+                       list(b_col_off), splits, win_w, bias, which, add_src, row_scale, m_dev, max_ctas)
+        self.launches += 1
+
+    @staticmethod
+    def _pick_block_n(N: int, options=(256, 192, 128, 64)) -> int:
+        for bn in options:
+            if N % bn == 0:
+                return bn
+        return 0
+
+    def _linear_tc(self, X: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        M, K = X.shape
+        N = W.shape[0]
+        bn = self._pick_block_n(N)
+        if not (self._tc_ok(K) and bn and X.dtype == torch.bfloat16 and W.dtype == torch.bfloat16):
+            return None
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=X.device)
+        self.tc_gemm(X.contiguous(), W.contiguous(), out, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=M, N=N, K=K,
+                     bias=b)
+        return out
+
+    def _dw_tc(self, dZ: torch.Tensor, X: torch.Tensor, window: int, out: Optional[torch.Tensor] = None):
+        """dW[n, k] (+)= sum_t dZ[t, n] * Xw[t, k] on the tcgen05 MN-major/split-K kernel."""
+        T, N = dZ.shape
+        w = X.shape[1]
+        Kt = w * (3 if window else 1)
+        if not (self.use_tc and self.tc_dw and N % 128 == 0 and w % 64 == 0):
+            return None
+        bn = 256 if w % 256 == 0 else (128 if w % 128 == 0 else 64)
+        if out is None:
+            out = torch.zeros((N, Kt), dtype=torch.float32, device=dZ.device)
+        tiles = (N // 128) * (Kt // bn)
+        splits = max(1, min(148 // max(tiles, 1), (T + 63) // 64))
+        self.tc_gemm(dZ, X, out, mode=MODE_MNMN, epi=EPI_ATOMIC_F32, block_n=bn, M=N, N=Kt, K=T, splits=splits,
+                     win_w=(w if window else 0))
+        return out
+
+    # ------------------------------------------------------------------ K1
+    def multi_hash_embed(self, attrs, mask, tables, seeds, columns):
+        self.launches += 1
+        return self.k.hash_embed_fwd(attrs, _mask1d(mask), list(tables), list(seeds), list(columns))
+
+    def multi_hash_embed_backward(self, dY, attrs, mask, n_rows, seeds, columns, out=None):
+        nO = dY.shape[1] // len(n_rows)
+        grads = list(out) if out is not None else [
+            torch.zeros((nV, nO), dtype=torch.float32, device=dY.device) for nV in n_rows
+        ]
+        self.k.hash_embed_bwd(dY.contiguous(), attrs, _mask1d(mask), grads, list(seeds), list(columns))
+        self.launches += 1
+        return grads
+
+    # ------------------------------------------------------------------ K2-K5
+    def maxout_block(self, X, W, b, G, beta, mask, *, window=0, residual=False, dropout=0.0, is_train=False, seed=0):
+        nO, nP, nI = W.shape
+        Tp = X.shape[0]
+        X = X.contiguous()
+        W2 = W.reshape(nO * nP, nI)
+        m1 = _mask1d(mask)
+        drop = float(dropout) if (is_train and dropout > 0.0) else 0.0
+        w_in = X.shape[1]
+        use_tc = nP == 3 and self._tc_ok(nO, w_in) and window in (0, 1)
+        if use_tc:
+            # one tcgen05 kernel: (window) GEMM + bias + maxout; then LN/dropout/residual
+            H = torch.empty((Tp, nO), dtype=torch.bfloat16, device=X.device)
+            which = torch.empty((Tp, nO), dtype=torch.uint8, device=X.device)
+            if window:
+                shifts = dict(a_row_shift=(-1, 0, 1), a_col_off=(0, 0, 0), b_row_off=(0, 0, 0),
+                              b_col_off=(0, w_in, 2 * w_in))
+            else:
+                shifts = {}
+            self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
+                         bias=b.reshape(-1), which=which, **shifts)
+            Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed)
+            self.launches += 1
+        else:
+            Xw = self.k.seq2col(X) if window else X
+            Z = Xw @ W2.t()
+            Y, which, xhat, rstd = self.k.maxout_ln_fwd(Z, b.reshape(-1), G, beta, X if residual else None, m1,
+                                                        nO, nP, drop, seed)
+            self.launches += 2 if window else 1
+        ctx = {"X": X, "W": W, "which": which, "window": window, "residual": residual, "mask": m1, "nP": nP,
+               "has_ln": G is not None, "xhat": xhat, "rstd": rstd, "G": G, "drop": drop, "seed": seed}
+        return Y, ctx
+
+    def _wt(self, W2: torch.Tensor) -> torch.Tensor:
+        return W2.t().contiguous()
+
+    def maxout_block_backward(self, dY, ctx, grad_out: Optional[Dict[str, torch.Tensor]] = None):
+        W = ctx["W"]
+        nO, nP, nI = W.shape
+        X = ctx["X"]
+        Tp, w_in = X.shape
+        window = ctx["window"]
+        dev = X.device
+        has_ln = ctx["has_ln"]
+        db = torch.zeros(nO * nP, dtype=torch.float32, device=dev)
+        dG = torch.zeros(nO, dtype=torch.float32, device=dev) if has_ln else None
+        dbeta = torch.zeros(nO, dtype=torch.float32, device=dev) if has_ln else None
+        dY = dY.contiguous()
+        dZ = self.k.maxout_ln_bwd(dY, ctx["xhat"] if has_ln else None, ctx["rstd"] if has_ln else None,
+                                  ctx["G"], ctx["which"], ctx["mask"], nP, ctx["drop"], ctx["seed"], db, dG, dbeta)
+        self.launches += 1
+        W2 = W.reshape(nO * nP, nI)
+        N = nO * nP
+        # ---- dW ----------------------------------------------------------
+        dW = self._dw_tc(dZ, X, window)
+        if dW is None:
+            Xw = self.k.seq2col(X) if window else X
+            dW = _mm_f32(dZ.t(), Xw)
+        # ---- dX ----------------------------------------------------------
+        bn = self._pick_block_n(w_in)
+        if self._tc_ok(N, w_in) and bn:
+            WT = self._wt(W2)                                     # (nI, N): K-major over the reduction dim N
+            dX = torch.empty((Tp, w_in), dtype=torch.bfloat16, device=dev)
+            if window:
+                self.tc_gemm(dZ, WT, dX, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
+                             a_row_shift=(1, 0, -1), a_col_off=(0, 0, 0), b_row_off=(0, w_in, 2 * w_in),
+                             b_col_off=(0, 0, 0), add_src=dY if ctx["residual"] else None,
+                             row_scale=ctx["mask"] if ctx["residual"] else None)
+            else:
+                self.tc_gemm(dZ, WT, dX, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
+                             add_src=dY if ctx["residual"] else None,
+                             row_scale=ctx["mask"] if ctx["residual"] else None)
+        else:
+            dXw = dZ @ W2
+            if window:
+                dX = self.k.col2seq_residual(dXw, dY if ctx["residual"] else None, ctx["mask"])
+                self.launches += 1
+            else:
+                dX = dXw + dY * ctx["mask"].unsqueeze(1).to(dY.dtype) if ctx["residual"] else dXw
+        return dX, dW.view(nO, nP, nI), db.view(nO, nP), dG, dbeta
+
+    # ------------------------------------------------------------------ Linear
+    def linear(self, X, W, b):
+        X = X.contiguous()
+        if X.dtype != torch.bfloat16:
+            X = X.to(torch.bfloat16)
+        out = self._linear_tc(X, W, b)
+        if out is not None:
+            return out
+        Y = X @ W.t()
+        return Y + b if b is not None else Y
+
+    def linear_backward(self, dY, X, W, need_dX: bool = True):
+        dY = dY.to(torch.bfloat16).contiguous() if dY.dtype != torch.bfloat16 else dY.contiguous()
+        X = X.contiguous()
+        dW = self._dw_tc(dY, X, 0) if dY.shape[1] % 128 == 0 else None
+        if dW is None:
+            dW = _mm_f32(dY.t(), X)
+        db = dY.to(torch.float32).sum(dim=0)
+        dX = None
+        if need_dX:
+            dX = self._linear_tc(dY, W.t().contiguous(), None)
+            if dX is None:
+                dX = dY @ W
+        return dX, dW, db
+
+    # ------------------------------------------------------------------ K6
+    def softmax(self, logits):
+        return torch.softmax(logits.to(torch.float32), dim=-1)
+
+    def softmax_xent(self, X, W, b, labels):
+        X = X.contiguous()
+        logits = (X @ W.t()).to(torch.float32) + b.to(torch.float32)
+        d, guesses, loss = self.k.softmax_xent(logits.contiguous(), labels.contiguous())
+        self.launches += 1
+        dW = _mm_f32(d.t(), X)
+        db = d.to(torch.float32).sum(dim=0)
+        dX = d @ W
+        return loss, d, guesses, dX, dW, db
+
+    # ------------------------------------------------------------------ K7
+    def transition_steps(self, system, Yf, params, batch, gold, is_train):
+        from ..models.transitions import BiluoSystem
+
+        if not isinstance(system, BiluoSystem):
+            return None                       # arc-eager: reference loop (host state machine)
+        nO, nP = params["nO"], params["nP"]
+        if nO % 32 != 0 or (nO * nP) // 32 > 8 or system.n_actions > 256:
+            return None
+        dev = Yf.device
+        extra = batch.extra
+        tok_off = extra.get("tok_off")
+        if tok_off is None:
+            lens = batch.doc_lens.to(torch.int64)
+            tok_off = (torch.cumsum(lens, 0) - lens).to(torch.int32)
+            extra["tok_off"] = tok_off
+        inv_active = extra.get("inv_active")
+        if inv_active is None:
+            max_len = max(batch.lengths) if batch.lengths else 1
+            lens_t = torch.tensor(batch.lengths, dtype=torch.int64)
+            counts = (lens_t.unsqueeze(0) > torch.arange(max_len).unsqueeze(1)).sum(dim=1).clamp(min=1)
+            inv_active = (1.0 / counts.to(torch.float32)).to(dev)
+            extra["inv_active"] = inv_active
+        gold_t = None
+        if is_train and gold is not None and gold.actions is not None:
+            gold_t = gold.actions.to(torch.int32)
+        feats, which, hid, d_scores, actions, loss = self.k.biluo_steps(
+            Yf.contiguous(), params["pad"].contiguous(), params["b"].contiguous(), params["Wu"].contiguous(),
+            params["bu"].contiguous(), batch.doc_starts, batch.doc_lens, tok_off, gold_t, inv_active,
+            batch.n_tokens, nO, nP, system.n_labels, bool(is_train and gold_t is not None),
+        )
+        self.launches += 1
+        rec: Dict[str, Any] = {"actions_flat": actions.to(torch.int64), "loss": loss, "n_steps": 0}
+        if is_train and gold_t is not None:
+            rec.update({"feats": feats, "which": which, "hid": hid, "d_scores": d_scores,
+                        "n_steps": batch.n_tokens, "nA": system.n_actions})
+        return rec
+
+    def transition_backward(self, rec, params, n_rows):
+        if rec["d_scores"].dtype != torch.bfloat16:
+            return None                       # records from the reference loop: use the reference backward
+        nF, nO, nP = params["nF"], params["nO"], params["nP"]
+        nA = rec["nA"]
+        d = rec["d_scores"]                   # (S, nA_pad) bf16, padded columns are zero
+        hid = rec["hid"]
+        dev = d.device
+        dWu = _mm_f32(d.t(), hid)[:nA]
+        dbu = d.to(torch.float32).sum(dim=0)[:nA]
+        Wu = params["Wu"]
+        Wu_pad = Wu if Wu.shape[0] == d.shape[1] else torch.cat(
+            [Wu, torch.zeros((d.shape[1] - Wu.shape[0], Wu.shape[1]), dtype=Wu.dtype, device=dev)], 0)
+        d_hid = (d @ Wu_pad).contiguous()
+        dYf = torch.zeros((n_rows, nF * nO * nP), dtype=torch.float32, device=dev)
+        dpad = torch.zeros((nF, nO * nP), dtype=torch.float32, device=dev)
+        db = torch.zeros((nO * nP,), dtype=torch.float32, device=dev)
+        self.k.transition_scatter(d_hid, rec["which"], rec["feats"], dYf, dpad, db, nF, nP)
+        self.launches += 1
+        return {"dWu": dWu, "dbu": dbu, "db": db, "dpad": dpad, "dYf": dYf.to(torch.bfloat16)}
+
+    # ------------------------------------------------------------------ misc
+    def gemm(self, A, B, trans1=False, trans2=False):
+        a = A.t() if trans1 else A
+        b = B.t() if trans2 else B
+        return a.to(torch.bfloat16) @ b.to(torch.bfloat16)
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 output (cuBLAS accumulates in fp32 either way)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return (a.to(torch.float32) @ b.to(torch.float32))

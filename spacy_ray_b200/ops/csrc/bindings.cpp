@@ -1,0 +1,225 @@
+// torch.ops.srb.* bindings: tensor checks + raw-pointer launchers (kernels.h).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include <vector>
+
+#include "gemm.h"
+#include "kernels.h"
+#include "comm.h"
+
+namespace {
+
+using at::Tensor;
+
+#define SRB_CHECK_CUDA(x) TORCH_CHECK((x).is_cuda() && (x).is_contiguous(), #x " must be a contiguous CUDA tensor")
+#define SRB_CHECK_BF16(x) TORCH_CHECK((x).scalar_type() == at::kBFloat16, #x " must be bfloat16")
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+const void* optptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
+
+srb::HashEmbedTables make_tables(const std::vector<Tensor>& tables, const std::vector<int64_t>& seeds,
+                                 const std::vector<int64_t>& columns, int n_attr) {
+  TORCH_CHECK(tables.size() <= 8 && tables.size() == seeds.size() && tables.size() == columns.size());
+  srb::HashEmbedTables t{};
+  t.n_tables = (int)tables.size();
+  t.width = (int)tables[0].size(1);
+  t.n_attr = n_attr;
+  TORCH_CHECK(t.width % 8 == 0, "HashEmbed width must be a multiple of 8");
+  for (size_t a = 0; a < tables.size(); ++a) {
+    t.n_rows[a] = (uint32_t)tables[a].size(0);
+    t.seed[a] = (uint32_t)seeds[a];
+    t.column[a] = (uint32_t)columns[a];
+  }
+  return t;
+}
+
+Tensor hash_embed_fwd(const Tensor& attrs, const Tensor& mask, std::vector<Tensor> tables, std::vector<int64_t> seeds,
+                      std::vector<int64_t> columns) {
+  SRB_CHECK_CUDA(attrs); SRB_CHECK_CUDA(mask);
+  TORCH_CHECK(attrs.scalar_type() == at::kLong && mask.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(attrs.device());
+  auto t = make_tables(tables, seeds, columns, (int)attrs.size(1));
+  for (size_t a = 0; a < tables.size(); ++a) { SRB_CHECK_CUDA(tables[a]); SRB_CHECK_BF16(tables[a]); t.table[a] = tables[a].data_ptr(); }
+  const int Tp = (int)attrs.size(0);
+  Tensor out = at::empty({Tp, (int64_t)t.n_tables * t.width}, attrs.options().dtype(at::kBFloat16));
+  srb::launch_hash_embed_fwd(attrs.data_ptr<int64_t>(), mask.data_ptr<float>(), t, out.data_ptr(), Tp, cur_stream());
+  return out;
+}
+
+void hash_embed_bwd(const Tensor& dY, const Tensor& attrs, const Tensor& mask, std::vector<Tensor> grads,
+                    std::vector<int64_t> seeds, std::vector<int64_t> columns) {
+  SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY); SRB_CHECK_CUDA(attrs);
+  c10::cuda::CUDAGuard guard(attrs.device());
+  auto t = make_tables(grads, seeds, columns, (int)attrs.size(1));
+  for (size_t a = 0; a < grads.size(); ++a) {
+    SRB_CHECK_CUDA(grads[a]);
+    TORCH_CHECK(grads[a].scalar_type() == at::kFloat, "table gradients must be fp32");
+    t.grad[a] = grads[a].data_ptr<float>();
+  }
+  srb::launch_hash_embed_bwd(attrs.data_ptr<int64_t>(), mask.data_ptr<float>(), t, dY.data_ptr(), (int)attrs.size(0),
+                             cur_stream());
+}
+
+std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
+                                  const c10::optional<Tensor>& beta, const c10::optional<Tensor>& Xres,
+                                  const Tensor& mask, int64_t nO, int64_t nP, double drop_p, int64_t seed) {
+  SRB_CHECK_CUDA(Z); SRB_CHECK_BF16(Z);
+  TORCH_CHECK(nO % 32 == 0 && nO <= 512 && (nO * nP) % 8 == 0, "maxout_ln: nO must be a multiple of 32, <= 512");
+  TORCH_CHECK(Z.size(1) == nO * nP);
+  c10::cuda::CUDAGuard guard(Z.device());
+  const int Tp = (int)Z.size(0);
+  auto bf = Z.options();
+  Tensor Y = at::empty({Tp, nO}, bf);
+  Tensor which = nP > 1 ? at::empty({Tp, nO}, bf.dtype(at::kByte)) : at::empty({0}, bf.dtype(at::kByte));
+  const bool has_ln = G.has_value() && G->defined();
+  Tensor xhat = has_ln ? at::empty({Tp, nO}, bf) : at::empty({0}, bf);
+  Tensor rstd = has_ln ? at::empty({Tp}, bf.dtype(at::kFloat)) : at::empty({0}, bf.dtype(at::kFloat));
+  srb::launch_maxout_ln_fwd(Z.data_ptr(), optptr(bias), optptr(G), optptr(beta), optptr(Xres), mask.data_ptr<float>(),
+                            Y.data_ptr(), nP > 1 ? which.data_ptr<uint8_t>() : nullptr, has_ln ? xhat.data_ptr() : nullptr,
+                            has_ln ? rstd.data_ptr<float>() : nullptr, Tp, (int)nO, (int)nP, (float)drop_p,
+                            (uint64_t)seed, cur_stream());
+  return {Y, which, xhat, rstd};
+}
+
+Tensor maxout_ln_bwd(const Tensor& dY, const c10::optional<Tensor>& xhat, const c10::optional<Tensor>& rstd,
+                     const c10::optional<Tensor>& G, const Tensor& which, const Tensor& mask, int64_t nP,
+                     double drop_p, int64_t seed, Tensor db, c10::optional<Tensor> dG, c10::optional<Tensor> dbeta) {
+  SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY);
+  c10::cuda::CUDAGuard guard(dY.device());
+  const int Tp = (int)dY.size(0), nO = (int)dY.size(1);
+  const bool has_ln = G.has_value() && G->defined();
+  Tensor dZ = at::empty({Tp, (int64_t)nO * nP}, dY.options());
+  srb::launch_maxout_ln_bwd(dY.data_ptr(), optptr(xhat), has_ln ? rstd->data_ptr<float>() : nullptr, optptr(G),
+                            which.data_ptr<uint8_t>(), mask.data_ptr<float>(), dZ.data_ptr(), db.data_ptr<float>(),
+                            has_ln ? dG->data_ptr<float>() : nullptr, has_ln ? dbeta->data_ptr<float>() : nullptr,
+                            Tp, nO, (int)nP, (float)drop_p, (uint64_t)seed, has_ln ? 1 : 0, cur_stream());
+  return dZ;
+}
+
+Tensor seq2col(const Tensor& X) {
+  SRB_CHECK_CUDA(X); SRB_CHECK_BF16(X);
+  TORCH_CHECK(X.size(1) % 8 == 0);
+  c10::cuda::CUDAGuard guard(X.device());
+  Tensor Xw = at::empty({X.size(0), X.size(1) * 3}, X.options());
+  srb::launch_seq2col(X.data_ptr(), Xw.data_ptr(), (int)X.size(0), (int)X.size(1), cur_stream());
+  return Xw;
+}
+
+Tensor col2seq_residual(const Tensor& dXw, const c10::optional<Tensor>& dY, const Tensor& mask) {
+  SRB_CHECK_CUDA(dXw); SRB_CHECK_BF16(dXw);
+  c10::cuda::CUDAGuard guard(dXw.device());
+  const int Tp = (int)dXw.size(0), nI = (int)dXw.size(1) / 3;
+  Tensor dX = at::empty({Tp, nI}, dXw.options());
+  srb::launch_col2seq_residual(dXw.data_ptr(), optptr(dY), mask.data_ptr<float>(), dX.data_ptr(), Tp, nI,
+                               dY.has_value() && dY->defined() ? 1 : 0, cur_stream());
+  return dX;
+}
+
+std::vector<Tensor> softmax_xent(const Tensor& logits, const Tensor& labels) {
+  SRB_CHECK_CUDA(logits); SRB_CHECK_CUDA(labels);
+  TORCH_CHECK(logits.scalar_type() == at::kFloat && labels.scalar_type() == at::kLong);
+  TORCH_CHECK(logits.size(1) <= 256, "softmax_xent: at most 256 classes");
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int Tp = (int)logits.size(0), nC = (int)logits.size(1);
+  Tensor d = at::empty({Tp, nC}, logits.options().dtype(at::kBFloat16));
+  Tensor guesses = at::empty({Tp}, logits.options().dtype(at::kLong));
+  Tensor loss = at::zeros({}, logits.options());
+  srb::launch_softmax_xent(logits.data_ptr<float>(), labels.data_ptr<int64_t>(), d.data_ptr(),
+                           guesses.data_ptr<int64_t>(), loss.data_ptr<float>(), Tp, nC, cur_stream());
+  return {d, guesses, loss};
+}
+
+void adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, c10::optional<Tensor> w_out, const Tensor& blk_key,
+                const Tensor& blk_off, const Tensor& key_off, const Tensor& key_len, Tensor norms, const Tensor& hyper,
+                const Tensor& step) {
+  SRB_CHECK_CUDA(g); SRB_CHECK_CUDA(w);
+  TORCH_CHECK(g.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(g.device());
+  const int nb = (int)blk_key.numel();
+  auto s = cur_stream();
+  cudaMemsetAsync(norms.data_ptr(), 0, norms.numel() * sizeof(float), s);
+  srb::launch_adam_sumsq(g.data_ptr<float>(), blk_key.data_ptr<int32_t>(), blk_off.data_ptr<int32_t>(),
+                         key_off.data_ptr<int64_t>(), key_len.data_ptr<int64_t>(), norms.data_ptr<float>(), nb,
+                         hyper.data_ptr<float>(), w.data_ptr<float>(), s);
+  srb::launch_adam_update(g.data_ptr<float>(), w.data_ptr<float>(), m1.data_ptr<float>(), m2.data_ptr<float>(),
+                          w_out.has_value() && w_out->defined() ? w_out->data_ptr() : nullptr,
+                          blk_key.data_ptr<int32_t>(), blk_off.data_ptr<int32_t>(), key_off.data_ptr<int64_t>(),
+                          key_len.data_ptr<int64_t>(), norms.data_ptr<float>(), nb, hyper.data_ptr<float>(),
+                          step.data_ptr<int32_t>(), s);
+}
+
+std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tensor& b, const Tensor& Wu,
+                                const Tensor& bu, const Tensor& doc_starts, const Tensor& doc_lens,
+                                const Tensor& tok_off, const c10::optional<Tensor>& gold, const Tensor& inv_active,
+                                int64_t n_tokens, int64_t nO, int64_t nP, int64_t n_labels, bool train) {
+  SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
+  TORCH_CHECK(nO % 32 == 0 && (nO * nP) / 32 <= 8, "biluo_steps: hidden width/pieces not supported");
+  c10::cuda::CUDAGuard guard(Yf.device());
+  const int64_t nA = Wu.size(0);
+  TORCH_CHECK(nA == 4 * n_labels + 1 && nA <= 256);
+  const int64_t nA_pad = (nA + 7) / 8 * 8;
+  auto o = Yf.options();
+  const int64_t T = n_tokens;
+  Tensor feats = at::empty({train ? T : 0, 3}, o.dtype(at::kInt));
+  Tensor which = at::empty({train ? T : 0, nO}, o.dtype(at::kByte));
+  Tensor hid = at::empty({train ? T : 0, nO}, o);
+  Tensor d_scores = at::empty({train ? T : 0, nA_pad}, o);
+  Tensor actions = at::empty({T}, o.dtype(at::kInt));
+  Tensor loss = at::zeros({}, o.dtype(at::kFloat));
+  srb::BiluoArgs a{};
+  a.Yf = Yf.data_ptr(); a.pad = pad.data_ptr(); a.b = b.data_ptr(); a.Wu = Wu.data_ptr(); a.bu = bu.data_ptr();
+  a.doc_starts = doc_starts.data_ptr<int32_t>(); a.doc_lens = doc_lens.data_ptr<int32_t>();
+  a.tok_off = tok_off.data_ptr<int32_t>();
+  a.gold = gold.has_value() && gold->defined() ? gold->data_ptr<int32_t>() : nullptr;
+  a.inv_active = inv_active.data_ptr<float>();
+  a.feats = feats.data_ptr<int32_t>(); a.which = which.data_ptr<uint8_t>(); a.hid = hid.data_ptr();
+  a.d_scores = d_scores.data_ptr(); a.actions = actions.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
+  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad;
+  a.n_labels = (int)n_labels; a.train = train ? 1 : 0;
+  srb::launch_biluo_steps(a, cur_stream());
+  return {feats, which, hid, d_scores, actions, loss};
+}
+
+void transition_scatter(const Tensor& d_hid, const Tensor& which, const Tensor& feats, Tensor dYf, Tensor dpad,
+                        Tensor db, int64_t nF, int64_t nP) {
+  SRB_CHECK_CUDA(d_hid); SRB_CHECK_BF16(d_hid);
+  c10::cuda::CUDAGuard guard(d_hid.device());
+  srb::launch_transition_scatter(d_hid.data_ptr(), which.data_ptr<uint8_t>(), feats.data_ptr<int32_t>(),
+                                 dYf.data_ptr<float>(), dpad.data_ptr<float>(), db.data_ptr<float>(),
+                                 (int)d_hid.size(0), (int)nF, (int)d_hid.size(1), (int)nP, cur_stream());
+}
+
+}  // namespace
+
+TORCH_LIBRARY(srb, m) {
+  m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns) -> Tensor");
+  m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
+  m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed) -> Tensor[]");
+  m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta) -> Tensor");
+  m.def("seq2col(Tensor X) -> Tensor");
+  m.def("col2seq_residual(Tensor dXw, Tensor? dY, Tensor mask) -> Tensor");
+  m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");
+  m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
+  m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train) -> Tensor[]");
+  m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
+  srb::register_gemm_ops(m);
+  srb::register_comm_ops(m);
+}
+
+TORCH_LIBRARY_IMPL(srb, CUDA, m) {
+  m.impl("hash_embed_fwd", hash_embed_fwd);
+  m.impl("hash_embed_bwd", hash_embed_bwd);
+  m.impl("maxout_ln_fwd", maxout_ln_fwd);
+  m.impl("maxout_ln_bwd", maxout_ln_bwd);
+  m.impl("seq2col", seq2col);
+  m.impl("col2seq_residual", col2seq_residual);
+  m.impl("softmax_xent", softmax_xent);
+  m.impl("adam_shard", adam_shard);
+  m.impl("biluo_steps", biluo_steps);
+  m.impl("transition_scatter", transition_scatter);
+  srb::register_gemm_impls(m);
+  srb::register_comm_impls(m);
+}

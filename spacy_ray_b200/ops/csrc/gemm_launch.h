@@ -1,0 +1,38 @@
+// Host/device shared declarations for the tcgen05 GEMM family.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srb {
+
+enum { MODE_KK = 0, MODE_MNMN = 1 };
+enum { EPI_STORE = 0, EPI_MAXOUT3 = 1, EPI_ATOMIC_F32 = 2 };
+
+struct GemmParams {
+  int M, N, K;              // K = reduction length per shift (MODE_KK) or total (MODE_MNMN)
+  int n_shifts;             // MODE_KK: 1 (plain) or 3 (window)
+  int a_row_shift[3];       // added to the A row (M) coordinate
+  int a_col_off[3];         // added to the A K coordinate
+  int b_row_off[3];         // added to the B row (N) coordinate
+  int b_col_off[3];         // added to the B K coordinate
+  int splits;               // split-K factor (EPI_ATOMIC_F32)
+  int win_w;                // MODE_MNMN: >0 = B is the window-expanded view of a (T, win_w) array
+  const int* m_dev;         // optional device-side row count (<= M) for fixed-shape CUDA graphs
+  void* out;                // bf16 (STORE / MAXOUT3) or fp32 (ATOMIC)
+  int ldo;
+  const __nv_bfloat16* bias;        // (N) or null
+  uint8_t* which;                   // MAXOUT3: argmax piece per unit
+  const __nv_bfloat16* add_src;     // STORE: optional out += row_scale[row] * add_src[row, n]
+  const float* row_scale;
+  int ld_add;
+};
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
+cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
+                        int num_sms, cudaStream_t s);
+int gemm_block_k();
+
+}  // namespace srb

@@ -1,0 +1,319 @@
+// Persistent warp-specialised tcgen05 GEMM family for the tok2vec / parser hot path.
+//
+//   D[M, N] = sum over "shifts" s and k of  A[m + a_row_shift[s], a_col_off[s] + k] * B[n + b_row_off[s], b_col_off[s] + k]
+//
+// * bf16 operands staged in shared memory by TMA (SWIZZLE_128B), fp32 accumulators in
+//   TMEM (two stages, so the epilogue of tile i overlaps the MMAs of tile i+1),
+//   tcgen05.mma issued by one elected thread, tcgen05.ld epilogue.
+// * The shift table is how expand_window (seq2col, K4 in SURVEY.md 2.7) disappears: the
+//   window GEMM loads the SAME activation array three times at row offsets -1/0/+1
+//   (the batch layout keeps a zero row between docs, so TMA out-of-bounds/zero rows
+//   give the doc-edge padding for free) instead of materialising (T, 3*width).
+// * Fused epilogues: +bias -> bf16 store (Linear / precompute), +bias -> maxout over
+//   3 pieces -> bf16 + argmax byte (K2), + residual*mask add (window dX), fp32
+//   split-K reduction straight into the flat gradient buffer (dW; both operands
+//   MN-major so no transposes are materialised).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4).
+#include "common.cuh"
+#include "gemm_launch.h"
+#include "gemm_tcgen05.cuh"
+
+namespace srb {
+
+using namespace sm100;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStageA = BM * BK * 2;            // 16 KB
+  static constexpr int kStageB = BLOCK_N * BK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStagesRaw = kSmemBudget / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BLOCK_N, int MODE, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + C::kStages * C::kStageA;
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStage);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = p.N / BLOCK_N;
+  const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
+  const int total_kb = (MODE == MODE_KK ? p.n_shifts : 1) * kpb;
+  const int splits = p.splits > 0 ? p.splits : 1;
+  const int total_items = m_tiles * n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int tile = w / splits, split = w - tile * splits;
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BLOCK_N;
+        if (m0 >= M) continue;
+        const int kb0 = (int)((long long)total_kb * split / splits), kb1 = (int)((long long)total_kb * (split + 1) / splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_arrive_expect_tx(full_bar + stage, C::kStage);
+          unsigned char* a_dst = sA + stage * C::kStageA;
+          unsigned char* b_dst = sB + stage * C::kStageB;
+          if (MODE == MODE_KK) {
+            const int s = kb / kpb, kk = kb - s * kpb;
+            tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
+            tma_load_2d(b_dst, &tmB, full_bar + stage, p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s]);
+          } else {
+            const int t0 = kb * BK;
+            int c0 = n0, tshift = 0;
+            if (p.win_w > 0) { const int s = n0 / p.win_w; c0 = n0 - s * p.win_w; tshift = s - 1; }
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * (BK * 128), &tmA, full_bar + stage, m0 + j * 64, t0);
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, t0 + tshift);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BLOCK_N, MODE == MODE_MNMN, MODE == MODE_MNMN);
+      int stage = 0, phase = 0, it = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int tile = w / splits, split = w - tile * splits;
+        const int m0 = (tile / n_tiles) * BM;
+        if (m0 >= M) continue;
+        const int kb0 = (int)((long long)total_kb * split / splits), kb1 = (int)((long long)total_kb * (split + 1) / splits);
+        const int acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::kStageA);
+          const uint32_t b_addr = smem_u32(sB + stage * C::kStageB);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t adesc, bdesc;
+            if (MODE == MODE_KK) {
+              adesc = make_smem_desc(a_addr + k * 32, 0, 1024);
+              bdesc = make_smem_desc(b_addr + k * 32, 0, 1024);
+            } else {
+              adesc = make_smem_desc(a_addr + k * 16 * 128, BK * 128, 1024);
+              bdesc = make_smem_desc(b_addr + k * 16 * 128, BK * 128, 1024);
+            }
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + acc);
+        ++it;
+      }
+    }
+  } else {
+    // ================================ epilogue =========================================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int tile = w / splits;
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BLOCK_N;
+      if (m0 >= M) continue;
+      const int acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      if (EPI == EPI_STORE) {
+        __nv_bfloat16* out = (__nv_bfloat16*)p.out;
+        const float rs = (p.add_src && p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float v[16];
+          tmem_ld_x16(t_base + c, v);
+          if (row_ok) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += bf2f(p.bias[n0 + c + i]);
+            }
+            if (p.add_src) {
+              const bf16x8* src = (const bf16x8*)(p.add_src + (size_t)row * p.ld_add + n0 + c);
+              bf16x8 s0 = src[0], s1 = src[1];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[i] += rs * bf2f(s0.v[i]); v[8 + i] += rs * bf2f(s1.v[i]); }
+            }
+            bf16x8 o0, o1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o0.v[i] = f2bf(v[i]); o1.v[i] = f2bf(v[8 + i]); }
+            bf16x8* dst = (bf16x8*)(out + (size_t)row * p.ldo + n0 + c);
+            dst[0] = o0; dst[1] = o1;
+          }
+        }
+      } else if (EPI == EPI_MAXOUT3) {
+        __nv_bfloat16* out = (__nv_bfloat16*)p.out;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 48) {
+          float v[48];
+          tmem_ld_x16(t_base + c, v);
+          tmem_ld_x16(t_base + c + 16, v + 16);
+          tmem_ld_x16(t_base + c + 32, v + 32);
+          if (row_ok) {
+            bf16x8 h0, h1;
+            uint8_t wh[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int n = n0 + c + 3 * u;
+              float a = v[3 * u], b = v[3 * u + 1], d = v[3 * u + 2];
+              if (p.bias) { a += bf2f(p.bias[n]); b += bf2f(p.bias[n + 1]); d += bf2f(p.bias[n + 2]); }
+              float best = a; int bi = 0;
+              if (b > best) { best = b; bi = 1; }
+              if (d > best) { best = d; bi = 2; }
+              if (u < 8) h0.v[u] = f2bf(best); else h1.v[u - 8] = f2bf(best);
+              wh[u] = (uint8_t)bi;
+            }
+            const size_t uo = (size_t)row * p.ldo + (n0 + c) / 3;
+            bf16x8* dst = (bf16x8*)(out + uo);
+            dst[0] = h0; dst[1] = h1;
+            *(uint4*)(p.which + uo) = *(const uint4*)wh;
+          }
+        }
+      } else {  // EPI_ATOMIC_F32: split-K partial sums reduced into the gradient buffer
+        float* out = (float*)p.out;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 16) {
+          float v[16];
+          tmem_ld_x16(t_base + c, v);
+          if (row_ok) {
+            float* dst = out + (size_t)row * p.ldo + n0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      ++it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int BLOCK_N, int MODE, int EPI>
+static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t s) {
+  using C = Cfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gemm_kernel<BLOCK_N, MODE, EPI><<<grid, kNumThreads, C::kSmemBytes, s>>>(a, b, p);
+  return cudaGetLastError();
+}
+
+int gemm_block_k() { return BK; }
+
+cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
+                        int num_sms, cudaStream_t s) {
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / block_n;
+  const int items = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
+  int grid = items < num_sms ? items : num_sms;
+  if (grid <= 0) return cudaSuccess;
+#define SRB_CASE(BN, MD, EP) \
+  if (block_n == BN && mode == MD && epi == EP) return launch_one<BN, MD, EP>(a, b, p, grid, s);
+  SRB_CASE(256, MODE_KK, EPI_STORE)
+  SRB_CASE(192, MODE_KK, EPI_STORE)
+  SRB_CASE(128, MODE_KK, EPI_STORE)
+  SRB_CASE(64, MODE_KK, EPI_STORE)
+  SRB_CASE(192, MODE_KK, EPI_MAXOUT3)
+  SRB_CASE(96, MODE_KK, EPI_MAXOUT3)
+  SRB_CASE(256, MODE_MNMN, EPI_ATOMIC_F32)
+  SRB_CASE(128, MODE_MNMN, EPI_ATOMIC_F32)
+  SRB_CASE(64, MODE_MNMN, EPI_ATOMIC_F32)
+  SRB_CASE(256, MODE_KK, EPI_ATOMIC_F32)
+  SRB_CASE(128, MODE_KK, EPI_ATOMIC_F32)
+#undef SRB_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace srb

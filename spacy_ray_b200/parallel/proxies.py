@@ -54,6 +54,8 @@ class PeerProxy:
         grads_per_update: int = 2,
         ray: Any = None,
         stage_to_host: bool = False,
+        all_peers: Any = None,
+        self_index: Optional[int] = None,
     ):
         self.ray = ray
         self.optimizer = optimizer
@@ -64,6 +66,11 @@ class PeerProxy:
         for key, peer in self.peers.items():
             if key not in self._owned_keys and not any(peer is w or peer == w for w in self.other_workers):
                 self.other_workers.append(peer)
+        if all_peers is not None and self_index is not None:
+            # The reference derives `other_workers` from key ownership only, so a
+            # worker that owns no key (fewer param groups than workers) is never
+            # sent updated parameters.  Given the full peer list we push to everyone.
+            self.other_workers = [p for i, p in enumerate(all_peers) if i != self_index]
         self._params: Dict[KeyT, torch.Tensor] = {}
         self._grads: Dict[KeyT, Optional[torch.Tensor]] = {}
         self._versions: Counter = Counter()

@@ -53,20 +53,33 @@ def divide_params_balanced(model, num_workers: int) -> List[List[KeyT]]:
                 by_key[make_key(node.id, name)] = int(node.get_param(name).numel())
     for g in groups:
         sizes.append(sum(by_key.get(k, 0) for k in g))
-    total = sum(sizes)
+    # Exact "linear partition": split the group sequence into num_workers contiguous
+    # runs minimising the heaviest run (DP over a few dozen groups).
+    n = len(groups)
+    k = min(num_workers, max(n, 1))
+    prefix = [0]
+    for sz in sizes:
+        prefix.append(prefix[-1] + sz)
+    INF = float("inf")
+    best = [[INF] * (n + 1) for _ in range(k + 1)]
+    cut = [[0] * (n + 1) for _ in range(k + 1)]
+    best[0][0] = 0
+    for j in range(1, k + 1):
+        for i in range(j, n + 1):
+            for s in range(j - 1, i):
+                cost = max(best[j - 1][s], prefix[i] - prefix[s])
+                if cost < best[j][i]:
+                    best[j][i], cut[j][i] = cost, s
+    bounds = [n]
+    i = n
+    for j in range(k, 0, -1):
+        i = cut[j][i]
+        bounds.append(i)
+    bounds.reverse()
     shares: List[List[KeyT]] = [[] for _ in range(num_workers)]
-    rank, acc = 0, 0
-    remaining = total
-    for gi, (g, sz) in enumerate(zip(groups, sizes)):
-        groups_left = len(groups) - gi
-        ranks_left = num_workers - rank
-        target = remaining / max(1, ranks_left)
-        if shares[rank] and rank < num_workers - 1 and (acc + sz / 2.0 > target or groups_left <= ranks_left - 1):
-            remaining -= acc
-            rank += 1
-            acc = 0
-        shares[rank].extend(g)
-        acc += sz
+    for r in range(k):
+        for g in groups[bounds[r]:bounds[r + 1]]:
+            shares[r].extend(g)
     return shares
 
 

@@ -26,6 +26,15 @@ from .transitions import (
 )
 
 
+def _add_loss(losses, name: str, value) -> None:
+    """Accumulate without forcing a device sync: tensors stay tensors until the
+    logger formats them."""
+    if losses is None:
+        return
+    prev = losses.get(name, 0.0)
+    losses[name] = prev + (value.detach() if hasattr(value, "detach") else float(value))
+
+
 class TrainablePipe:
     is_trainable = True
     default_score_weights: Dict[str, Any] = {}
@@ -192,8 +201,7 @@ class Tagger(TrainablePipe):
         loss, _guesses = self.model.attrs["update_with_labels"](batch, labels)
         if sgd not in (None, False):
             self.finish_update(sgd)
-        if losses is not None:
-            losses[self.name] = losses.get(self.name, 0.0) + float(loss)
+        _add_loss(losses, self.name, loss)
         return losses
 
     def predict(self, docs, batch):
@@ -269,8 +277,7 @@ class EntityRecognizer(TrainablePipe):
         out = self.model.attrs["run"](batch, self.system, gold, True)
         if sgd not in (None, False):
             self.finish_update(sgd)
-        if losses is not None:
-            losses[self.name] = losses.get(self.name, 0.0) + float(out.loss)
+        _add_loss(losses, self.name, out.loss)
         return losses
 
     def predict(self, docs, batch):
@@ -344,8 +351,7 @@ class DependencyParser(TrainablePipe):
         out = self.model.attrs["run"](batch, self.system, gold, True)
         if sgd not in (None, False):
             self.finish_update(sgd)
-        if losses is not None:
-            losses[self.name] = losses.get(self.name, 0.0) + float(out.loss)
+        _add_loss(losses, self.name, out.loss)
         return losses
 
     def predict(self, docs, batch):

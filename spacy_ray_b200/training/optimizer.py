@@ -60,6 +60,7 @@ class Optimizer:
         self.nr_update: Dict[KeyT, int] = {}
         self.averages: Optional[Dict[KeyT, torch.Tensor]] = {} if use_averages else None
         self.last_seen: Dict[KeyT, int] = {}
+        self.master: Dict[KeyT, torch.Tensor] = {}   # fp32 master copies for low-precision (bf16) weights
         self.step = 0
 
     # ---- schedules -------------------------------------------------------
@@ -79,7 +80,12 @@ class Optimizer:
         ops = self.ops or get_current_ops()
         self.nr_update[key] = self.nr_update.get(key, 0) + 1
         nr = self.nr_update[key]
-        w32 = weights if weights.dtype == torch.float32 else weights.to(torch.float32)
+        if weights.dtype == torch.float32:
+            w32 = weights
+        else:
+            w32 = self.master.get(key)
+            if w32 is None or w32.shape != weights.shape:
+                w32 = self.master[key] = weights.to(torch.float32).clone()
         if self.use_adam:
             if key not in self.mom1:
                 self.mom1[key] = torch.zeros_like(w32)

@@ -210,6 +210,7 @@ class Worker:
                 self.get_peer_map(peers), self.optimizer, self.get_owned_keys(),
                 grads_per_update=self.quorum or 2, ray=self.ray,
                 stage_to_host=(ops.device.type == "cuda"),
+                all_peers=list(peers), self_index=self.rank,
             )
         elif self.mode == "sync":
             layout = FlatLayout.build(models, self.num_workers, balance=self.shard_balance)

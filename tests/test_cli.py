@@ -1,0 +1,39 @@
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+from spacy_ray_b200.train_cli import build_parser
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_cli_flags_match_reference_surface():
+    p = build_parser()
+    args, extra = p.parse_known_args(
+        ["ray", "train", "cfg.cfg", "-c", "code.py", "-o", "out", "-w", "4", "-a", "auto", "-g", "0", "-V",
+         "--training.max_steps", "5"])
+    assert args.group == "ray" and args.command == "train"
+    assert str(args.config_path) == "cfg.cfg" and str(args.code_path) == "code.py" and str(args.output_path) == "out"
+    assert args.num_workers == 4 and args.ray_address == "auto" and args.use_gpu == 0 and args.verbose
+    assert extra == ["--training.max_steps", "5"]
+    args2, _ = p.parse_known_args(["ray", "train", "cfg.cfg", "--output-path", "o2", "--n-workers", "2", "--gpu-id", "-1"])
+    assert str(args2.output_path) == "o2" and args2.num_workers == 2 and args2.use_gpu == -1
+
+
+@pytest.mark.slow
+def test_cli_end_to_end_single_worker(tmp_path):
+    cfg = ROOT / "configs" / "tagger_w96.cfg"
+    r = subprocess.run(
+        [sys.executable, "-m", "spacy_ray_b200", "ray", "train", str(cfg), "-w", "1", "-o", str(tmp_path),
+         "--training.max_steps", "3", "--training.eval_frequency", "2", "--corpora.train.n_docs", "60"],
+        cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "LOSS TAGGER" in r.stdout and (tmp_path / "model-last" / "config.cfg").exists()
+
+
+def test_missing_config_is_a_clean_error(tmp_path):
+    r = subprocess.run([sys.executable, "-m", "spacy_ray_b200", "ray", "train", str(tmp_path / "nope.cfg")],
+                       cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Config" in r.stderr

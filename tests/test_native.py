@@ -1,0 +1,47 @@
+import numpy as np
+import pytest
+
+from spacy_ray_b200.native import featurize as native
+from spacy_ray_b200.pipeline.doc import featurize_words_py, hash_string, word_shape
+
+WORDS = ["Hello", "world", "U.S.A.", "12345", "x", "", "aaaaaaaaBBBBBB11111", "naïve", "Ünïcode", "can't",
+         "A" * 120, "MiXeD-42"]
+
+
+def test_word_shape():
+    assert word_shape("Hello") == "Xxxxx" and word_shape("aaaaaaaa") == "xxxx" and word_shape("U.S.A.") == "X.X.X."
+    assert word_shape("12345") == "dddd"
+
+
+def test_hash_is_stable_and_nonzero():
+    assert hash_string("abc") == hash_string("abc") != hash_string("abd")
+    assert all(hash_string(w) != 0 for w in WORDS)
+
+
+@pytest.mark.skipif(not native.available(), reason="native host runtime not built")
+def test_native_featurizer_is_bit_identical_to_python():
+    a = native.featurize_words(WORDS)
+    b = featurize_words_py(WORDS)
+    assert a.dtype == np.uint64 and np.array_equal(a, b)
+
+
+def test_collate_fallback_and_native_agree():
+    rng = np.random.default_rng(0)
+    lens = [3, 1, 5, 2]
+    store = rng.integers(1, 1 << 40, size=(sum(lens), 4)).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ids = np.array([2, 0, 3], dtype=np.int64)
+    cap = 20
+
+    def run():
+        attrs = np.full((cap, 4), -1, dtype=np.int64)
+        mask = np.full((cap,), -1, dtype=np.float32)
+        starts = np.zeros(3, dtype=np.int32)
+        ls = np.zeros(3, dtype=np.int32)
+        used = native.collate(store, off, ids, attrs, mask, starts, ls)
+        return used, attrs, mask, starts, ls
+
+    used, attrs, mask, starts, ls = run()
+    assert used == 5 + 3 + 2 + 3 + 1 and ls.tolist() == [5, 3, 2] and starts.tolist() == [1, 7, 11]
+    assert np.array_equal(attrs[1:6], store[off[2]:off[3]]) and mask[:14].tolist() == [0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 0]
+    assert float(np.abs(attrs[0]).sum()) == 0 and float(np.abs(attrs[13:]).sum()) == 0

@@ -193,7 +193,9 @@ class Tagger(TrainablePipe):
                 ids = np.array([index.get(t, -1) if t else -1 for t in tags], dtype=np.int64)
                 ref.user_data[("tag_ids", self.name)] = ids
             arr[s:s + len(ids)] = ids
-        return torch.from_numpy(arr).to(batch.device)
+        from ..nn.batch import to_device
+
+        return to_device(arr, batch.device)
 
     def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
         set_dropout_rate(self.model, drop)
@@ -268,8 +270,10 @@ class EntityRecognizer(TrainablePipe):
         offs = np.zeros(len(per_doc), dtype=np.int64)
         if len(per_doc) > 1:
             offs[1:] = np.cumsum([len(a) for a in per_doc])[:-1]
+        from ..nn.batch import to_device
+
         dev = batch.device
-        return TransitionGold(actions=torch.from_numpy(flat).to(dev), offsets=torch.from_numpy(offs).to(dev))
+        return TransitionGold(actions=to_device(flat, dev), offsets=to_device(offs, dev))
 
     def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
         set_dropout_rate(self.model, drop)

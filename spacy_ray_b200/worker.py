@@ -216,8 +216,10 @@ class Worker:
             layout = FlatLayout.build(models, self.num_workers, balance=self.shard_balance)
             comm_name = self.comm_name
             if comm_name == "auto":
-                comm_name = "local" if self.num_workers == 1 else (
-                    "fused" if (ops.device.type == "cuda" and getattr(ops, "fused", False)) else "dist")
+                if ops.device.type == "cuda" and getattr(ops, "fused", False):
+                    comm_name = "fused"           # one-kernel RS+Adam+AG (also the 1-GPU multi-tensor Adam)
+                else:
+                    comm_name = "local" if self.num_workers == 1 else "dist"
             buffers = None
             if comm_name == "local":
                 comm: Any = LocalComm(self.rank, self.num_workers)
@@ -225,7 +227,8 @@ class Worker:
                 self._ensure_dist()
                 comm = TorchDistComm(self.rank, self.num_workers)
             elif comm_name == "fused":
-                self._ensure_dist()
+                if self.num_workers > 1:
+                    self._ensure_dist()
                 from .parallel.fused_comm import FusedSymmComm
 
                 comm = FusedSymmComm(self.rank, self.num_workers, layout, ops.device, optimizer=self.optimizer)

@@ -1,0 +1,323 @@
+"""Numerics of every sm_100a kernel against the plain-PyTorch fp32 reference
+(``TorchOps``) of the same op.  Run on a B200: ``pytest -m gpu``."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from spacy_ray_b200.ops.b200_ops import B200Ops
+
+    return B200Ops("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from spacy_ray_b200.ops.torch_ops import TorchOps
+
+    return TorchOps("cuda:0", dtype=torch.float32)
+
+
+def _padded_batch(lens, w, dev="cuda:0", seed=0):
+    g = torch.Generator().manual_seed(seed)
+    rows = sum(lens) + len(lens) + 1
+    mask = torch.zeros(rows, 1)
+    r = 1
+    for n in lens:
+        mask[r:r + n] = 1
+        r += n + 1
+    X = torch.randn(rows, w, generator=g) * mask
+    return X.to(dev), mask.to(dev)
+
+
+def _close(a, b, rtol, atol, name=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = (err > tol).float().mean().item()
+    assert bad < 1e-3, f"{name}: {bad:.4%} elements out of tolerance, max err {err.max().item():.4g}"
+
+
+# ---------------------------------------------------------------------------- K1
+def test_hash_embed_fwd_bwd(ops, ref):
+    torch.manual_seed(0)
+    Tp, w = 301, 64
+    attrs = torch.randint(-(1 << 62), 1 << 62, (Tp, 4), dtype=torch.int64, device="cuda")
+    attrs[:, 0] = attrs[torch.randint(0, 20, (Tp,), device="cuda"), 0]      # heavy collisions
+    mask = (torch.rand(Tp, 1, device="cuda") > 0.1).float()
+    rows = [5000, 1000, 2500, 2500]
+    tables = [(torch.randn(n, w, device="cuda") * 0.1).bfloat16() for n in rows]
+    seeds, cols = [8, 9, 10, 11], [0, 1, 2, 3]
+    Y = ops.multi_hash_embed(attrs, mask, tables, seeds, cols)
+    Yr = ref.multi_hash_embed(attrs, mask, [t.float() for t in tables], seeds, cols)
+    _close(Y, Yr, 1e-2, 1e-2, "hash_embed_fwd")
+    assert float((Y.float() * (1 - mask)).abs().sum()) == 0.0
+    dY = torch.randn(Tp, 4 * w, device="cuda").bfloat16()
+    g = ops.multi_hash_embed_backward(dY, attrs, mask, rows, seeds, cols)
+    gr = ref.multi_hash_embed_backward(dY.float(), attrs, mask, rows, seeds, cols)
+    for a, b in zip(g, gr):
+        _close(a, b, 1e-3, 1e-3, "hash_embed_bwd")
+
+
+# ---------------------------------------------------------------------------- tcgen05 GEMMs
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 256, 256, 256), (1000, 768, 192, 192),
+                                      (257, 64, 128, 64), (4096, 384, 64, 128)])
+def test_tc_gemm_plain_nt(ops, M, N, K, bn):
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda").bfloat16()
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.tc_gemm(A, B, out, mode=0, epi=0, block_n=bn, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t() + bias.float()
+    _close(out, want, 2e-2, 2e-2 * math.sqrt(K), f"tc_gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("w,lens", [(64, (5, 1, 9, 30)), (256, tuple(range(3, 40)))])
+def test_tc_window_maxout_epilogue(ops, ref, w, lens):
+    torch.manual_seed(2)
+    X, mask = _padded_batch(lens, w)
+    Xb = X.bfloat16()
+    nO, nP = w, 3
+    W = (torch.randn(nO, nP, 3 * w, device="cuda") * 0.1).bfloat16()
+    b = (torch.randn(nO, nP, device="cuda") * 0.1).bfloat16()
+    Tp = X.shape[0]
+    H = torch.empty(Tp, nO, device="cuda", dtype=torch.bfloat16)
+    which = torch.empty(Tp, nO, device="cuda", dtype=torch.uint8)
+    ops.tc_gemm(Xb, W.reshape(nO * nP, 3 * w), H, mode=0, epi=1, block_n=192, M=Tp, N=nO * nP, K=w,
+                a_row_shift=(-1, 0, 1), a_col_off=(0, 0, 0), b_row_off=(0, 0, 0), b_col_off=(0, w, 2 * w),
+                bias=b.reshape(-1), which=which)
+    torch.cuda.synchronize()
+    Xw = ref.seq2col(Xb.float(), 1)
+    Z = (Xw @ W.float().reshape(nO * nP, 3 * w).t() + b.float().reshape(-1)).view(Tp, nO, nP)
+    Href, wref = Z.max(dim=2)
+    _close(H, Href, 2e-2, 5e-2, "window maxout H")
+    # argmax may legitimately differ where two pieces are within rounding of each other
+    top2 = Z.topk(2, dim=2).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05
+    assert (which.long()[clear] == wref[clear]).float().mean().item() > 0.999
+
+
+def test_tc_window_dx_with_residual(ops, ref):
+    torch.manual_seed(3)
+    w, N = 128, 384
+    dZ, mask = _padded_batch((7, 2, 33, 12), N)
+    dZb = dZ.bfloat16()
+    Tp = dZ.shape[0]
+    W2 = (torch.randn(N, 3 * w, device="cuda") * 0.1).bfloat16()
+    dY = (torch.randn(Tp, w, device="cuda")).bfloat16()
+    WT = W2.t().contiguous()
+    dX = torch.empty(Tp, w, device="cuda", dtype=torch.bfloat16)
+    ops.tc_gemm(dZb, WT, dX, mode=0, epi=0, block_n=128, M=Tp, N=w, K=N, a_row_shift=(1, 0, -1),
+                a_col_off=(0, 0, 0), b_row_off=(0, w, 2 * w), b_col_off=(0, 0, 0), add_src=dY,
+                row_scale=mask.reshape(-1))
+    torch.cuda.synchronize()
+    dXw = dZb.float() @ W2.float()
+    want = ref.backprop_seq2col(dXw, 1) + dY.float() * mask
+    _close(dX, want, 2e-2, 0.1, "window dX")
+
+
+@pytest.mark.parametrize("window", [0, 1])
+def test_tc_dw_mn_major_split_k(ops, ref, window):
+    torch.manual_seed(4)
+    w, N = 128, 384
+    X, mask = _padded_batch(tuple(range(2, 60)), w)
+    Xb = X.bfloat16()
+    Tp = X.shape[0]
+    dZ = (torch.randn(Tp, N, device="cuda") * mask).bfloat16()
+    Kt = w * (3 if window else 1)
+    out = torch.zeros(N, Kt, device="cuda", dtype=torch.float32)
+    got = ops._dw_tc(dZ, Xb, window, out)
+    torch.cuda.synchronize()
+    assert got is not None
+    Xw = ref.seq2col(Xb.float(), 1) if window else Xb.float()
+    want = dZ.float().t() @ Xw
+    _close(out, want, 2e-2, 2e-2 * math.sqrt(Tp), f"dW window={window}")
+
+
+# ---------------------------------------------------------------------------- fused blocks
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("window,residual,w", [(0, False, 64), (1, True, 64), (1, True, 256)])
+def test_maxout_block_fwd_bwd(ref, use_tc, window, residual, w):
+    from spacy_ray_b200.ops.b200_ops import B200Ops
+
+    ops = B200Ops("cuda:0", use_tc=use_tc)
+    torch.manual_seed(5)
+    nI = w if window else 4 * w
+    X, mask = _padded_batch((4, 9, 1, 17, 30), nI if not window else w)
+    nO, nP = w, 3
+    W = (torch.randn(nO, nP, nI * (3 if window else 1), device="cuda") * 0.08).bfloat16()
+    b = (torch.randn(nO, nP, device="cuda") * 0.1).bfloat16()
+    G = (torch.rand(nO, device="cuda") + 0.5).bfloat16()
+    beta = (torch.randn(nO, device="cuda") * 0.1).bfloat16()
+    if residual and X.shape[1] != nO:
+        pytest.skip("residual needs nI == nO")
+    Xb = X.bfloat16()
+    Y, ctx = ops.maxout_block(Xb, W, b, G, beta, mask, window=window, residual=residual, dropout=0.2,
+                              is_train=True, seed=11)
+    Yr, cr = ref.maxout_block(Xb.float(), W.float(), b.float(), G.float(), beta.float(), mask, window=window,
+                              residual=residual, dropout=0.2, is_train=True, seed=11)
+    _close(Y, Yr, 3e-2, 6e-2, "maxout_block fwd")
+    assert float((Y.float() * (1 - mask)).abs().sum()) == 0.0
+    dY = torch.randn_like(Yr).bfloat16()
+    dX, dW, db, dG, dbeta = ops.maxout_block_backward(dY, ctx)
+    # the reference backward must route through the same winners to be comparable
+    cr["which"] = ctx["which"]
+    dXr, dWr, dbr, dGr, dbetar = ref.maxout_block_backward(dY.float(), cr)
+    T = X.shape[0]
+    _close(dX, dXr, 5e-2, 0.15, "dX")
+    _close(dW, dWr, 5e-2, 0.05 * math.sqrt(T), "dW")
+    _close(db, dbr.reshape(-1).view_as(db), 5e-2, 0.05 * math.sqrt(T), "db")
+    _close(dG, dGr, 5e-2, 0.05 * math.sqrt(T), "dG")
+    _close(dbeta, dbetar, 5e-2, 0.05 * math.sqrt(T), "dbeta")
+
+
+def test_softmax_xent(ops, ref):
+    torch.manual_seed(6)
+    X = torch.randn(500, 64, device="cuda").bfloat16()
+    W = (torch.randn(17, 64, device="cuda") * 0.2).bfloat16()
+    b = (torch.randn(17, device="cuda") * 0.1).bfloat16()
+    labels = torch.randint(-1, 17, (500,), device="cuda")
+    loss, d, guesses, dX, dW, db = ops.softmax_xent(X, W, b, labels)
+    lr, dr, gr, dXr, dWr, dbr = ref.softmax_xent(X.float(), W.float(), b.float(), labels)
+    _close(d, dr, 2e-2, 1e-2, "d_logits")
+    assert abs(float(loss) - float(lr)) / float(lr) < 2e-2
+    assert (guesses == gr).float().mean().item() > 0.98
+    _close(dW, dWr, 3e-2, 0.3, "dW")
+
+
+def test_adam_shard_matches_reference(ops, ref):
+    torch.manual_seed(7)
+    lens = [128 * 3, 4096 + 128, 128, 128 * 70]
+    offs = [0]
+    for n in lens[:-1]:
+        offs.append(offs[-1] + n)
+    total = sum(lens)
+    g = torch.randn(total, device="cuda") * 3
+    w = torch.randn(total, device="cuda")
+    m1 = torch.zeros(total, device="cuda")
+    m2 = torch.zeros(total, device="cuda")
+    w_bf = torch.zeros(total, device="cuda", dtype=torch.bfloat16)
+    blk_key, blk_off = [], []
+    for k, n in enumerate(lens):
+        for c in range((n + 4095) // 4096):
+            blk_key.append(k)
+            blk_off.append(c)
+    dev = "cuda"
+    hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8, 1.0, 0.01, 1.0, 1.0], device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    wr, gr_, m1r, m2r = w.clone(), g.clone(), m1.clone(), m2.clone()
+    torch.ops.srb.adam_shard(g, w, m1, m2, w_bf, torch.tensor(blk_key, dtype=torch.int32, device=dev),
+                             torch.tensor(blk_off, dtype=torch.int32, device=dev),
+                             torch.tensor(offs, dtype=torch.int64, device=dev),
+                             torch.tensor(lens, dtype=torch.int64, device=dev),
+                             torch.zeros(len(lens), device=dev), hyper, step)
+    for o, n in zip(offs, lens):
+        ref.adam_step(wr[o:o + n], gr_[o:o + n], m1r[o:o + n], m2r[o:o + n], lr=0.01, beta1=0.9, beta2=0.999,
+                      eps=1e-8, nr_update=1, grad_clip=1.0, l2=0.01, l2_is_weight_decay=True)
+    _close(w, wr, 1e-4, 1e-5, "adam w")
+    _close(m2, m2r, 1e-4, 1e-7, "adam m2")
+    _close(w_bf, wr, 1e-2, 1e-2, "adam bf16 out")
+    assert float(g.abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------- K7
+def test_biluo_kernel_matches_reference_loop(ops, ref):
+    from spacy_ray_b200.models.transition_model import (
+        TransitionGold, _biluo_steps_reference, transition_backward,
+    )
+    from spacy_ray_b200.models.transitions import BiluoSystem, spans_to_biluo_actions
+    from spacy_ray_b200.nn.batch import make_token_batch
+    import numpy as np
+    import random
+
+    rng = random.Random(0)
+    torch.manual_seed(8)
+    L = 5
+    system = BiluoSystem([f"L{i}" for i in range(L)])
+    lens = [rng.randint(1, 30) for _ in range(67)]
+    batch = make_token_batch([np.ones((n, 4), dtype=np.uint64) for n in lens], "cuda:0")
+    golds = []
+    for n in lens:
+        spans, t = [], 0
+        while t < n:
+            if rng.random() < 0.3:
+                ln = min(n - t, rng.randint(1, 3))
+                spans.append((t, t + ln, rng.randint(0, L - 1)))
+                t += ln
+            t += 1
+        golds.append(spans_to_biluo_actions(n, spans))
+    flat = torch.tensor([a for g in golds for a in g], device="cuda")
+    offs = torch.tensor([sum(lens[:i]) for i in range(len(lens))], device="cuda")
+    gold = TransitionGold(actions=flat, offsets=offs)
+    nF, nO, nP = 3, 64, 2
+    Tp = batch.n_rows
+    Yf = (torch.randn(Tp, nF * nO * nP, device="cuda") * batch.mask).bfloat16()
+    params = {
+        "pad": (torch.randn(nF, nO * nP, device="cuda") * 0.3).bfloat16(),
+        "b": (torch.randn(nO * nP, device="cuda") * 0.3).bfloat16(),
+        "Wu": (torch.randn(system.n_actions, nO, device="cuda") * 0.3).bfloat16(),
+        "bu": (torch.randn(system.n_actions, device="cuda") * 0.1).bfloat16(),
+        "nF": nF, "nO": nO, "nP": nP,
+    }
+    rec = ops.transition_steps(system, Yf, params, batch, gold, True)
+    pf = {k: (v.float() if torch.is_tensor(v) else v) for k, v in params.items()}
+    rref = _biluo_steps_reference(system, Yf.float(), pf, batch, gold, True)
+    torch.cuda.synchronize()
+    agree = (rec["actions_flat"] == rref["actions_flat"]).float().mean().item()
+    assert agree > 0.97, agree          # bf16 hidden vs fp32 can flip near-ties, which then diverge
+    # teacher-forced comparison of loss/grad is not possible once trajectories diverge; compare on
+    # docs whose whole action sequence agrees
+    tok_doc = torch.repeat_interleave(torch.arange(len(lens), device="cuda"), torch.tensor(lens, device="cuda"))
+    same_tok = rec["actions_flat"] == rref["actions_flat"]
+    doc_ok = torch.ones(len(lens), dtype=torch.bool, device="cuda")
+    doc_ok.scatter_reduce_(0, tok_doc, same_tok, reduce="amin")
+    assert doc_ok.float().mean().item() > 0.8
+    # reference records are ordered step-major; rebuild a per-token view of d_scores from the kernel's
+    # records and check that it is a valid gradient: rows sum to ~0 and are zero for docs w/o gold
+    d = rec["d_scores"].float()[:, : system.n_actions]
+    assert d.shape[0] == sum(lens)
+    assert float(d.sum(dim=1).abs().max()) < 2e-2
+    # loss of the agreeing docs must match the reference contribution closely overall
+    assert abs(float(rec["loss"]) - float(rref["loss"])) / max(float(rref["loss"]), 1e-6) < 0.25
+    # backward scatter vs reference backward on the kernel's own records
+    g = ops.transition_backward(rec, params, Tp)
+    rec_f = {"d_scores": d, "hid": rec["hid"].float(), "which": rec["which"], "feats": rec["feats"].long()}
+    gr = transition_backward(ref, rec_f, pf, Tp)
+    _close(g["dYf"], gr["dYf"], 3e-2, 2e-2, "dYf")
+    _close(g["dpad"], gr["dpad"], 3e-2, 5e-2, "dpad")
+    _close(g["db"], gr["db"], 3e-2, 5e-2, "db")
+    _close(g["dWu"], gr["dWu"], 3e-2, 5e-2, "dWu")
+
+
+# ---------------------------------------------------------------------------- end to end
+def test_gpu_training_loss_goes_down_and_uses_native_kernels():
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.worker import Worker
+
+    cfg = Config().from_str(multi_cfg(["ner"], width=64, depth=2, n_docs=400, max_len=16, hidden=64), interpolate=False)
+    w = Worker(cfg, rank=0, num_workers=1, use_gpu=0, mode="sync", comm="auto")
+    w.set_proxy(None)
+    assert w.proxy.comm.name == "fused"
+    nlp = w.nlp
+    ops = nlp.get_pipe("ner").model.ops
+    assert ops.name == "b200"
+    exs = list(w.train_corpus(nlp))
+    hist = []
+    for step in range(60):
+        losses = {}
+        lo = (step * 64) % (len(exs) - 64)
+        nlp.update(exs[lo:lo + 64], drop=0.1, sgd=False, losses=losses)
+        w.proxy.step()
+        hist.append(float(losses["ner"]))
+    w.proxy.comm.check()
+    assert ops.launches > 0 and w.proxy.comm.launches == 60
+    assert sum(hist[-5:]) < 0.5 * sum(hist[:5]), hist[::6]
+    scores = nlp.evaluate(exs[:100])
+    assert scores["ents_f"] > 0.3, scores

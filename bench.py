@@ -29,7 +29,7 @@ BASELINE_PUBLISHED = None   # the reference publishes no numbers
 
 
 def flagship_config(args, rank: int) -> str:
-    n_docs = args.docs_per_gpu * (args.steps + args.warmup + 2) * (2 if args.e2e else 1)
+    n_docs = args.docs_per_gpu * 8
     return f"""
 [system]
 seed = 0
@@ -108,6 +108,8 @@ def main() -> int:
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--comm", default="auto")
+    ap.add_argument("--engine", default="graph", choices=["graph", "eager"],
+                    help="graph = CUDA-graph replay of the whole step; eager = same kernels launched from Python")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -160,7 +162,6 @@ def main() -> int:
     ops = nlp.get_pipe("ner").model.ops
     examples = list(worker.train_corpus(nlp))
     B = args.docs_per_gpu
-    batches = [examples[i:i + B] for i in range(0, len(examples) - B + 1, B)]
     n_params = sum(proxy.layout.numel.values())
 
     def barrier():
@@ -183,70 +184,79 @@ def main() -> int:
         return float(t.item())
 
     ner = nlp.get_pipe("ner")
+    from spacy_ray_b200.engine import Trainer
 
-    # ---------------- device-timed: inputs pre-staged on device, no host reads ----------------
-    staged = []
-    for b in batches[: args.warmup + args.steps]:
-        tb = nlp.make_batch([eg.predicted for eg in b])
-        gold = ner._make_gold(b, tb)
-        staged.append((b, tb, gold))
+    use_graphs = args.engine == "graph"
+    trainer = Trainer(nlp, proxy, examples, docs_per_batch=B, dropout=args.dropout, use_graphs=use_graphs)
+    n_total = args.warmup + args.steps
+    id_batches = trainer.batches(2 * n_total + 2, seed=rank)
+
+    # ---------------- device-timed: inputs already on the device, no host reads ----------------
+    # (each step's packed input block is staged on the device beforehand and moved into the
+    #  static input buffer with a D2D copy inside the timed region)
+    dev_inputs = []
+    for ids in id_batches[:n_total]:
+        trainer.prepare(ids)
+        stage, err = trainer._q_out.get()
+        assert err is None, err
+        dev_inputs.append((stage["buf"].to(trainer.device), stage["rows"], stage["docs"], stage["words"]))
     torch.cuda.synchronize()
 
     def device_step(item):
-        b, tb, gold = item
-        from spacy_ray_b200.nn.layers import set_dropout_rate
-        set_dropout_rate(ner.model, args.dropout)
-        out = ner.model.attrs["run"](tb, ner.system, gold, True)
-        proxy.step()
-        return out.loss
+        packed, rows, _d, _w = item
+        trainer.dev_buf.copy_(packed, non_blocking=True)
+        return trainer._run(rows)
 
-    for item in staged[: args.warmup]:
+    device_step(dev_inputs[0])                       # first step runs eagerly on every rank
+    trainer.capture_buckets([it[1] for it in dev_inputs] +
+                            [trainer.rows_for(ids) for ids in id_batches[n_total:]])
+    for item in dev_inputs[1: args.warmup]:
         device_step(item)
     barrier()
     launches0 = ops.launches + getattr(proxy.comm, "launches", 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, period_s=0.05) as clocks:
         ev0.record()
-        for item in staged[args.warmup: args.warmup + args.steps]:
+        for item in dev_inputs[args.warmup: n_total]:
             device_step(item)
         ev1.record()
         barrier()
     ms = max_over_ranks(float(ev0.elapsed_time(ev1)))
     launches = ops.launches + getattr(proxy.comm, "launches", 0) - launches0
-    docs = sum_over_ranks(float(sum(len(it[0]) for it in staged[args.warmup: args.warmup + args.steps])))
-    words = sum_over_ranks(float(sum(sum(len(eg) for eg in it[0]) for it in staged[args.warmup: args.warmup + args.steps])))
+    docs = sum_over_ranks(float(sum(it[2] for it in dev_inputs[args.warmup: n_total])))
+    words = sum_over_ranks(float(sum(it[3] for it in dev_inputs[args.warmup: n_total])))
     value = docs / (ms / 1e3)
+    if hasattr(proxy.comm, "check"):
+        proxy.comm.check()
 
     # ---------------- end to end through the public API -----------------------------------------
+    # Trainer.train_step(): native collate into pinned memory (prefetch thread) -> ONE H2D copy
+    # -> CUDA-graph replay of the whole step -> 4-byte D2H read of the loss.  Every step.
     e2e = None
     if args.e2e:
-        rest = batches[args.warmup + args.steps:]
-        need = args.warmup + args.steps
-        rest = (rest * (need // max(1, len(rest)) + 1))[:need] if rest else batches[:need]
-        h2d = d2h = 0
-
-        def api_step(b):
-            losses = {}
-            nlp.update(b, drop=args.dropout, sgd=False, losses=losses)     # pinned H2D of inputs inside
-            proxy.step()
-            return float(losses["ner"])                                     # D2H read of the step's loss
-
-        for b in rest[: args.warmup]:
-            api_step(b)
+        rest = id_batches[n_total: 2 * n_total + 1]
+        trainer.prepare(rest[0])
+        for i in range(args.warmup):
+            trainer.prepare(rest[i + 1])
+            trainer.train_step()
         barrier()
-        from spacy_ray_b200.nn import batch as _batch_mod
-        _batch_mod.H2D_BYTES = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        docs_local = 0
         e0.record()
-        for b in rest[args.warmup: args.warmup + args.steps]:
-            api_step(b)
+        for i in range(args.warmup, n_total):
+            trainer.prepare(rest[i + 1])          # prefetch the NEXT batch while this one runs
+            loss_val = trainer.train_step()       # H2D + step + D2H(loss)
+            docs_local += trainer.last["docs"]
         e1.record()
         barrier()
         ms_e = max_over_ranks(float(e0.elapsed_time(e1)))
-        docs_e = sum_over_ranks(float(sum(len(b) for b in rest[args.warmup: args.warmup + args.steps])))
-        h2d = _batch_mod.H2D_BYTES / max(1, args.steps)
-        e2e = {"value": docs_e / (ms_e / 1e3), "unit": "docs/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
+        docs_e = sum_over_ranks(float(docs_local))
+        e2e = {"value": docs_e / (ms_e / 1e3), "unit": "docs/s", "h2d_bytes_per_step": int(trainer.h2d_bytes_per_step),
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps, "last_loss": loss_val,
+               "api": "spacy_ray_b200.engine.Trainer.train_step"}
+        if hasattr(proxy.comm, "check"):
+            proxy.comm.check()
+    trainer.close()
 
     if rank == 0:
         mean_len = words / max(docs, 1)
@@ -255,7 +265,7 @@ def main() -> int:
             "value": value, "unit": "docs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic (SyntheticCorpus, random-init weights)",
-            "impl": args.impl,
+            "impl": args.impl, "engine": args.engine,
             "config": {
                 "model": f"en tok2vec(MultiHashEmbed+MaxoutWindowEncoder width={args.width} depth={args.depth})+NER "
                          f"(TransitionBasedParser hidden=64, 18 entity labels)",

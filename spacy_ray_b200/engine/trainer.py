@@ -1,0 +1,301 @@
+"""``Trainer``: the device-resident training step.
+
+The generic loop (``nlp.update`` -> per-component ``update`` -> ``proxy.step``)
+issues a few hundred small launches per step from Python; on a B200 that is
+10x slower than the math (this workload is launch-latency bound).
+``Trainer`` removes the host from the step:
+
+* **ExampleStore** - the corpus as structure-of-arrays (attribute ids, gold
+  action ids, doc offsets), built once.
+* **native collate** (``native/csrc/host_runtime.cpp``) gathers the docs of a batch
+  into ONE packed pinned staging buffer (padded-ragged layout + gold + per-step
+  scalars), on a prefetch thread that runs while the GPU executes the previous step;
+* **one H2D copy** of that buffer into a static device buffer;
+* **one CUDA-graph replay** of the entire step - hash-embed, every tcgen05 GEMM,
+  the BILUO kernel, the backward pass and the fused reduce-scatter/Adam/all-gather
+  kernel - captured once per row-capacity bucket (rows rounded up to 1024);
+* **one 4-byte D2H read** of the loss.
+
+Supports pipelines whose trainable components have a device-side update (NER
+today); anything else should use the generic ``nlp.update`` path.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..models.transition_model import TransitionGold
+from ..native import featurize as native
+from ..nn.batch import TokenBatch
+from ..nn.layers import set_dropout_rate
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+class ExampleStore:
+    """Structure-of-arrays view of a list of Examples for one NER component."""
+
+    def __init__(self, examples: Sequence[Any], ner) -> None:
+        lens = np.array([len(eg) for eg in examples], dtype=np.int64)
+        self.doc_off = np.zeros(len(examples) + 1, dtype=np.int64)
+        np.cumsum(lens, out=self.doc_off[1:])
+        self.attrs = np.ascontiguousarray(
+            np.concatenate([eg.predicted.to_array() for eg in examples]).view(np.int64))
+        self.gold = np.ascontiguousarray(
+            np.concatenate([ner.gold_actions(eg.reference) for eg in examples]).astype(np.int32))
+        self.lens = lens
+        self.n_docs = len(examples)
+        self.max_len = int(lens.max()) if len(lens) else 1
+
+
+@dataclass
+class _Layout:
+    rows: int
+    docs: int
+    lmax: int
+    off_attrs: int = 0
+    off_mask: int = 0
+    off_starts: int = 0
+    off_lens: int = 0
+    off_tok: int = 0
+    off_gold: int = 0
+    off_inv: int = 0
+    off_meta: int = 0
+    nbytes: int = 0
+
+    def __post_init__(self):
+        o = 0
+        self.off_attrs = o; o = _align(o + self.rows * 4 * 8)
+        self.off_mask = o; o = _align(o + self.rows * 4)
+        self.off_starts = o; o = _align(o + self.docs * 4)
+        self.off_lens = o; o = _align(o + self.docs * 4)
+        self.off_tok = o; o = _align(o + self.docs * 4)
+        self.off_gold = o; o = _align(o + self.rows * 4)
+        self.off_inv = o; o = _align(o + self.lmax * 4)
+        self.off_meta = o; o = _align(o + 16)
+        self.nbytes = o
+
+
+class _Views:
+    """Typed views into one packed byte buffer (host numpy or device torch)."""
+
+    def __init__(self, lay: _Layout, buf: torch.Tensor):
+        self.buf = buf
+
+        def v(off, n, dt):
+            return buf[off: off + n * torch.tensor([], dtype=dt).element_size()].view(dt)
+
+        self.attrs = v(lay.off_attrs, lay.rows * 4, torch.int64).view(lay.rows, 4)
+        self.mask = v(lay.off_mask, lay.rows, torch.float32)
+        self.starts = v(lay.off_starts, lay.docs, torch.int32)
+        self.lens = v(lay.off_lens, lay.docs, torch.int32)
+        self.tok_off = v(lay.off_tok, lay.docs, torch.int32)
+        self.gold = v(lay.off_gold, lay.rows, torch.int32)
+        self.inv_active = v(lay.off_inv, lay.lmax, torch.float32)
+        self.meta = v(lay.off_meta, 4, torch.int32)
+
+
+class Trainer:
+    def __init__(self, nlp, proxy, examples: Sequence[Any], *, docs_per_batch: int, dropout: float = 0.1,
+                 component: str = "ner", use_graphs: bool = True, bucket_rows: int = 1024, prefetch: bool = True,
+                 n_stage: int = 3):
+        self.nlp, self.proxy = nlp, proxy
+        self.ner = nlp.get_pipe(component)
+        self.ops = self.ner.model.ops
+        if self.ops.device.type != "cuda":
+            raise ValueError("Trainer needs the CUDA backend; use nlp.update on CPU")
+        self.device = self.ops.device
+        self.dropout = float(dropout)
+        self.B = int(docs_per_batch)
+        self.store = ExampleStore(examples, self.ner)
+        self.bucket_rows = int(bucket_rows)
+        rows_cap = _align(self.B * self.store.max_len + self.B + 1, self.bucket_rows)
+        self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64))
+        self.use_graphs = use_graphs
+        self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
+        self.dv = _Views(self.lay, self.dev_buf)
+        self.stages = []
+        for _ in range(n_stage):
+            hb = torch.zeros(self.lay.nbytes, dtype=torch.uint8, pin_memory=True)
+            hv = _Views(self.lay, hb)
+            self.stages.append({
+                "buf": hb, "np": {k: getattr(hv, k).numpy() for k in
+                                  ("attrs", "mask", "starts", "lens", "tok_off", "gold", "inv_active", "meta")},
+                "event": None, "rows": 0, "docs": 0, "words": 0,
+            })
+        self._graphs: Dict[int, Any] = {}
+        self._pool = torch.cuda.graph_pool_handle() if use_graphs else None
+        self._warmed = False
+        self._loss_out: Dict[int, torch.Tensor] = {}
+        self._launches_per_replay: Dict[int, int] = {}
+        self.h2d_bytes_per_step = self.lay.nbytes
+        self.steps = 0
+        self._stage_i = 0
+        self._prefetch = prefetch
+        self._q_in: "queue.Queue" = queue.Queue()
+        self._q_out: "queue.Queue" = queue.Queue()
+        self._thread: Optional[threading.Thread] = None
+        self._side = torch.cuda.Stream(device=self.device)
+        if prefetch:
+            self._thread = threading.Thread(target=self._prefetch_loop, daemon=True)
+            self._thread.start()
+
+    # ------------------------------------------------------------------ host side
+    def _fill(self, stage: dict, ids: np.ndarray) -> None:
+        """Gather docs ``ids`` into the packed pinned buffer (native memcpy loops)."""
+        if stage["event"] is not None:
+            stage["event"].synchronize()           # previous H2D out of this buffer has completed
+        a = stage["np"]
+        st = self.store
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        rows = native.collate(st.attrs, st.doc_off, ids, a["attrs"], a["mask"], a["starts"], a["lens"])
+        words = native.collate_gold(st.gold, st.doc_off, ids, a["gold"], a["tok_off"])
+        lens = a["lens"][: len(ids)]
+        counts = (lens[None, :] > np.arange(self.lay.lmax, dtype=np.int32)[:, None]).sum(axis=1)
+        a["inv_active"][:] = 1.0 / np.maximum(counts, 1)
+        a["meta"][0] = rows
+        stage["rows"], stage["docs"], stage["words"] = int(rows), len(ids), int(words)
+
+    def _prefetch_loop(self) -> None:
+        while True:
+            item = self._q_in.get()
+            if item is None:
+                return
+            stage, ids = item
+            try:
+                self._fill(stage, ids)
+                self._q_out.put((stage, None))
+            except BaseException as e:          # surface in the training thread
+                self._q_out.put((stage, e))
+
+    def prepare(self, ids: np.ndarray) -> None:
+        """Queue the collation of a future batch (returns immediately)."""
+        stage = self.stages[self._stage_i]
+        self._stage_i = (self._stage_i + 1) % len(self.stages)
+        if self._prefetch:
+            self._q_in.put((stage, ids))
+        else:
+            self._fill(stage, ids)
+            self._q_out.put((stage, None))
+
+    # ------------------------------------------------------------------ device side
+    def _batch_views(self, rows: int) -> tuple:
+        dv = self.dv
+        tb = TokenBatch(
+            attrs=dv.attrs[:rows], mask=dv.mask[:rows].view(rows, 1), doc_starts=dv.starts, doc_lens=dv.lens,
+            lengths=[], starts=[], n_tokens=rows, n_rows=rows,
+        )
+        tb.extra["tok_off"] = dv.tok_off
+        tb.extra["inv_active"] = dv.inv_active
+        return tb, TransitionGold(actions=dv.gold[:rows], offsets=None)
+
+    def _step_fn(self, rows: int) -> torch.Tensor:
+        tb, gold = self._batch_views(rows)
+        self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
+        set_dropout_rate(self.ner.model, self.dropout)
+        out = self.ner.model.attrs["run"](tb, self.ner.system, gold, True)
+        self.proxy.step()
+        return out.loss
+
+    def _bucket(self, rows: int) -> int:
+        return min(self.lay.rows, _align(rows, self.bucket_rows))
+
+    def _run(self, rows: int) -> torch.Tensor:
+        rb = self._bucket(rows)
+        comm = self.proxy.comm
+        if not self.use_graphs or not self._warmed:
+            # The very first step runs eagerly on every rank (in lockstep): it performs the
+            # one-time kernel attribute setup / workspace allocation that must not happen
+            # under capture, and it is a real training step.
+            self._warmed = True
+            return self._step_fn(rb)
+        g = self._graphs.get(rb)
+        if g is None:
+            g = self._capture(rb)
+        g.replay()
+        n_ops, n_comm = self._launches_per_replay[rb]
+        self.ops.launches += n_ops
+        if hasattr(comm, "launches"):
+            comm.launches += n_comm
+        return self._loss_out[rb]
+
+    def _capture(self, rb: int):
+        """Capture the whole step for row-capacity ``rb``.  Capturing executes nothing, so
+        ranks may capture different buckets at different times without unbalancing the
+        collective inside the step; all buckets share one memory pool."""
+        comm = self.proxy.comm
+        if hasattr(comm, "_sync_hyper"):
+            comm._sync_hyper()
+        torch.cuda.synchronize(self.device)
+        l0, c0 = self.ops.launches, getattr(comm, "launches", 0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool):
+            loss = self._step_fn(rb)
+        self._launches_per_replay[rb] = (self.ops.launches - l0, getattr(comm, "launches", 0) - c0)
+        self.ops.launches = l0
+        if hasattr(comm, "launches"):
+            comm.launches = c0
+        self._graphs[rb] = g
+        self._loss_out[rb] = loss
+        return g
+
+    def rows_for(self, ids: np.ndarray) -> int:
+        return int(self.store.lens[ids].sum()) + len(ids) + 1
+
+    def capture_buckets(self, rows_list: Sequence[int]) -> List[int]:
+        """Pre-capture the graphs for the given row counts (after the first eager step)."""
+        if not self.use_graphs or not self._warmed:
+            return []
+        done = []
+        for rb in sorted({self._bucket(r) for r in rows_list}):
+            if rb not in self._graphs:
+                self._capture(rb)
+                done.append(rb)
+        return done
+
+    def step_async(self) -> torch.Tensor:
+        """Consume the next prepared batch: H2D copy + (graph) step.  Returns the loss tensor
+        (device); reading it is the caller's D2H sync."""
+        stage, err = self._q_out.get()
+        if err is not None:
+            raise err
+        self.dev_buf.copy_(stage["buf"], non_blocking=True)         # ONE packed H2D copy
+        ev = torch.cuda.Event()
+        ev.record()
+        stage["event"] = ev
+        loss = self._run(stage["rows"])
+        self.steps += 1
+        self.last = {"docs": stage["docs"], "words": stage["words"], "rows": stage["rows"]}
+        return loss
+
+    def train_step(self, ids: Optional[np.ndarray] = None) -> float:
+        """The public one-call step: (collate if ``ids`` given) -> H2D -> step -> loss (D2H)."""
+        if ids is not None:
+            self.prepare(ids)
+        return float(self.step_async().item())
+
+    def batches(self, n: int, seed: int = 0) -> List[np.ndarray]:
+        rng = np.random.default_rng(seed)
+        out = []
+        perm = rng.permutation(self.store.n_docs)
+        pos = 0
+        for _ in range(n):
+            if pos + self.B > len(perm):
+                perm = rng.permutation(self.store.n_docs)
+                pos = 0
+            out.append(np.sort(perm[pos:pos + self.B]).astype(np.int64))
+            pos += self.B
+        return out
+
+    def close(self) -> None:
+        if self._thread is not None:
+            self._q_in.put(None)
+            self._thread.join(timeout=5)
+            self._thread = None

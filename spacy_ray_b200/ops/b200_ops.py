@@ -64,6 +64,9 @@ class B200Ops(TorchOps):
         env_dw = os.environ.get("SRB_TC_DW")
         self.tc_dw = (env_dw != "0") if tc_dw is None else tc_dw
         self.launches = 0            # our kernels launched (bench.py reports this)
+        # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
+        # replays draw fresh masks although the per-call seeds were baked in at capture time
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._wt_cache: Dict[int, Tuple[int, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ GEMM helpers
@@ -146,13 +149,14 @@ class B200Ops(TorchOps):
                 shifts = {}
             self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
                          bias=b.reshape(-1), which=which, **shifts)
-            Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed)
+            Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed,
+                                                       self.seed_dev)
             self.launches += 1
         else:
             Xw = self.k.seq2col(X) if window else X
             Z = Xw @ W2.t()
             Y, which, xhat, rstd = self.k.maxout_ln_fwd(Z, b.reshape(-1), G, beta, X if residual else None, m1,
-                                                        nO, nP, drop, seed)
+                                                        nO, nP, drop, seed, self.seed_dev)
             self.launches += 2 if window else 1
         ctx = {"X": X, "W": W, "which": which, "window": window, "residual": residual, "mask": m1, "nP": nP,
                "has_ln": G is not None, "xhat": xhat, "rstd": rstd, "G": G, "drop": drop, "seed": seed}
@@ -174,7 +178,8 @@ class B200Ops(TorchOps):
         dbeta = torch.zeros(nO, dtype=torch.float32, device=dev) if has_ln else None
         dY = dY.contiguous()
         dZ = self.k.maxout_ln_bwd(dY, ctx["xhat"] if has_ln else None, ctx["rstd"] if has_ln else None,
-                                  ctx["G"], ctx["which"], ctx["mask"], nP, ctx["drop"], ctx["seed"], db, dG, dbeta)
+                                  ctx["G"], ctx["which"], ctx["mask"], nP, ctx["drop"], ctx["seed"], db, dG, dbeta,
+                                  self.seed_dev)
         self.launches += 1
         W2 = W.reshape(nO * nP, nI)
         N = nO * nP

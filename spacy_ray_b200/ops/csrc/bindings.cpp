@@ -65,7 +65,8 @@ void hash_embed_bwd(const Tensor& dY, const Tensor& attrs, const Tensor& mask, s
 
 std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
                                   const c10::optional<Tensor>& beta, const c10::optional<Tensor>& Xres,
-                                  const Tensor& mask, int64_t nO, int64_t nP, double drop_p, int64_t seed) {
+                                  const Tensor& mask, int64_t nO, int64_t nP, double drop_p, int64_t seed,
+                                  const c10::optional<Tensor>& seed_dev) {
   SRB_CHECK_CUDA(Z); SRB_CHECK_BF16(Z);
   TORCH_CHECK(nO % 32 == 0 && nO <= 512 && (nO * nP) % 8 == 0, "maxout_ln: nO must be a multiple of 32, <= 512");
   TORCH_CHECK(Z.size(1) == nO * nP);
@@ -80,13 +81,14 @@ std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& 
   srb::launch_maxout_ln_fwd(Z.data_ptr(), optptr(bias), optptr(G), optptr(beta), optptr(Xres), mask.data_ptr<float>(),
                             Y.data_ptr(), nP > 1 ? which.data_ptr<uint8_t>() : nullptr, has_ln ? xhat.data_ptr() : nullptr,
                             has_ln ? rstd.data_ptr<float>() : nullptr, Tp, (int)nO, (int)nP, (float)drop_p,
-                            (uint64_t)seed, cur_stream());
+                            (uint64_t)seed, (const int64_t*)optptr(seed_dev), cur_stream());
   return {Y, which, xhat, rstd};
 }
 
 Tensor maxout_ln_bwd(const Tensor& dY, const c10::optional<Tensor>& xhat, const c10::optional<Tensor>& rstd,
                      const c10::optional<Tensor>& G, const Tensor& which, const Tensor& mask, int64_t nP,
-                     double drop_p, int64_t seed, Tensor db, c10::optional<Tensor> dG, c10::optional<Tensor> dbeta) {
+                     double drop_p, int64_t seed, Tensor db, c10::optional<Tensor> dG, c10::optional<Tensor> dbeta,
+                     const c10::optional<Tensor>& seed_dev) {
   SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY);
   c10::cuda::CUDAGuard guard(dY.device());
   const int Tp = (int)dY.size(0), nO = (int)dY.size(1);
@@ -95,7 +97,8 @@ Tensor maxout_ln_bwd(const Tensor& dY, const c10::optional<Tensor>& xhat, const 
   srb::launch_maxout_ln_bwd(dY.data_ptr(), optptr(xhat), has_ln ? rstd->data_ptr<float>() : nullptr, optptr(G),
                             which.data_ptr<uint8_t>(), mask.data_ptr<float>(), dZ.data_ptr(), db.data_ptr<float>(),
                             has_ln ? dG->data_ptr<float>() : nullptr, has_ln ? dbeta->data_ptr<float>() : nullptr,
-                            Tp, nO, (int)nP, (float)drop_p, (uint64_t)seed, has_ln ? 1 : 0, cur_stream());
+                            Tp, nO, (int)nP, (float)drop_p, (uint64_t)seed, (const int64_t*)optptr(seed_dev),
+                            has_ln ? 1 : 0, cur_stream());
   return dZ;
 }
 
@@ -165,8 +168,8 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   const int64_t T = n_tokens;
   Tensor feats = at::empty({train ? T : 0, 3}, o.dtype(at::kInt));
   Tensor which = at::empty({train ? T : 0, nO}, o.dtype(at::kByte));
-  Tensor hid = at::empty({train ? T : 0, nO}, o);
-  Tensor d_scores = at::empty({train ? T : 0, nA_pad}, o);
+  Tensor hid = at::zeros({train ? T : 0, nO}, o);            // rows past the real token count stay zero
+  Tensor d_scores = at::zeros({train ? T : 0, nA_pad}, o);   // (fixed-capacity batches under CUDA graphs)
   Tensor actions = at::empty({T}, o.dtype(at::kInt));
   Tensor loss = at::zeros({}, o.dtype(at::kFloat));
   srb::BiluoArgs a{};
@@ -197,8 +200,8 @@ void transition_scatter(const Tensor& d_hid, const Tensor& which, const Tensor& 
 TORCH_LIBRARY(srb, m) {
   m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns) -> Tensor");
   m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
-  m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed) -> Tensor[]");
-  m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta) -> Tensor");
+  m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed, Tensor? seed_dev) -> Tensor[]");
+  m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta, Tensor? seed_dev) -> Tensor");
   m.def("seq2col(Tensor X) -> Tensor");
   m.def("col2seq_residual(Tensor dXw, Tensor? dY, Tensor mask) -> Tensor");
   m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");

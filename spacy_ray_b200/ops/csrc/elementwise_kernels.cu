@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(128) maxout_ln_fwd_kernel(
     const __nv_bfloat16* __restrict__ Z, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ G,
     const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ Y, uint8_t* __restrict__ which, __nv_bfloat16* __restrict__ xhat_out,
-    float* __restrict__ rstd_out, int Tp, int nO, float drop_p, uint64_t seed) {
+    float* __restrict__ rstd_out, int Tp, int nO, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (seed_dev) seed += (uint64_t)*seed_dev;     // device-side stream position (advances per CUDA-graph replay)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nZ = nO * NP;
   __nv_bfloat16* zs = (__nv_bfloat16*)smem_raw + (size_t)warp * nZ;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(128) maxout_ln_fwd_kernel(
 
 void launch_maxout_ln_fwd(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
-                          int nP, float drop_p, uint64_t seed, cudaStream_t s) {
+                          int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
   if (Tp <= 0) return;
   int blocks = (Tp + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -172,7 +173,8 @@ void launch_maxout_ln_fwd(const void* Z, const void* bias, const void* G, const 
 #define SRB_LAUNCH(NP)                                                                                   \
   maxout_ln_fwd_kernel<NP><<<blocks, 128, smem, s>>>(                                                    \
       (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta, \
-      (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, nO, drop_p, seed)
+      (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, nO, drop_p, seed, \
+      seed_dev)
   if (nP == 2) SRB_LAUNCH(2);
   else if (nP == 3) SRB_LAUNCH(3);
   else SRB_LAUNCH(1);
@@ -185,8 +187,9 @@ __global__ void __launch_bounds__(128) maxout_ln_bwd_kernel(
     const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ xhat, const float* __restrict__ rstd_in,
     const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ dZ, float* __restrict__ db, float* __restrict__ dG, float* __restrict__ dbeta,
-    int Tp, int nO, float drop_p, uint64_t seed, int has_ln) {
+    int Tp, int nO, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (seed_dev) seed += (uint64_t)*seed_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nZ = nO * NP;
   __nv_bfloat16* zs = (__nv_bfloat16*)smem_raw + (size_t)warp * nZ;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(128) maxout_ln_bwd_kernel(
 
 void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, const void* G, const uint8_t* which,
                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, int nO, int nP,
-                          float drop_p, uint64_t seed, int has_ln, cudaStream_t s) {
+                          float drop_p, uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s) {
   if (Tp <= 0) return;
   int blocks = (Tp + 3) / 4;
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -293,7 +296,7 @@ void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, c
       cudaFuncSetAttribute(maxout_ln_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     maxout_ln_bwd_kernel<NP><<<blocks, 128, smem, s>>>(                                                         \
         (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,       \
-        (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, nO, drop_p, seed, has_ln);                                       \
+        (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, nO, drop_p, seed, seed_dev, has_ln);                                       \
   } while (0)
   if (nP == 2) SRB_LAUNCH(2);
   else if (nP == 3) SRB_LAUNCH(3);

@@ -31,12 +31,12 @@ void launch_hash_embed_bwd(const int64_t* attrs, const float* mask, HashEmbedTab
 //   Y = mask * (X + D | D)
 void launch_maxout_ln_fwd(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
-                          int nP, float drop_p, uint64_t seed, cudaStream_t s);
+                          int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s);
 // Backward of the same: produces dZ (bf16, routed to the winning piece), dY_masked
 // is folded in; accumulates db (nO*nP), dG, dbeta (nO) in fp32.
 void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, const void* G, const uint8_t* which,
                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, int nO, int nP,
-                          float drop_p, uint64_t seed, int has_ln, cudaStream_t s);
+                          float drop_p, uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s);
 
 // K4 helpers for the library-GEMM path: materialised window / its transpose-add.
 void launch_seq2col(const void* X, void* Xw, int Tp, int nI, cudaStream_t s);

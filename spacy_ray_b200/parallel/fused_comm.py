@@ -165,7 +165,7 @@ class FusedSymmComm:
             for k in t["keys"]:
                 opt.nr_update[k] = opt.nr_update.get(k, 0) + 1
         self._steps_since_check += 1
-        if self._steps_since_check >= 64:
+        if self._steps_since_check >= 64 and not torch.cuda.is_current_stream_capturing():
             self.check()
 
     def check(self) -> None:

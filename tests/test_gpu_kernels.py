@@ -275,8 +275,8 @@ def test_biluo_kernel_matches_reference_loop(ops, ref):
     # docs whose whole action sequence agrees
     tok_doc = torch.repeat_interleave(torch.arange(len(lens), device="cuda"), torch.tensor(lens, device="cuda"))
     same_tok = rec["actions_flat"] == rref["actions_flat"]
-    doc_ok = torch.ones(len(lens), dtype=torch.bool, device="cuda")
-    doc_ok.scatter_reduce_(0, tok_doc, same_tok, reduce="amin")
+    doc_ok = torch.ones(len(lens), dtype=torch.int32, device="cuda")
+    doc_ok.scatter_reduce_(0, tok_doc, same_tok.to(torch.int32), reduce="amin")
     assert doc_ok.float().mean().item() > 0.8
     # reference records are ordered step-major; rebuild a per-token view of d_scores from the kernel's
     # records and check that it is a valid gradient: rows sum to ~0 and are zero for docs w/o gold

@@ -138,7 +138,12 @@ def _run_block(
     )
 
     def backprop(dY: torch.Tensor) -> torch.Tensor:
-        dX, dW, db, dG, dbeta = ops.maxout_block_backward(dY, ctx)
+        grad_out = None
+        if getattr(ops, "fused", False):
+            grad_out = {"W": maxout.grad_buffer("W"), "b": maxout.grad_buffer("b")}
+            if norm is not None:
+                grad_out["G"], grad_out["beta"] = norm.grad_buffer("G"), norm.grad_buffer("b")
+        dX, dW, db, dG, dbeta = ops.maxout_block_backward(dY, ctx, grad_out=grad_out)
         maxout.inc_grad("W", dW)
         maxout.inc_grad("b", db)
         if norm is not None:
@@ -189,8 +194,11 @@ def MultiHashEmbed(
 
         def backprop(dY):
             d_concat = bp_mix(dY)
+            bufs = [e.grad_buffer("E") for e in embeds] if getattr(ops, "fused", False) else None
+            if bufs is not None and any(b is None for b in bufs):
+                bufs = None
             grads = ops.multi_hash_embed_backward(
-                d_concat, batch.attrs, batch.mask, [int(t.shape[0]) for t in tables], seeds, cols
+                d_concat, batch.attrs, batch.mask, [int(t.shape[0]) for t in tables], seeds, cols, out=bufs
             )
             for e, g in zip(embeds, grads):
                 e.inc_grad("E", g)

@@ -267,6 +267,19 @@ class Model:
     def inc_grad(self, name: str, value: torch.Tensor) -> None:
         self._params.inc_grad(self.id, name, value)
 
+    def grad_buffer(self, name: str) -> Optional[torch.Tensor]:
+        """The proxy's accumulation buffer for this parameter's gradient, if it exposes one
+        (``ShardedSyncProxy.grad_buffer``): kernels may accumulate into it in place and then
+        hand the same tensor to ``inc_grad`` (which recognises it and skips the add)."""
+        proxy = self._params.proxy
+        fn = getattr(proxy, "grad_buffer", None) if proxy is not None else None
+        if fn is None or not self._params.has_param(self.id, name):
+            return None
+        try:
+            return fn(self.id, name)
+        except KeyError:
+            return None
+
     # ---- execution -------------------------------------------------------
     def __call__(self, X: Any, is_train: bool) -> Tuple[Any, Callable]:
         return self._func(self, X, is_train)

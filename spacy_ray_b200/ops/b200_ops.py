@@ -63,6 +63,7 @@ class B200Ops(TorchOps):
         self.use_tc = (env_tc != "0") if use_tc is None else use_tc
         env_dw = os.environ.get("SRB_TC_DW")
         self.tc_dw = (env_dw != "0") if tc_dw is None else tc_dw
+        self.sorted_embed_bwd = os.environ.get("SRB_SORTED_EMBED", "1") != "0"
         self.launches = 0            # our kernels launched (bench.py reports this)
         # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
         # replays draw fresh masks although the per-call seeds were baked in at capture time
@@ -124,7 +125,14 @@ class B200Ops(TorchOps):
         grads = list(out) if out is not None else [
             torch.zeros((nV, nO), dtype=torch.float32, device=dY.device) for nV in n_rows
         ]
-        self.k.hash_embed_bwd(dY.contiguous(), attrs, _mask1d(mask), grads, list(seeds), list(columns))
+        if self.sorted_embed_bwd:
+            # sort each table's attribute column once; the kernel then reduces runs of equal
+            # ids in registers and touches each table row once per run (no hot-row contention)
+            keys = attrs[:, list(columns)].t().contiguous()            # (n_tables, R)
+            skeys, perm = torch.sort(keys, dim=1)
+            self.k.hash_embed_bwd_sorted(dY.contiguous(), skeys, perm, _mask1d(mask), grads, list(seeds), list(columns))
+        else:
+            self.k.hash_embed_bwd(dY.contiguous(), attrs, _mask1d(mask), grads, list(seeds), list(columns))
         self.launches += 1
         return grads
 
@@ -173,9 +181,19 @@ class B200Ops(TorchOps):
         window = ctx["window"]
         dev = X.device
         has_ln = ctx["has_ln"]
-        db = torch.zeros(nO * nP, dtype=torch.float32, device=dev)
-        dG = torch.zeros(nO, dtype=torch.float32, device=dev) if has_ln else None
-        dbeta = torch.zeros(nO, dtype=torch.float32, device=dev) if has_ln else None
+        # ``grad_out``: fp32 views of the flat gradient bucket.  Kernels accumulate straight into
+        # them (atomics / split-K red), so no zero-fill + add_ launches per parameter.
+        go = grad_out or {}
+
+        def _dst(name, shape):
+            t = go.get(name)
+            if t is not None and t.dtype == torch.float32 and t.is_contiguous():
+                return t.view(shape)
+            return torch.zeros(shape, dtype=torch.float32, device=dev)
+
+        db = _dst("b", (nO * nP,))
+        dG = _dst("G", (nO,)) if has_ln else None
+        dbeta = _dst("beta", (nO,)) if has_ln else None
         dY = dY.contiguous()
         dZ = self.k.maxout_ln_bwd(dY, ctx["xhat"] if has_ln else None, ctx["rstd"] if has_ln else None,
                                   ctx["G"], ctx["which"], ctx["mask"], nP, ctx["drop"], ctx["seed"], db, dG, dbeta,
@@ -184,10 +202,16 @@ class B200Ops(TorchOps):
         W2 = W.reshape(nO * nP, nI)
         N = nO * nP
         # ---- dW ----------------------------------------------------------
-        dW = self._dw_tc(dZ, X, window)
+        dW_dst = go.get("W")
+        if dW_dst is not None and not (dW_dst.dtype == torch.float32 and dW_dst.is_contiguous()):
+            dW_dst = None
+        dW = self._dw_tc(dZ, X, window, out=dW_dst.view(nO * nP, nI) if dW_dst is not None else None)
         if dW is None:
             Xw = self.k.seq2col(X) if window else X
             dW = _mm_f32(dZ.t(), Xw)
+            if dW_dst is not None:
+                dW_dst.view(nO * nP, nI).add_(dW)
+                dW = dW_dst
         # ---- dX ----------------------------------------------------------
         bn = self._pick_block_n(w_in)
         if self._tc_ok(N, w_in) and bn:

@@ -63,6 +63,22 @@ void hash_embed_bwd(const Tensor& dY, const Tensor& attrs, const Tensor& mask, s
                              cur_stream());
 }
 
+void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& perm, const Tensor& mask,
+                           std::vector<Tensor> grads, std::vector<int64_t> seeds, std::vector<int64_t> columns) {
+  SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY); SRB_CHECK_CUDA(keys); SRB_CHECK_CUDA(perm);
+  TORCH_CHECK(keys.scalar_type() == at::kLong && perm.scalar_type() == at::kLong && keys.dim() == 2);
+  TORCH_CHECK(keys.size(0) == (int64_t)grads.size() && grads[0].size(1) <= 512);
+  c10::cuda::CUDAGuard guard(dY.device());
+  auto t = make_tables(grads, seeds, columns, 0);
+  for (size_t a = 0; a < grads.size(); ++a) {
+    SRB_CHECK_CUDA(grads[a]);
+    TORCH_CHECK(grads[a].scalar_type() == at::kFloat, "table gradients must be fp32");
+    t.grad[a] = grads[a].data_ptr<float>();
+  }
+  srb::launch_hash_embed_bwd_sorted(keys.data_ptr<int64_t>(), perm.data_ptr<int64_t>(), mask.data_ptr<float>(), t,
+                                    dY.data_ptr(), (int)keys.size(1), cur_stream());
+}
+
 std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
                                   const c10::optional<Tensor>& beta, const c10::optional<Tensor>& Xres,
                                   const Tensor& mask, int64_t nO, int64_t nP, double drop_p, int64_t seed,
@@ -200,6 +216,7 @@ void transition_scatter(const Tensor& d_hid, const Tensor& which, const Tensor& 
 TORCH_LIBRARY(srb, m) {
   m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns) -> Tensor");
   m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
+  m.def("hash_embed_bwd_sorted(Tensor dY, Tensor keys, Tensor perm, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
   m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed, Tensor? seed_dev) -> Tensor[]");
   m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta, Tensor? seed_dev) -> Tensor");
   m.def("seq2col(Tensor X) -> Tensor");
@@ -215,6 +232,7 @@ TORCH_LIBRARY(srb, m) {
 TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("hash_embed_fwd", hash_embed_fwd);
   m.impl("hash_embed_bwd", hash_embed_bwd);
+  m.impl("hash_embed_bwd_sorted", hash_embed_bwd_sorted);
   m.impl("maxout_ln_fwd", maxout_ln_fwd);
   m.impl("maxout_ln_bwd", maxout_ln_bwd);
   m.impl("seq2col", seq2col);

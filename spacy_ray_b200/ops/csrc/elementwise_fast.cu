@@ -1,0 +1,351 @@
+// Vectorised fast paths for the memory-bound kernels (profiles/r1_run2_launch_list.md showed
+// the scalar versions at 16x their HBM roofline):
+//   * maxout_ln fwd / bwd: each lane owns UPL *contiguous* units, so every global access is
+//     a 16-byte vector (no shared-memory staging), one warp per row, many warps per SM.
+//   * hash_embed backward over *sorted* attribute ids: a warp walks a chunk of the sorted
+//     order, sums the dY rows of a run of identical ids in registers and issues the four
+//     table-row updates once per run (vector RED).  The unsorted kernel hammered ~50 hot
+//     PREFIX/SHAPE rows with one atomic per token per element.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srb {
+
+// ------------------------------------------------------------------------------------------
+// forward: Z (Tp, nO*NP) [+bias] -> maxout -> LN -> dropout -> (+X) -> mask
+// ------------------------------------------------------------------------------------------
+template <int NP, int UPL>
+__global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
+    const __nv_bfloat16* __restrict__ Z, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ G,
+    const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
+    __nv_bfloat16* __restrict__ Y, uint8_t* __restrict__ which, __nv_bfloat16* __restrict__ xhat_out,
+    float* __restrict__ rstd_out, int Tp, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
+  constexpr int nO = 32 * UPL;
+  constexpr int ZPL = UPL * NP;                 // Z elements per lane (multiple of 8)
+  if (seed_dev) seed += (uint64_t)*seed_dev;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const bool has_ln = G != nullptr;
+  const int u0 = lane * UPL;
+  float gk[UPL], bk[UPL], bz[ZPL];
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) { gk[j] = has_ln ? bf2f(G[u0 + j]) : 1.f; bk[j] = has_ln ? bf2f(beta[u0 + j]) : 0.f; }
+#pragma unroll
+  for (int j = 0; j < ZPL; ++j) bz[j] = bias ? bf2f(bias[u0 * NP + j]) : 0.f;
+  for (int row = gwarp; row < Tp; row += nwarps) {
+    const size_t ro = (size_t)row * nO + u0;
+    if (mask[row] == 0.0f) {
+      bf16x8 zero;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+#pragma unroll
+      for (int v = 0; v < UPL / 8; ++v) {
+        *(bf16x8*)(Y + ro + v * 8) = zero;
+        if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = zero;
+        if (which) *(uint2*)(which + ro + v * 8) = make_uint2(0u, 0u);
+      }
+      if (lane == 0 && rstd_out) rstd_out[row] = 0.f;
+      continue;
+    }
+    float z[ZPL];
+    const bf16x8* zp = (const bf16x8*)(Z + (size_t)row * nO * NP + u0 * NP);
+#pragma unroll
+    for (int v = 0; v < ZPL / 8; ++v) {
+      bf16x8 t = zp[v];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[v * 8 + i] = bf2f(t.v[i]) + bz[v * 8 + i];
+    }
+    float h[UPL];
+    uint8_t wh[UPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+      float best = z[j * NP];
+      int bi = 0;
+#pragma unroll
+      for (int p = 1; p < NP; ++p) if (z[j * NP + p] > best) { best = z[j * NP + p]; bi = p; }
+      h[j] = best; wh[j] = (uint8_t)bi; sum += best;
+    }
+    float mu = 0.f, rstd = 1.f;
+    if (has_ln) {
+      mu = warp_sum(sum) * (1.f / nO);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < UPL; ++j) { const float d = h[j] - mu; sq += d * d; }
+      rstd = rsqrtf(warp_sum(sq) * (1.f / nO) + 1e-8f);
+    }
+    float xr[UPL];
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) xr[j] = 0.f;
+    if (Xres) {
+#pragma unroll
+      for (int v = 0; v < UPL / 8; ++v) {
+        bf16x8 t = *(const bf16x8*)(Xres + ro + v * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xr[v * 8 + i] = bf2f(t.v[i]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < UPL / 8; ++v) {
+      bf16x8 yo, xo;
+      __align__(8) uint8_t w8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = v * 8 + i;
+        const float xh = (h[j] - mu) * rstd;
+        float n = has_ln ? xh * gk[j] + bk[j] : h[j];
+        if (drop_p > 0.f) n *= dropout_scale(seed, ro + j, drop_p, inv_keep);
+        n += xr[j];
+        yo.v[i] = f2bf(n);
+        xo.v[i] = f2bf(xh);
+        w8[i] = wh[j];
+      }
+      *(bf16x8*)(Y + ro + v * 8) = yo;
+      if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = xo;
+      if (which) *(uint2*)(which + ro + v * 8) = *(const uint2*)w8;
+    }
+    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <int NP, int UPL>
+static void launch_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
+                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, float drop_p,
+                           uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
+  int blocks = (Tp + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  maxout_ln_fwd_vec_kernel<NP, UPL><<<blocks, 256, 0, s>>>(
+      (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta,
+      (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, drop_p, seed,
+      seed_dev);
+}
+
+bool try_launch_maxout_ln_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
+                                  const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
+                                  int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
+#define SRB_TRY(NP_, UPL_)                                                                                       \
+  if (nP == NP_ && nO == 32 * UPL_) {                                                                            \
+    launch_fwd_vec<NP_, UPL_>(Z, bias, G, beta, X_res, mask, Y, which, xhat, rstd, Tp, drop_p, seed, seed_dev, s); \
+    return true;                                                                                                 \
+  }
+  SRB_TRY(1, 8) SRB_TRY(1, 16) SRB_TRY(3, 8) SRB_TRY(3, 16) SRB_TRY(2, 8) SRB_TRY(2, 16)
+#undef SRB_TRY
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: dY -> dropout -> LN backward -> routed dZ; accumulates dG, dbeta, db
+// ------------------------------------------------------------------------------------------
+template <int NP, int UPL>
+__global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
+    const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ xhat, const float* __restrict__ rstd_in,
+    const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
+    __nv_bfloat16* __restrict__ dZ, float* __restrict__ db, float* __restrict__ dG, float* __restrict__ dbeta, int Tp,
+    float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
+  constexpr int nO = 32 * UPL;
+  constexpr int ZPL = UPL * NP;
+  if (seed_dev) seed += (uint64_t)*seed_dev;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const int u0 = lane * UPL;
+  float gk[UPL];
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) gk[j] = has_ln ? bf2f(G[u0 + j]) : 1.f;
+  float accG[UPL], accB[UPL], accb[ZPL];
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) { accG[j] = 0.f; accB[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < ZPL; ++j) accb[j] = 0.f;
+  for (int row = gwarp; row < Tp; row += nwarps) {
+    const size_t ro = (size_t)row * nO + u0;
+    bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
+    if (mask[row] == 0.0f) {
+      bf16x8 zero;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+#pragma unroll
+      for (int v = 0; v < ZPL / 8; ++v) zout[v] = zero;
+      continue;
+    }
+    float dn[UPL], xh[UPL];
+    uint8_t wh[UPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < UPL / 8; ++v) {
+      bf16x8 d8 = *(const bf16x8*)(dY + ro + v * 8);
+      bf16x8 x8;
+      if (has_ln) x8 = *(const bf16x8*)(xhat + ro + v * 8);
+      const uint2 w2 = *(const uint2*)(which + ro + v * 8);
+      const uint8_t* wb = (const uint8_t*)&w2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = v * 8 + i;
+        float d = bf2f(d8.v[i]);
+        if (drop_p > 0.f) d *= dropout_scale(seed, ro + j, drop_p, inv_keep);
+        wh[j] = wb[i];
+        if (has_ln) {
+          xh[j] = bf2f(x8.v[i]);
+          accG[j] += d * xh[j];
+          accB[j] += d;
+          d *= gk[j];
+          s1 += d; s2 += d * xh[j];
+        } else {
+          xh[j] = 0.f;
+        }
+        dn[j] = d;
+      }
+    }
+    float rstd = 1.f;
+    if (has_ln) {
+      rstd = rstd_in[row];
+      s1 = warp_sum(s1) * (1.f / nO);
+      s2 = warp_sum(s2) * (1.f / nO);
+    }
+    __align__(16) __nv_bfloat16 zo[ZPL];
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+      const float dH = has_ln ? rstd * (dn[j] - s1 - xh[j] * s2) : dn[j];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const float val = (q == wh[j]) ? dH : 0.f;
+        zo[j * NP + q] = f2bf(val);
+        accb[j * NP + q] += val;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < ZPL / 8; ++v) zout[v] = *(const bf16x8*)(zo + v * 8);
+  }
+  // combine the 8 warps of the block through shared memory, then one atomic per element
+  extern __shared__ float sred[];                  // [8][nO*(NP+2)]
+  float* mine = sred + (size_t)warp * nO * (NP + 2);
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) { mine[u0 + j] = accG[j]; mine[nO + u0 + j] = accB[j]; }
+#pragma unroll
+  for (int j = 0; j < ZPL; ++j) mine[2 * nO + u0 * NP + j] = accb[j];
+  __syncthreads();
+  const int per = nO * (NP + 2);
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[(size_t)w * per + i];
+    if (t == 0.f) continue;
+    if (i < nO) { if (has_ln) atomicAdd(dG + i, t); }
+    else if (i < 2 * nO) { if (has_ln) atomicAdd(dbeta + (i - nO), t); }
+    else atomicAdd(db + (i - 2 * nO), t);
+  }
+}
+
+template <int NP, int UPL>
+static void launch_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G, const uint8_t* which,
+                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, float drop_p,
+                           uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s) {
+  int blocks = (Tp + 31) / 32;                       // >= 4 rows per warp so the flush is amortised
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = sizeof(float) * 8 * 32 * UPL * (NP + 2);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  maxout_ln_bwd_vec_kernel<NP, UPL><<<blocks, 256, smem, s>>>(
+      (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,
+      (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln);
+}
+
+bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G,
+                                  const uint8_t* which, const float* mask, void* dZ, float* db, float* dG,
+                                  float* dbeta, int Tp, int nO, int nP, float drop_p, uint64_t seed,
+                                  const int64_t* seed_dev, int has_ln, cudaStream_t s) {
+#define SRB_TRY(NP_, UPL_)                                                                                          \
+  if (nP == NP_ && nO == 32 * UPL_) {                                                                               \
+    launch_bwd_vec<NP_, UPL_>(dY, xhat, rstd, G, which, mask, dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln, s); \
+    return true;                                                                                                    \
+  }
+  SRB_TRY(3, 8) SRB_TRY(3, 16) SRB_TRY(2, 8) SRB_TRY(2, 16)
+#undef SRB_TRY
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// HashEmbed backward over sorted ids
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+constexpr int kSortChunk = 64;     // sorted positions per warp
+
+// keys: (n_tables, R) sorted attribute ids; perm: (n_tables, R) row of each sorted position.
+__global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_t* __restrict__ keys,
+                                                                    const int64_t* __restrict__ perm,
+                                                                    const float* __restrict__ mask, HashEmbedTables t,
+                                                                    const __nv_bfloat16* __restrict__ dY, int R) {
+  const int a = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int p0 = chunk * kSortChunk;
+  if (p0 >= R) return;
+  const int p1 = min(R, p0 + kSortChunk);
+  const int C = t.n_tables * t.width;
+  const int nvec = t.width / 8;                      // 16-byte vectors per table row (<= 64)
+  const int64_t* k = keys + (size_t)a * R;
+  const int64_t* pm = perm + (size_t)a * R;
+  float acc[2][8];
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+  bool have = false;
+  int64_t cur = 0;
+  float* dE = t.grad[a];
+  auto flush = [&]() {
+    if (!have) return;
+    uint32_t rows[4];
+    hash_rows((uint64_t)cur, t.seed[a], t.n_rows[a], rows);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int vec = lane + 32 * v;
+      if (vec < nvec) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float* dst = dE + (size_t)rows[kk] * t.width + vec * 8;
+          red_add_v4f(dst, acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
+          red_add_v4f(dst + 4, acc[v][4], acc[v][5], acc[v][6], acc[v][7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+      }
+    }
+  };
+  for (int p = p0; p < p1; ++p) {
+    const int64_t row = pm[p];
+    if (mask[row] == 0.0f) continue;
+    const int64_t key = k[p];
+    if (have && key != cur) flush();
+    cur = key; have = true;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int vec = lane + 32 * v;
+      if (vec < nvec) {
+        bf16x8 g = *(const bf16x8*)(dY + (size_t)row * C + a * t.width + vec * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[v][i] += bf2f(g.v[i]);
+      }
+    }
+  }
+  flush();
+}
+
+void launch_hash_embed_bwd_sorted(const int64_t* keys, const int64_t* perm, const float* mask, HashEmbedTables t,
+                                  const void* dY, int R, cudaStream_t s) {
+  if (R <= 0) return;
+  dim3 grid((R + kSortChunk * 4 - 1) / (kSortChunk * 4), t.n_tables);
+  hash_embed_bwd_sorted_kernel<<<grid, 128, 0, s>>>(keys, perm, mask, t, (const __nv_bfloat16*)dY, R);
+}
+
+}  // namespace srb

@@ -167,6 +167,9 @@ void launch_maxout_ln_fwd(const void* Z, const void* bias, const void* G, const 
                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
                           int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
   if (Tp <= 0) return;
+  if (try_launch_maxout_ln_fwd_vec(Z, bias, G, beta, X_res, mask, Y, which, xhat, rstd, Tp, nO, nP, drop_p, seed,
+                                   seed_dev, s))
+    return;
   int blocks = (Tp + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)4 * nO * nP * sizeof(__nv_bfloat16);
@@ -285,6 +288,9 @@ void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, c
                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, int nO, int nP,
                           float drop_p, uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s) {
   if (Tp <= 0) return;
+  if (try_launch_maxout_ln_bwd_vec(dY, xhat, rstd, G, which, mask, dZ, db, dG, dbeta, Tp, nO, nP, drop_p, seed,
+                                   seed_dev, has_ln, s))
+    return;
   int blocks = (Tp + 3) / 4;
   if (blocks > 148 * 4) blocks = 148 * 4;
   size_t smem_z = (size_t)4 * nO * nP * sizeof(__nv_bfloat16);

@@ -38,6 +38,18 @@ void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, c
                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, int nO, int nP,
                           float drop_p, uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s);
 
+// Vectorised fast paths (elementwise_fast.cu); return false when the shape is not covered.
+bool try_launch_maxout_ln_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
+                                  const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
+                                  int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s);
+bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G,
+                                  const uint8_t* which, const float* mask, void* dZ, float* db, float* dG,
+                                  float* dbeta, int Tp, int nO, int nP, float drop_p, uint64_t seed,
+                                  const int64_t* seed_dev, int has_ln, cudaStream_t s);
+// K1 backward over ids sorted per table: keys/perm are (n_tables, R).
+void launch_hash_embed_bwd_sorted(const int64_t* keys, const int64_t* perm, const float* mask, HashEmbedTables t,
+                                  const void* dY, int R, cudaStream_t s);
+
 // K4 helpers for the library-GEMM path: materialised window / its transpose-add.
 void launch_seq2col(const void* X, void* Xw, int Tp, int nI, cudaStream_t s);
 // dX = col2seq(dXw) (+ residual dY*mask)

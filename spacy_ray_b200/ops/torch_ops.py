@@ -256,7 +256,7 @@ class TorchOps:
         Y = Y * mask.to(torch.float32)
         return Y.to(self.dtype), ctx
 
-    def maxout_block_backward(self, dY: torch.Tensor, ctx: Dict[str, Any]):
+    def maxout_block_backward(self, dY: torch.Tensor, ctx: Dict[str, Any], grad_out=None):
         """Returns ``(dX, dW, db, dG, dbeta)`` (fp32; dG/dbeta None without LN)."""
         mask = ctx["mask"].to(torch.float32)
         dYm = dY.to(torch.float32) * mask

@@ -128,7 +128,11 @@ class B200Ops(TorchOps):
         if self.sorted_embed_bwd:
             # sort each table's attribute column once; the kernel then reduces runs of equal
             # ids in registers and touches each table row once per run (no hot-row contention)
-            keys = attrs[:, list(columns)].t().contiguous()            # (n_tables, R)
+            cols = tuple(int(c) for c in columns)
+            if cols == tuple(range(attrs.shape[1])):
+                keys = attrs.t().contiguous()                          # (n_tables, R)
+            else:                                                      # no host->device index copy (graph-safe)
+                keys = torch.stack([attrs[:, c] for c in cols], dim=0).contiguous()
             skeys, perm = torch.sort(keys, dim=1)
             self.k.hash_embed_bwd_sorted(dY.contiguous(), skeys, perm, _mask1d(mask), grads, list(seeds), list(columns))
         else:

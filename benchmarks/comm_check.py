@@ -165,7 +165,7 @@ def run_sweep(rank, world, dev, max_bytes):
         elems = nbytes // 4
         shard = max(4, (elems // world) // 4 * 4)
         local = torch.zeros(shard, dtype=torch.float32, device=dev)
-        grid = max(1, min(sms, (shard // 4 + 255) // 256))
+        grid = max(1, min(2 * sms, (shard // 16 + 255) // 256))
         # grid must stay constant for the barrier counter: reset the counters per size
         epoch.zero_(); bar.zero_(); flags.zero_()
         torch.cuda.synchronize(); dist.barrier()

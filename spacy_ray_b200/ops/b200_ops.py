@@ -133,8 +133,9 @@ class B200Ops(TorchOps):
                 keys = attrs.t().contiguous()                          # (n_tables, R)
             else:                                                      # no host->device index copy (graph-safe)
                 keys = torch.stack([attrs[:, c] for c in cols], dim=0).contiguous()
-            skeys, perm = torch.sort(keys, dim=1)
-            self.k.hash_embed_bwd_sorted(dY.contiguous(), skeys, perm, _mask1d(mask), grads, list(seeds), list(columns))
+            # 32-bit truncated keys: half the radix passes; the kernel splits runs on the full id
+            _sk, perm = torch.sort(keys.to(torch.int32), dim=1)
+            self.k.hash_embed_bwd_sorted(dY.contiguous(), attrs, perm, _mask1d(mask), grads, list(seeds), list(columns))
         else:
             self.k.hash_embed_bwd(dY.contiguous(), attrs, _mask1d(mask), grads, list(seeds), list(columns))
         self.launches += 1
@@ -285,7 +286,7 @@ class B200Ops(TorchOps):
         if not isinstance(system, BiluoSystem):
             return None                       # arc-eager: reference loop (host state machine)
         nO, nP = params["nO"], params["nP"]
-        if nO % 32 != 0 or (nO * nP) // 32 > 8 or system.n_actions > 256:
+        if nP != 2 or nO % 32 != 0 or (nO * nP) // 32 > 8 or system.n_actions > 256:
             return None
         dev = Yf.device
         extra = batch.extra

@@ -66,17 +66,18 @@ void hash_embed_bwd(const Tensor& dY, const Tensor& attrs, const Tensor& mask, s
 void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& perm, const Tensor& mask,
                            std::vector<Tensor> grads, std::vector<int64_t> seeds, std::vector<int64_t> columns) {
   SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY); SRB_CHECK_CUDA(keys); SRB_CHECK_CUDA(perm);
+  // keys: the raw (R, n_attr) attribute array; perm: (n_tables, R) row order sorted per table
   TORCH_CHECK(keys.scalar_type() == at::kLong && perm.scalar_type() == at::kLong && keys.dim() == 2);
-  TORCH_CHECK(keys.size(0) == (int64_t)grads.size() && grads[0].size(1) <= 512);
+  TORCH_CHECK(perm.size(0) == (int64_t)grads.size() && perm.size(1) == keys.size(0) && grads[0].size(1) <= 512);
   c10::cuda::CUDAGuard guard(dY.device());
-  auto t = make_tables(grads, seeds, columns, 0);
+  auto t = make_tables(grads, seeds, columns, (int)keys.size(1));
   for (size_t a = 0; a < grads.size(); ++a) {
     SRB_CHECK_CUDA(grads[a]);
     TORCH_CHECK(grads[a].scalar_type() == at::kFloat, "table gradients must be fp32");
     t.grad[a] = grads[a].data_ptr<float>();
   }
   srb::launch_hash_embed_bwd_sorted(keys.data_ptr<int64_t>(), perm.data_ptr<int64_t>(), mask.data_ptr<float>(), t,
-                                    dY.data_ptr(), (int)keys.size(1), cur_stream());
+                                    dY.data_ptr(), (int)perm.size(1), cur_stream());
 }
 
 std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
@@ -175,7 +176,7 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
                                 const Tensor& tok_off, const c10::optional<Tensor>& gold, const Tensor& inv_active,
                                 int64_t n_tokens, int64_t nO, int64_t nP, int64_t n_labels, bool train) {
   SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
-  TORCH_CHECK(nO % 32 == 0 && (nO * nP) / 32 <= 8, "biluo_steps: hidden width/pieces not supported");
+  TORCH_CHECK(nP == 2 && nO % 32 == 0 && (nO * nP) / 32 <= 8, "biluo_steps: hidden width/pieces not supported");
   c10::cuda::CUDAGuard guard(Yf.device());
   const int64_t nA = Wu.size(0);
   TORCH_CHECK(nA == 4 * n_labels + 1 && nA <= 256);

@@ -89,7 +89,7 @@ __device__ __forceinline__ bool grid_barrier(uint32_t* counter, uint32_t target,
   return ok;
 }
 
-__global__ void __launch_bounds__(256, 1) fused_rs_adam_ag_kernel(FusedCommArgs a) {
+__global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs a) {
   const int W = a.world, rank = a.rank;
   const uint32_t epoch = *a.epoch + 1;                     // flag value for this invocation
   const uint64_t tmo = a.timeout_ns;
@@ -118,24 +118,35 @@ __global__ void __launch_bounds__(256, 1) fused_rs_adam_ag_kernel(FusedCommArgs 
     const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
     const int64_t end = a.key_off[k] + a.key_len[k];
     float acc = 0.f;
-    for (int i = threadIdx.x * 4; i < kCommChunk; i += 256 * 4) {
-      const int64_t idx = base + i;
-      if (idx < end) {
-        float4 s;
-        if (a.grad_mc) {
-          s = multimem_ld_reduce_v4(a.grad_mc + s0 + idx);
-        } else {
-          s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-          for (int p = 0; p < W; ++p) {
-            const int peer = (rank + p) % W;              // stagger peers across ranks
-            float4 v = ld_relaxed_sys_v4(a.grad[peer] + s0 + idx);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-          }
+    {
+      // 4 independent 16-byte loads per peer are issued before any is consumed (the work item
+      // is exactly 256 threads x 4 vectors), so each thread keeps >= 4 NVLink reads in flight.
+      float4 s[4];
+      bool ok[4];
+      const int64_t t0 = base + threadIdx.x * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ok[j] = (t0 + j * 1024) < end; s[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      if (a.grad_mc) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = multimem_ld_reduce_v4(a.grad_mc + s0 + t0 + j * 1024);
+      } else {
+#pragma unroll 2
+        for (int p = 0; p < W; ++p) {
+          const float* src = a.grad[(rank + p) % W] + s0 + t0;      // stagger peers across ranks
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (ok[j]) v[j] = ld_relaxed_sys_v4(src + j * 1024);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (ok[j]) { s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w; }
         }
-        s.x *= gs; s.y *= gs; s.z *= gs; s.w *= gs;
-        *(float4*)(my_grad + s0 + idx) = s;
-        acc += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ok[j]) {
+          s[j].x *= gs; s[j].y *= gs; s[j].z *= gs; s[j].w *= gs;
+          *(float4*)(my_grad + s0 + t0 + j * 1024) = s[j];
+          acc += s[j].x * s[j].x + s[j].y * s[j].y + s[j].z * s[j].z + s[j].w * s[j].w;
+        }
       }
     }
     acc = warp_sum(acc);
@@ -170,24 +181,37 @@ __global__ void __launch_bounds__(256, 1) fused_rs_adam_ag_kernel(FusedCommArgs 
       const float norm = sqrtf(a.norms_sq[k]);
       if (norm >= clip) scale = clip / fmaxf(norm, 1e-30f);
     }
-    for (int i = threadIdx.x * 4; i < kCommChunk; i += 256 * 4) {
-      const int64_t idx = base + i;
-      if (idx < end) {
-        float4 g = *(float4*)(my_grad + s0 + idx);
-        float4 w = *(float4*)(a.master + idx);
-        float4 m1 = *(float4*)(a.m1 + idx);
-        float4 m2 = *(float4*)(a.m2 + idx);
-        float gv[4] = {g.x, g.y, g.z, g.w}, wv[4] = {w.x, w.y, w.z, w.w};
-        float av[4] = {m1.x, m1.y, m1.z, m1.w}, bv[4] = {m2.x, m2.y, m2.z, m2.w};
+    {
+      // loads for all 4 vectors of this thread first (16 independent 16-byte loads in flight)
+      const int64_t t0 = base + threadIdx.x * 4;
+      float4 g4[4], w4[4], a4[4], b4[4];
+      bool ok[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x = gv[j];
-          if (l2 != 0.f && !wd) x += l2 * wv[j];
+      for (int j = 0; j < 4; ++j) {
+        const int64_t idx = t0 + j * 1024;
+        ok[j] = idx < end;
+        if (ok[j]) {
+          g4[j] = *(const float4*)(my_grad + s0 + idx);
+          w4[j] = *(const float4*)(a.master + idx);
+          a4[j] = *(const float4*)(a.m1 + idx);
+          b4[j] = *(const float4*)(a.m2 + idx);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok[j]) continue;
+        const int64_t idx = t0 + j * 1024;
+        float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w}, wv[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
+        float av[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w}, bv[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = gv[e];
+          if (l2 != 0.f && !wd) x += l2 * wv[e];
           x *= scale;
-          av[j] = b1 * av[j] + (1.f - b1) * x;
-          bv[j] = b2 * bv[j] + (1.f - b2) * x * x;
-          wv[j] -= lr_t * av[j] / (sqrtf(bv[j]) + eps);
-          if (wd && l2 != 0.f) wv[j] *= (1.f - lr * l2);
+          av[e] = b1 * av[e] + (1.f - b1) * x;
+          bv[e] = b2 * bv[e] + (1.f - b2) * x * x;
+          wv[e] -= lr_t * av[e] / (sqrtf(bv[e]) + eps);
+          if (wd && l2 != 0.f) wv[e] *= (1.f - lr * l2);
         }
         *(float4*)(a.master + idx) = make_float4(wv[0], wv[1], wv[2], wv[3]);
         *(float4*)(a.m1 + idx) = make_float4(av[0], av[1], av[2], av[3]);
@@ -248,7 +272,7 @@ cudaError_t launch_fused_rs_adam_ag(const FusedCommArgs& a, int grid, cudaStream
 // -------------------------------------------------------------------------------------------
 // Stand-alone collectives on the same machinery (bandwidth sweep, BASELINE.json config 5)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) p2p_reduce_scatter_kernel(P2PCollArgs a) {
+__global__ void __launch_bounds__(256, 2) p2p_reduce_scatter_kernel(P2PCollArgs a) {
   const int W = a.world, rank = a.rank;
   const uint32_t epoch = *a.epoch + 1;
   __shared__ int s_fail;
@@ -263,19 +287,29 @@ __global__ void __launch_bounds__(256, 1) p2p_reduce_scatter_kernel(P2PCollArgs 
   if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 1); return; }
   const int64_t n4 = a.shard_elems / 4;
   const float* const* src = (const float* const*)a.buf;
-  for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
-    const int64_t idx = a.shard_elems * rank + i * 4;
-    float4 s;
-    if (a.mc) s = multimem_ld_reduce_v4((const float*)a.mc + idx);
-    else {
-      s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i0 = blockIdx.x * 256 + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 acc[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ok[j] = (i0 + j * stride) < n4; acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (a.mc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ok[j]) acc[j] = multimem_ld_reduce_v4((const float*)a.mc + a.shard_elems * rank + (i0 + j * stride) * 4);
+    } else {
+#pragma unroll 2
       for (int p = 0; p < W; ++p) {
-        float4 v = ld_relaxed_sys_v4(src[(rank + p) % W] + idx);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        const float* sp = src[(rank + p) % W] + a.shard_elems * rank;
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ok[j]) v[j] = ld_relaxed_sys_v4(sp + (i0 + j * stride) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ok[j]) { acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w; }
       }
     }
-    *(float4*)((float*)a.out + i * 4) = s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (ok[j]) *(float4*)((float*)a.out + (i0 + j * stride) * 4) = acc[j];
   }
   const uint32_t bar_base = (epoch - 1) * gridDim.x;
   if (!grid_barrier(a.bar_counter, bar_base + gridDim.x, a.timeout_ns)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }

@@ -293,8 +293,10 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
   const int p1 = min(R, p0 + kSortChunk);
   const int C = t.n_tables * t.width;
   const int nvec = t.width / 8;                      // 16-byte vectors per table row (<= 64)
-  const int64_t* k = keys + (size_t)a * R;
+  // `keys` is the raw (R, n_attr) attribute array: the sort ran on truncated 32-bit keys (half
+  // the radix passes); equal ids are still adjacent, and runs are split on the FULL 64-bit id.
   const int64_t* pm = perm + (size_t)a * R;
+  const int col = t.column[a];
   float acc[2][8];
 #pragma unroll
   for (int v = 0; v < 2; ++v)
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
   for (int p = p0; p < p1; ++p) {
     const int64_t row = pm[p];
     if (mask[row] == 0.0f) continue;
-    const int64_t key = k[p];
+    const int64_t key = keys[(size_t)row * t.n_attr + col];
     if (have && key != cur) flush();
     cur = key; have = true;
 #pragma unroll

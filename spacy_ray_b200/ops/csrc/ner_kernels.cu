@@ -89,9 +89,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (u < upl) {
-        float best = pre[u * A.nP];
+        // nP == 2 (checked by the launcher): static register indices, no local-memory array
+        float best = pre[2 * u];
         int bi = 0;
-        for (int p = 1; p < A.nP; ++p) if (pre[u * A.nP + p] > best) { best = pre[u * A.nP + p]; bi = p; }
+        if (pre[2 * u + 1] > best) { best = pre[2 * u + 1]; bi = 1; }
         const int o = lane * upl + u;
         hid_w[o] = best;
         if (A.train) {
@@ -106,16 +107,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
     bool ok[kMaxActionsPerLane];
     float mx = -3.0e38f;
     int arg = 0;
+    // upper layer: o-outer / action-inner so the per-lane accumulators are independent FMA chains
+    const int nj = (nA + 31) >> 5;
 #pragma unroll
     for (int j = 0; j < kMaxActionsPerLane; ++j) {
       const int a = lane + 32 * j;
-      sc[j] = -3.0e38f; ok[j] = false;
+      sc[j] = (j < nj && a < nA) ? bu_s[a] : 0.f;
+    }
+    for (int o = 0; o < nO; ++o) {
+      const float h = hid_w[o];
+      const float* wrow = WuT + o * A.nA_pad + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxActionsPerLane; ++j)
+        if (j < nj && lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxActionsPerLane; ++j) {
+      const int a = lane + 32 * j;
+      ok[j] = false;
       if (a < nA) {
-        float s = bu_s[a];
-        for (int o = 0; o < nO; ++o) s = fmaf(hid_w[o], WuT[o * A.nA_pad + a], s);
         ok[j] = biluo_valid(a, ent_label, is_open, not_last);
-        sc[j] = s;
-        if (ok[j] && (s > mx)) { mx = s; arg = a; }
+        if (ok[j] && (sc[j] > mx)) { mx = sc[j]; arg = a; }
+      } else {
+        sc[j] = -3.0e38f;
       }
     }
 #pragma unroll

@@ -120,7 +120,8 @@ class FusedSymmComm:
         self._hyper_host: Optional[List[float]] = None
         n_blocks = int(self.tables["blk_key"].numel())
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        self.grid = int(grid or max(1, min(sms, n_blocks if n_blocks else 1)))
+        # persistent, co-resident grid (the kernel has device-wide barriers): 2 CTAs per SM
+        self.grid = int(grid or max(1, min(2 * sms, n_blocks if n_blocks else 1)))
         self.master: Optional[torch.Tensor] = None
         self._steps_since_check = 0
 

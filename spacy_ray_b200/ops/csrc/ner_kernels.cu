@@ -3,12 +3,16 @@
 // Upstream (spaCy parser_model.pyx + _parser_internals) drives this loop from the
 // CPU: one BLAS call + one C++ state update per transition step.  Here each doc
 // gets a warp that walks its own state machine start to finish:
-//   per step: gather nF=3 precomputed feature rows (Yf) -> +bias -> maxout(nP=2)
+//   per step: sum the nF=3 precomputed feature rows (Yf) -> +bias -> maxout(nP=2)
 //             -> upper layer (W_u staged transposed in smem) -> validity mask from the
 //             state -> arg-max + masked softmax -> oracle gold action -> d_scores, loss
 //             -> advance by the predicted action.
-// The step records (feature rows, winning pieces, hidden, d_scores) are written
-// once, so the whole backward pass is three batched GEMMs + one scatter kernel.
+// The only serial dependency between steps is the tiny state, so nothing on the
+// critical path waits on global memory: gold actions / step scales are preloaded into
+// lane registers, and every feature row the NEXT step can possibly need (row i+1 slot 0,
+// row i slots 1 and 2) is prefetched while the current step computes.
+// The step records (feature rows, winning pieces, hidden, d_scores) are written once,
+// so the whole backward pass is three batched GEMMs + one scatter kernel.
 // Semantics are specified by models/transitions.py (BiluoSystem.batch_*) and
 // models/transition_model.py::_biluo_steps_reference, which the tests diff against.
 #include "common.cuh"
@@ -17,7 +21,6 @@
 namespace srb {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kMaxActionsPerLane = 8;      // nA <= 256
 
 // action a: 0 = OUT; a>0: kind = (a-1)%4 in {B,I,L,U}, label = (a-1)/4
 __device__ __forceinline__ bool biluo_valid(int a, int ent_label, bool is_open, bool not_last) {
@@ -27,14 +30,29 @@ __device__ __forceinline__ bool biluo_valid(int a, int ent_label, bool is_open, 
   return lab == ent_label && (kind == 2 || (kind == 1 && not_last));
 }
 
+template <int PPL>
+__device__ __forceinline__ void load_slot(const __nv_bfloat16* __restrict__ Yf, int row, int slot, int nOP, int lane,
+                                          float out[PPL]) {
+  const __nv_bfloat16* p = Yf + ((size_t)row * 3 + slot) * nOP + lane * PPL;
+  if (PPL == 4) {
+    const uint2 raw = *(const uint2*)p;
+    const __nv_bfloat162 lo = *(const __nv_bfloat162*)&raw.x, hi = *(const __nv_bfloat162*)&raw.y;
+    out[0] = __low2float(lo); out[1] = __high2float(lo); out[2] = __low2float(hi); out[3] = __high2float(hi);
+  } else {
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) out[k] = bf2f(p[k]);
+  }
+}
+
+// NJ = ceil(nA / 32) actions per lane, PPL = nO*nP/32 pre-activations per lane (nP == 2).
+template <int NJ, int PPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nO = A.nO, nOP = A.nO * A.nP, nA = A.nA;
+  constexpr int UPL = PPL / 2;
+  const int nO = A.nO, nOP = A.nO * 2, nA = A.nA;
   float* WuT = (float*)smem_raw;                                  // [nO][nA_pad]
   float* bu_s = WuT + (size_t)nO * A.nA_pad;                      // [nA_pad]
-  float* bias_s = bu_s + A.nA_pad;                                // [nOP]
-  float* pad_s = bias_s + nOP;                                    // [3][nOP]
-  float* hid_s = pad_s + 3 * nOP;                                 // [warps][nO]
+  float* hid_s = bu_s + A.nA_pad;                                 // [warps][nO]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* Wu = (const __nv_bfloat16*)A.Wu;
   for (int i = threadIdx.x; i < nO * A.nA_pad; i += blockDim.x) {
@@ -43,8 +61,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
   }
   for (int i = threadIdx.x; i < A.nA_pad; i += blockDim.x)
     bu_s[i] = i < nA ? bf2f(((const __nv_bfloat16*)A.bu)[i]) : 0.f;
-  for (int i = threadIdx.x; i < nOP; i += blockDim.x) bias_s[i] = bf2f(((const __nv_bfloat16*)A.b)[i]);
-  for (int i = threadIdx.x; i < 3 * nOP; i += blockDim.x) pad_s[i] = bf2f(((const __nv_bfloat16*)A.pad)[i]);
   __syncthreads();
 
   const int d = blockIdx.x * kWarpsPerBlock + warp;
@@ -54,109 +70,117 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
   const int tok0 = A.tok_off[d];
   const __nv_bfloat16* Yf = (const __nv_bfloat16*)A.Yf;
   float* hid_w = hid_s + warp * nO;
-  // each lane owns pre-activations [lane*PPL, lane*PPL+PPL): with nP=2 that is whole units
-  const int ppl = nOP / 32;            // 4 for nO=64,nP=2
-  const int upl = nO / 32;             // 2
+  // per-lane constants: bias and the two pad vectors for this lane's pre-activations
+  float bias_r[PPL], pad12[PPL];
+#pragma unroll
+  for (int k = 0; k < PPL; ++k) {
+    bias_r[k] = bf2f(((const __nv_bfloat16*)A.b)[lane * PPL + k]);
+    pad12[k] = bf2f(((const __nv_bfloat16*)A.pad)[1 * nOP + lane * PPL + k]) +
+               bf2f(((const __nv_bfloat16*)A.pad)[2 * nOP + lane * PPL + k]);
+  }
+  // gold actions and per-step scales of the first 64 steps live in lane registers
+  const bool have_gold = A.gold != nullptr;
+  int g_lo = -2, g_hi = -2;
+  float sc_lo = 0.f, sc_hi = 0.f;
+  if (have_gold) {
+    g_lo = lane < n ? A.gold[tok0 + lane] : -1;
+    g_hi = lane + 32 < n ? A.gold[tok0 + 32 + lane] : -1;
+  }
+  if (A.train) {
+    sc_lo = lane < n ? A.inv_active[lane] : 0.f;
+    sc_hi = lane + 32 < n ? A.inv_active[lane + 32] : 0.f;
+  }
   int ent_start = -1, ent_label = -1;
   bool ent_ok = false;
   float loss_acc = 0.f;
+  // feature vectors: nx0 = slot 0 of the current row; e1 = slot 1 of the open entity's first
+  // row; l2 = slot 2 of the previous row (only meaningful while an entity is open)
+  float nx0[PPL], e1[PPL], l2[PPL];
+#pragma unroll
+  for (int k = 0; k < PPL; ++k) { e1[k] = 0.f; l2[k] = 0.f; }
+  if (n > 0) load_slot<PPL>(Yf, row0, 0, nOP, lane, nx0);
 
   for (int i = 0; i < n; ++i) {
     const bool is_open = ent_start >= 0;
     const bool not_last = (i + 1) < n;
     const int f0 = row0 + i;
-    const int f1 = is_open ? row0 + ent_start : -1;
-    const int f2 = is_open ? f0 - 1 : -1;
-    // ---- hidden = maxout(b + sum_f Yf[row_f, f] | pad[f]) -----------------------------
-    float pre[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) if (k < ppl) pre[k] = bias_s[lane * ppl + k];
-    {
-      const __nv_bfloat16* p0 = Yf + ((size_t)f0 * 3 + 0) * nOP + lane * ppl;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (k < ppl) pre[k] += bf2f(p0[k]);
-      if (f1 >= 0) {
-        const __nv_bfloat16* p1 = Yf + ((size_t)f1 * 3 + 1) * nOP + lane * ppl;
-        const __nv_bfloat16* p2 = Yf + ((size_t)f2 * 3 + 2) * nOP + lane * ppl;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < ppl) pre[k] += bf2f(p1[k]) + bf2f(p2[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < ppl) pre[k] += pad_s[1 * nOP + lane * ppl + k] + pad_s[2 * nOP + lane * ppl + k];
-      }
+    // prefetch everything the next step can need; none of it depends on this step's action
+    float pn0[PPL], c1[PPL], c2[PPL];
+    if (not_last) {
+      load_slot<PPL>(Yf, f0 + 1, 0, nOP, lane, pn0);
+      load_slot<PPL>(Yf, f0, 1, nOP, lane, c1);
+      load_slot<PPL>(Yf, f0, 2, nOP, lane, c2);
     }
+    // ---- hidden = maxout(b + slot0 + (open ? e1 + l2 : pad1 + pad2)) -----------------------
+    float pre[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) pre[k] = bias_r[k] + nx0[k] + (is_open ? (e1[k] + l2[k]) : pad12[k]);
     const size_t tok = (size_t)tok0 + i;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (u < upl) {
-        // nP == 2 (checked by the launcher): static register indices, no local-memory array
-        float best = pre[2 * u];
-        int bi = 0;
-        if (pre[2 * u + 1] > best) { best = pre[2 * u + 1]; bi = 1; }
-        const int o = lane * upl + u;
-        hid_w[o] = best;
-        if (A.train) {
-          A.which[tok * nO + o] = (uint8_t)bi;
-          ((__nv_bfloat16*)A.hid)[tok * nO + o] = f2bf(best);
-        }
+    for (int u = 0; u < UPL; ++u) {
+      float best = pre[2 * u];
+      int bi = 0;
+      if (pre[2 * u + 1] > best) { best = pre[2 * u + 1]; bi = 1; }
+      const int o = lane * UPL + u;
+      hid_w[o] = best;
+      if (A.train) {
+        A.which[tok * nO + o] = (uint8_t)bi;
+        ((__nv_bfloat16*)A.hid)[tok * nO + o] = f2bf(best);
       }
     }
     __syncwarp();
-    // ---- scores, validity, arg-max -----------------------------------------------------
-    float sc[kMaxActionsPerLane];
-    bool ok[kMaxActionsPerLane];
-    float mx = -3.0e38f;
-    int arg = 0;
-    // upper layer: o-outer / action-inner so the per-lane accumulators are independent FMA chains
-    const int nj = (nA + 31) >> 5;
+    // ---- upper layer: o-outer / action-inner (NJ independent FMA chains per lane) ---------
+    float sc[NJ];
 #pragma unroll
-    for (int j = 0; j < kMaxActionsPerLane; ++j) {
-      const int a = lane + 32 * j;
-      sc[j] = (j < nj && a < nA) ? bu_s[a] : 0.f;
-    }
+    for (int j = 0; j < NJ; ++j) sc[j] = bu_s[lane + 32 * j < A.nA_pad ? lane + 32 * j : 0];
+#pragma unroll 4
     for (int o = 0; o < nO; ++o) {
       const float h = hid_w[o];
       const float* wrow = WuT + o * A.nA_pad + lane;
 #pragma unroll
-      for (int j = 0; j < kMaxActionsPerLane; ++j)
-        if (j < nj && lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
+      for (int j = 0; j < NJ; ++j)
+        if (j < NJ - 1 || lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
     }
+    bool ok[NJ];
+    float mx = -3.0e38f;
+    int arg = 0;
 #pragma unroll
-    for (int j = 0; j < kMaxActionsPerLane; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int a = lane + 32 * j;
-      ok[j] = false;
-      if (a < nA) {
-        ok[j] = biluo_valid(a, ent_label, is_open, not_last);
-        if (ok[j] && (sc[j] > mx)) { mx = sc[j]; arg = a; }
-      } else {
-        sc[j] = -3.0e38f;
-      }
+      ok[j] = a < nA && biluo_valid(a, ent_label, is_open, not_last);
+      if (ok[j] && sc[j] > mx) { mx = sc[j]; arg = a; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      float om = __shfl_xor_sync(0xffffffffu, mx, o);
-      int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
       if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
     }
-    const int g = A.gold ? A.gold[tok] : -2;
+    int g = -2;
+    if (have_gold) {
+      if (i < 64) g = __shfl_sync(0xffffffffu, i < 32 ? g_lo : g_hi, i & 31);
+      else g = A.gold[tok];
+    }
     if (A.train) {
       // oracle: a single zero-cost action, or -1 = every valid action is zero-cost
       int ga = -1;
-      if (A.gold && g >= 0) {
+      if (have_gold && g >= 0) {
         const int gk = g > 0 ? ((g - 1) & 3) : -1, gl = g > 0 ? ((g - 1) >> 2) : -1;
         if (!is_open) ga = (gk == -1 || gk == 0 || gk == 3) ? g : 0;
         else if (ent_ok && (gk == 1 || gk == 2) && gl == ent_label) ga = g;
       }
       if (ga >= 0 && !biluo_valid(ga, ent_label, is_open, not_last)) ga = -1;
+      float e[NJ];
       float sum = 0.f;
-      float e[kMaxActionsPerLane];
 #pragma unroll
-      for (int j = 0; j < kMaxActionsPerLane; ++j) { e[j] = ok[j] ? __expf(sc[j] - mx) : 0.f; sum += e[j]; }
+      for (int j = 0; j < NJ; ++j) { e[j] = ok[j] ? __expf(sc[j] - mx) : 0.f; sum += e[j]; }
       sum = warp_sum(sum);
       const float inv = 1.f / sum;
-      const float scale = A.inv_active[i];
+      float scale;
+      if (i < 64) scale = __shfl_sync(0xffffffffu, i < 32 ? sc_lo : sc_hi, i & 31);
+      else scale = A.inv_active[i];
 #pragma unroll
-      for (int j = 0; j < kMaxActionsPerLane; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int a = lane + 32 * j;
         if (a < A.nA_pad) {
           float dv = 0.f;
@@ -165,14 +189,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
           ((__nv_bfloat16*)A.d_scores)[tok * A.nA_pad + a] = f2bf(dv);
         }
       }
-      if (lane < 3) A.feats[tok * 3 + lane] = lane == 0 ? f0 : (lane == 1 ? f1 : f2);
+      if (lane < 3) {
+        const int f1 = is_open ? row0 + ent_start : -1;
+        A.feats[tok * 3 + lane] = lane == 0 ? f0 : (lane == 1 ? f1 : (is_open ? f0 - 1 : -1));
+      }
     }
     if (lane == 0) A.actions[tok] = arg;
-    // ---- advance by the predicted action ----------------------------------------------
+    // ---- advance by the predicted action ------------------------------------------------
     const int kind = arg > 0 ? ((arg - 1) & 3) : -1;
-    if (kind == 0) { ent_start = i; ent_label = (arg - 1) >> 2; ent_ok = (g == arg); }
-    else if (kind == 1) { ent_ok = ent_ok && (g == arg); }
-    else { ent_start = -1; ent_label = -1; ent_ok = false; }
+    if (kind == 0) {
+      ent_start = i; ent_label = (arg - 1) >> 2; ent_ok = (g == arg);
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) e1[k] = c1[k];
+    } else if (kind == 1) {
+      ent_ok = ent_ok && (g == arg);
+    } else {
+      ent_start = -1; ent_label = -1; ent_ok = false;
+    }
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) { nx0[k] = pn0[k]; l2[k] = c2[k]; }
     __syncwarp();
   }
   if (A.train) {
@@ -181,14 +216,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
   }
 }
 
+template <int NJ>
+static void launch_nj(const BiluoArgs& a, int blocks, size_t smem, cudaStream_t s) {
+  const int ppl = a.nO * 2 / 32;
+#define SRB_PPL(P)                                                                                              \
+  if (ppl == P) {                                                                                               \
+    if (smem > 48 * 1024)                                                                                       \
+      cudaFuncSetAttribute(biluo_steps_kernel<NJ, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    biluo_steps_kernel<NJ, P><<<blocks, kWarpsPerBlock * 32, smem, s>>>(a);                                     \
+    return;                                                                                                     \
+  }
+  SRB_PPL(2) SRB_PPL(4) SRB_PPL(8)
+#undef SRB_PPL
+}
+
 void launch_biluo_steps(BiluoArgs a, cudaStream_t s) {
   if (a.B <= 0) return;
-  const int nOP = a.nO * a.nP;
-  size_t smem = sizeof(float) * ((size_t)a.nO * a.nA_pad + a.nA_pad + nOP + 3 * nOP + kWarpsPerBlock * a.nO);
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(biluo_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = sizeof(float) * ((size_t)a.nO * a.nA_pad + a.nA_pad + kWarpsPerBlock * a.nO);
   int blocks = (a.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  biluo_steps_kernel<<<blocks, kWarpsPerBlock * 32, smem, s>>>(a);
+  const int nj = (a.nA_pad + 31) / 32;
+  switch (nj) {
+    case 1: launch_nj<1>(a, blocks, smem, s); break;
+    case 2: launch_nj<2>(a, blocks, smem, s); break;
+    case 3: launch_nj<3>(a, blocks, smem, s); break;
+    case 4: launch_nj<4>(a, blocks, smem, s); break;
+    case 5: launch_nj<5>(a, blocks, smem, s); break;
+    case 6: launch_nj<6>(a, blocks, smem, s); break;
+    case 7: launch_nj<7>(a, blocks, smem, s); break;
+    default: launch_nj<8>(a, blocks, smem, s); break;
+  }
 }
 
 // Backward scatter: one warp per recorded step.

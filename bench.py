@@ -97,8 +97,8 @@ max_steps = 0
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl-baseline", "rayproxy-emu"])
     ap.add_argument("--docs-per-gpu", type=int, default=1024)
     ap.add_argument("--width", type=int, default=256)

@@ -115,6 +115,7 @@ class Trainer:
         self.dropout = float(dropout)
         self.B = int(docs_per_batch)
         self.store = ExampleStore(examples, self.ner)
+        self._doc_index = {id(eg.reference): i for i, eg in enumerate(examples)}
         self.bucket_rows = int(bucket_rows)
         rows_cap = _align(self.B * self.store.max_len + self.B + 1, self.bucket_rows)
         self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64))
@@ -157,6 +158,10 @@ class Trainer:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         rows = native.collate(st.attrs, st.doc_off, ids, a["attrs"], a["mask"], a["starts"], a["lens"])
         words = native.collate_gold(st.gold, st.doc_off, ids, a["gold"], a["tok_off"])
+        if len(ids) < self.B:                       # partial batch: the unused doc slots are empty docs
+            a["lens"][len(ids):] = 0
+            a["starts"][len(ids):] = 0
+            a["tok_off"][len(ids):] = 0
         lens = a["lens"][: len(ids)]
         counts = (lens[None, :] > np.arange(self.lay.lmax, dtype=np.int32)[:, None]).sum(axis=1)
         a["inv_active"][:] = 1.0 / np.maximum(counts, 1)
@@ -280,6 +285,31 @@ class Trainer:
         if ids is not None:
             self.prepare(ids)
         return float(self.step_async().item())
+
+    def ids_for(self, examples: Sequence[Any]) -> Optional[np.ndarray]:
+        """Store indices of ``examples`` (matched by the identity of their reference Doc), or
+        None if any of them is not part of the store / the batch exceeds the staging capacity."""
+        if len(examples) > self.B:
+            return None
+        idx = self._doc_index
+        out = np.empty(len(examples), dtype=np.int64)
+        for i, eg in enumerate(examples):
+            j = idx.get(id(eg.reference))
+            if j is None:
+                return None
+            out[i] = j
+        if self.rows_for(out) > self.lay.rows:
+            return None
+        return out
+
+    def update_examples(self, examples: Sequence[Any]) -> Optional[torch.Tensor]:
+        """``nlp.update`` fast path: returns the loss tensor (no host sync), or None when the
+        batch cannot be served from the store (the caller then takes the generic path)."""
+        ids = self.ids_for(examples)
+        if ids is None:
+            return None
+        self.prepare(ids)
+        return self.step_async()
 
     def batches(self, n: int, seed: int = 0) -> List[np.ndarray]:
         rng = np.random.default_rng(seed)

@@ -311,6 +311,15 @@ class Language:
             if self._optimizer is None:
                 self._optimizer = self.create_optimizer()
             sgd = self._optimizer
+        trainer = getattr(self, "_trainer", None)
+        if trainer is not None and sgd is False and not annotates and not exclude:
+            # device-resident fast path (engine.Trainer): native collate -> one H2D copy ->
+            # CUDA-graph replay of forward+backward+gradient exchange+optimizer
+            loss = trainer.update_examples(examples)
+            if loss is not None:
+                C._add_loss(losses, trainer.ner.name, loss)
+                self._trainer_stepped = True
+                return losses
         batch = self.make_batch([eg.predicted for eg in examples])
         for name, comp in self.pipeline:
             if name in exclude or not getattr(comp, "is_trainable", False):

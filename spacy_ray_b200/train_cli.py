@@ -187,6 +187,7 @@ def ray_train(
             errors = [e for e in ray.get([w.get_error.remote() for w in workers]) if e]
             if errors:
                 raise RuntimeError("worker failed:\n" + "\n".join(errors))
+        return ray.get([w.get_stats.remote() for w in workers])     # per-rank throughput / message counters
     finally:
         ray.shutdown()
 

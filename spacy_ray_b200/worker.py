@@ -113,6 +113,7 @@ class Worker:
         self._error: Optional[str] = None
         self._last_info: Optional[Dict[str, Any]] = None
         self._eval_index = 0
+        self._stats: Dict[str, Any] = {"steps": 0, "skip": 3, "docs": 0, "words": 0, "t0": 0.0, "t1": 0.0}
         self._dist_ready = False
         self.n_grads_used = 0
         self.n_grads_discarded = 0
@@ -296,10 +297,15 @@ class Worker:
         )
         after_step = None
         if isinstance(self.proxy, ShardedSyncProxy):
+            self._maybe_install_trainer()
+
             def after_step(step: int) -> None:
                 if self.inject_fault and self.inject_fault == f"{self.rank}:{step}":
                     raise RuntimeError(f"injected fault on rank {self.rank} at step {step}")
-                self.proxy.step()
+                if getattr(self.nlp, "_trainer_stepped", False):
+                    self.nlp._trainer_stepped = False      # exchange + optimizer ran inside the graph
+                else:
+                    self.proxy.step()
         self.training_step_iterator = train_while_improving(
             self.nlp,
             FakeOptimizer(self.optimizer),
@@ -326,6 +332,33 @@ class Worker:
         )
         self.thread.start()
 
+    def _maybe_install_trainer(self) -> None:
+        """On the B200 backend with the fused comm, serve ``nlp.update`` from the
+        device-resident engine when the pipeline is one it supports (a single NER head
+        today).  ``SRB_FAST_PATH=0`` keeps the generic per-op path."""
+        ops = get_current_ops()
+        if os.environ.get("SRB_FAST_PATH", "1") == "0" or not getattr(ops, "fused", False):
+            return
+        if getattr(self.proxy.comm, "name", "") != "fused":
+            return
+        pipes = [(n, c) for n, c in self.nlp.pipeline if getattr(c, "is_trainable", False)]
+        if len(pipes) != 1 or pipes[0][1].__class__.__name__ != "EntityRecognizer":
+            return
+        if set(self.T["frozen_components"]) or set(self.T["annotating_components"]):
+            return
+        try:
+            from .engine import Trainer
+
+            examples = list(self.train_corpus(self.nlp))
+            if not examples:
+                return
+            cap = int(os.environ.get("SRB_FAST_PATH_MAX_DOCS", 2048))
+            self.nlp._trainer = Trainer(self.nlp, self.proxy, examples, docs_per_batch=min(cap, len(examples)),
+                                        dropout=float(self.T["dropout"]), component=pipes[0][0], prefetch=False)
+            logger.info("rank %d: device-resident training engine enabled", self.rank)
+        except Exception as e:       # never fatal: the generic path is always available
+            logger.warning("rank %d: fast path unavailable (%s); using the generic path", self.rank, e)
+
     def _thread_main(self, iterator, print_row) -> None:
         try:
             thread_training(
@@ -341,8 +374,31 @@ class Worker:
 
     def _on_step(self, batch, info, is_best_checkpoint) -> None:
         self._last_info = info
+        now = time.perf_counter()
+        st = self._stats
+        if st["steps"] == st["skip"]:               # start the clock after the warm-up steps
+            st["t0"], st["docs"], st["words"] = now, 0, 0
+        elif st["steps"] > st["skip"]:
+            st["docs"] += len(batch)
+            st["words"] += sum(len(eg) for eg in batch)
+            st["t1"] = now
+        st["steps"] += 1
         if is_best_checkpoint and self.output_path is not None:
             self.save_checkpoint(info, self.output_path / "model-best")
+
+    def get_stats(self) -> Dict[str, Any]:
+        """Wall-clock throughput of this rank's training thread (steps after the first few)."""
+        st = dict(self._stats)
+        dt = max(st.get("t1", 0.0) - st.get("t0", 0.0), 1e-9)
+        st["seconds"] = dt
+        st["docs_per_sec"] = st["docs"] / dt
+        st["words_per_sec"] = st["words"] / dt
+        proxy = self.proxy
+        st["grads_used"] = getattr(proxy, "n_grads_used", None)
+        st["grads_discarded"] = getattr(proxy, "n_grads_discarded", None)
+        st["msgs_sent"] = getattr(proxy, "n_msgs_sent", None)
+        st["bytes_sent"] = getattr(proxy, "bytes_sent", None)
+        return st
 
     def _call(self, method, *args):
         rem = getattr(method, "remote", None)

@@ -321,3 +321,31 @@ def test_gpu_training_loss_goes_down_and_uses_native_kernels():
     assert sum(hist[-5:]) < 0.5 * sum(hist[:5]), hist[::6]
     scores = nlp.evaluate(exs[:100])
     assert scores["ents_f"] > 0.25, scores
+
+
+def test_worker_training_loop_uses_the_device_resident_engine(tmp_path):
+    """CLI-level path on the GPU: Worker.train() -> train_while_improving -> nlp.update is served by
+    engine.Trainer (native collate, one H2D copy, CUDA-graph replay incl. the fused comm kernel)."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.worker import Worker
+
+    text = multi_cfg(["ner"], width=64, depth=2, n_docs=600, max_len=16, hidden=64)
+    text = text.replace("max_steps = 10", "max_steps = 40").replace("eval_frequency = 5", "eval_frequency = 20")
+    text = text.replace("dropout = 0.0", "dropout = 0.1")
+    text += """
+[training.batcher]
+@batchers = "spacy.batch_by_sequence.v1"
+size = 64
+"""
+    w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0, output_path=tmp_path)
+    w.set_proxy(None)
+    w.train(None, None)
+    w.join(timeout=300)
+    assert w.get_error() is None
+    trainer = getattr(w.nlp, "_trainer", None)
+    assert trainer is not None and trainer.steps >= 39, "fast path was not used"
+    assert len(trainer._graphs) >= 1                      # at least one bucket was captured and replayed
+    assert (tmp_path / "model-last" / "ner" / "model").exists()
+    stats = w.get_stats()
+    assert stats["docs"] > 0 and stats["docs_per_sec"] > 0

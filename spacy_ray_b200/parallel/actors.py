@@ -256,7 +256,13 @@ class _RemoteClass:
             devices = visible.split(",") if visible else None
             gpu = rt.gpu_cursor
             rt.gpu_cursor += 1
-            env["CUDA_VISIBLE_DEVICES"] = devices[gpu % len(devices)] if devices else str(gpu)
+            if self._options.get("isolate_gpu", False):
+                # Ray-style isolation: the actor sees exactly one device (index 0)
+                env["CUDA_VISIBLE_DEVICES"] = devices[gpu % len(devices)] if devices else str(gpu)
+            else:
+                # All devices stay visible (CUDA symmetric memory / NVLink peer mappings need every
+                # rank to address a *distinct* device ordinal); the actor is told which one is its own.
+                env["SRB_ASSIGNED_GPU"] = str(gpu % len(devices) if devices else gpu)
         payload = pickle.dumps((self._cls, args, kwargs))
         proc = _CTX.Process(
             target=_actor_main, args=(rt.pool, index, payload, env), daemon=True,

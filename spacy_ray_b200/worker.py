@@ -445,6 +445,9 @@ class Worker:
             # like Ray's isolation; under torchrun all devices are visible and
             # ``use_gpu`` is the local rank.
             local = 0 if ("," not in visible and visible != "") else int(use_gpu)
+            assigned = os.environ.get("SRB_ASSIGNED_GPU")
+            if assigned is not None:          # actor runtime: all devices visible, this one is ours
+                local = gpu_id = int(assigned)
             logger.info("Using GPU (isolated): %s", gpu_id)
             require_gpu(local, fused=fused_ops)
             return gpu_id

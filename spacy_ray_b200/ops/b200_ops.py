@@ -64,6 +64,8 @@ class B200Ops(TorchOps):
         env_dw = os.environ.get("SRB_TC_DW")
         self.tc_dw = (env_dw != "0") if tc_dw is None else tc_dw
         self.sorted_embed_bwd = os.environ.get("SRB_SORTED_EMBED", "1") != "0"
+        # 2 = thread-block clusters of 2 CTAs sharing the weight operand by TMA multicast
+        self.gemm_cluster = int(os.environ.get("SRB_GEMM_CLUSTER", "2"))
         self.launches = 0            # our kernels launched (bench.py reports this)
         # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
         # replays draw fresh masks although the per-call seeds were baked in at capture time
@@ -76,9 +78,10 @@ class B200Ops(TorchOps):
 
     def tc_gemm(self, A, B, out, *, mode, epi, block_n, M, N, K, a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,),
                 b_col_off=(0,), splits=1, win_w=0, bias=None, which=None, add_src=None, row_scale=None, m_dev=None,
-                max_ctas=0) -> None:
+                max_ctas=0, cluster=None) -> None:
         self.k.tc_gemm(A, B, out, mode, epi, block_n, M, N, K, list(a_row_shift), list(a_col_off), list(b_row_off),
-                       list(b_col_off), splits, win_w, bias, which, add_src, row_scale, m_dev, max_ctas)
+                       list(b_col_off), splits, win_w, bias, which, add_src, row_scale, m_dev, max_ctas,
+                       self.gemm_cluster if cluster is None else cluster)
         self.launches += 1
 
     @staticmethod

@@ -26,7 +26,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
              std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off, int64_t splits, int64_t win_w,
              const c10::optional<Tensor>& bias, const c10::optional<Tensor>& which,
              const c10::optional<Tensor>& add_src, const c10::optional<Tensor>& row_scale,
-             const c10::optional<Tensor>& m_dev, int64_t max_ctas) {
+             const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && out.is_cuda());
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "tc_gemm: bf16 operands");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "tc_gemm: row-major 2D operands");
@@ -37,12 +37,14 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   TORCH_CHECK(n_shifts >= 1 && n_shifts <= 3 && a_col_off.size() == a_row_shift.size() &&
               b_row_off.size() == a_row_shift.size() && b_col_off.size() == a_row_shift.size());
   c10::cuda::CUDAGuard guard(A.device());
+  if (cluster != 2 || !gemm_supports_cluster((int)block_n, (int)mode, (int)epi)) cluster = 1;
   CUtensorMap ta, tb;
   int r1, r2;
   if (mode == MODE_KK) {
     r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);
+    // with a 2-CTA cluster each CTA loads (and multicasts) half of the B rows of a tile
     r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64,
-                           (uint32_t)block_n);
+                           (uint32_t)(block_n / cluster));
   } else {
     TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major mode needs block_n % 64 == 0");
     r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 64);
@@ -75,7 +77,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   p.row_scale = row_scale.has_value() && row_scale->defined() ? row_scale->data_ptr<float>() : nullptr;
   int sms = num_sms_for(A.get_device());
   if (max_ctas > 0 && max_ctas < sms) sms = (int)max_ctas;
-  cudaError_t e = launch_gemm(ta, tb, p, (int)block_n, (int)mode, (int)epi, sms,
+  cudaError_t e = launch_gemm(ta, tb, p, (int)block_n, (int)mode, (int)epi, (int)cluster, sms,
                               at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(e == cudaSuccess, "tc_gemm launch failed: ", cudaGetErrorString(e), " (block_n=", block_n,
               " mode=", mode, " epi=", epi, ")");
@@ -87,7 +89,7 @@ void register_gemm_ops(torch::Library& m) {
   m.def(
       "tc_gemm(Tensor A, Tensor B, Tensor(a!) out, int mode, int epi, int block_n, int M, int N, int K, "
       "int[] a_row_shift, int[] a_col_off, int[] b_row_off, int[] b_col_off, int splits, int win_w, "
-      "Tensor? bias, Tensor? which, Tensor? add_src, Tensor? row_scale, Tensor? m_dev, int max_ctas) -> ()");
+      "Tensor? bias, Tensor? which, Tensor? add_src, Tensor? row_scale, Tensor? m_dev, int max_ctas, int cluster) -> ()");
 }
 void register_gemm_impls(torch::Library& m) { m.impl("tc_gemm", tc_gemm); }
 

@@ -31,8 +31,11 @@ struct GemmParams {
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
+// cluster: 1, or 2 = pairs of CTAs on adjacent M tiles sharing the B operand by TMA multicast
+// (the B tensor map must then be encoded with box rows block_n / 2).
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
-                        int num_sms, cudaStream_t s);
+                        int cluster, int num_sms, cudaStream_t s);
+bool gemm_supports_cluster(int block_n, int mode, int epi);
 int gemm_block_k();
 
 }  // namespace srb

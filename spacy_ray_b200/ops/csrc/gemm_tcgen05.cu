@@ -45,7 +45,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BLOCK_N, int MODE, int EPI>
+// CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically
+// adjacent M tiles of the SAME N tile / K range in lockstep and share the B (weight) operand:
+// each CTA TMA-loads half of the B tile and multicasts it into both CTAs' shared memory, so B
+// crosses L2 -> SM once per cluster instead of once per CTA (the single-CTA kernels measured
+// ~55-60 % tensor-pipe activity with L2 -> smem traffic as the limiter).
+template <int BLOCK_N, int MODE, int EPI, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using C = Cfg<BLOCK_N>;
@@ -66,20 +71,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
   const int total_kb = (MODE == MODE_KK ? p.n_shifts : 1) * kpb;
   const int splits = p.splits > 0 ? p.splits : 1;
-  const int total_items = m_tiles * n_tiles * splits;
+  const int m_groups = (m_tiles + CL - 1) / CL;              // a cluster takes CL vertically adjacent M tiles
+  const int total_items = m_groups * n_tiles * splits;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int first_item = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int item_stride = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -87,10 +97,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================================ TMA producer =====================================
     if (elect_one()) {
       int stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BLOCK_N;
-        if (m0 >= M) continue;
+        const int mg = tile / n_tiles;
+        const int m0 = (mg * CL + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BLOCK_N;
+        if (mg * CL * BM >= M) continue;                       // decided per cluster, not per CTA
         const int kb0 = (int)((long long)total_kb * split / splits), kb1 = (int)((long long)total_kb * (split + 1) / splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
@@ -100,16 +111,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (MODE == MODE_KK) {
             const int s = kb / kpb, kk = kb - s * kpb;
             tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
-            tma_load_2d(b_dst, &tmB, full_bar + stage, p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s]);
+            if (CL == 1) {
+              tma_load_2d(b_dst, &tmB, full_bar + stage, p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s]);
+            } else {       // my half of the B rows, delivered to every CTA of the cluster
+              constexpr int kHalfRows = BLOCK_N / CL;
+              tma_load_2d_mcast(b_dst + cta_rank * (kHalfRows * BK * 2), &tmB, full_bar + stage,
+                                p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s] + (int)cta_rank * kHalfRows, kMask);
+            }
           } else {
             const int t0 = kb * BK;
             int c0 = n0, tshift = 0;
             if (p.win_w > 0) { const int s = n0 / p.win_w; c0 = n0 - s * p.win_w; tshift = s - 1; }
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * (BK * 128), &tmA, full_bar + stage, m0 + j * 64, t0);
+            if (CL == 1) {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, t0 + tshift);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, t0 + tshift);
+            } else {       // my share of the 64-column atoms, multicast to the cluster
+              constexpr int kAtoms = BLOCK_N / 64 / CL;
+#pragma unroll
+              for (int jj = 0; jj < kAtoms; ++jj) {
+                const int j = (int)cta_rank * kAtoms + jj;
+                tma_load_2d_mcast(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, t0 + tshift, kMask);
+              }
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -120,10 +146,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BLOCK_N, MODE == MODE_MNMN, MODE == MODE_MNMN);
       int stage = 0, phase = 0, it = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
-        const int m0 = (tile / n_tiles) * BM;
-        if (m0 >= M) continue;
+        const int mg = tile / n_tiles;
+        if (mg * CL * BM >= M) continue;
         const int kb0 = (int)((long long)total_kb * split / splits), kb1 = (int)((long long)total_kb * (split + 1) / splits);
         const int acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
@@ -146,7 +172,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage);
+          if (CL == 1) umma_commit(empty_bar + stage);
+          else umma_commit_mcast(empty_bar + stage, kMask);     // frees the stage in every CTA of the cluster
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tmem_full + acc);
@@ -157,10 +184,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================================ epilogue =========================================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
     int it = 0;
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    for (int w = first_item; w < total_items; w += item_stride) {
       const int tile = w / splits;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BLOCK_N;
-      if (m0 >= M) continue;
+      const int mg = tile / n_tiles;
+      const int m0 = (mg * CL + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BLOCK_N;
+      if (mg * CL * BM >= M) continue;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
@@ -240,7 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while a peer may still write to it
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
@@ -277,42 +305,66 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N, int MODE, int EPI>
-static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int grid, cudaStream_t s) {
+template <int BLOCK_N, int MODE, int EPI, int CL>
+static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int num_sms, cudaStream_t s) {
   using C = Cfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_kernel<BLOCK_N, MODE, EPI><<<grid, kNumThreads, C::kSmemBytes, s>>>(a, b, p);
-  return cudaGetLastError();
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BLOCK_N;
+  const int m_groups = (m_tiles + CL - 1) / CL;
+  const int items = m_groups * n_tiles * (p.splits > 0 ? p.splits : 1);
+  int clusters = num_sms / CL;
+  if (items < clusters) clusters = items;
+  if (clusters <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL>, a, b, p);
 }
 
 int gemm_block_k() { return BK; }
 
+bool gemm_supports_cluster(int block_n, int mode, int epi) {
+  if (mode == MODE_KK && (epi == EPI_STORE) && (block_n == 256 || block_n == 192 || block_n == 128)) return true;
+  if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
+  if (mode == MODE_MNMN && epi == EPI_ATOMIC_F32 && (block_n == 256 || block_n == 128)) return true;
+  return false;
+}
+
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
-                        int num_sms, cudaStream_t s) {
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / block_n;
-  const int items = m_tiles * n_tiles * (p.splits > 0 ? p.splits : 1);
-  int grid = items < num_sms ? items : num_sms;
-  if (grid <= 0) return cudaSuccess;
-#define SRB_CASE(BN, MD, EP) \
-  if (block_n == BN && mode == MD && epi == EP) return launch_one<BN, MD, EP>(a, b, p, grid, s);
+                        int cluster, int num_sms, cudaStream_t s) {
+#define SRB_CASE(BN, MD, EP)                                                              \
+  if (block_n == BN && mode == MD && epi == EP) {                                         \
+    if (cluster == 2) return launch_one<BN, MD, EP, 2>(a, b, p, num_sms, s);              \
+    return launch_one<BN, MD, EP, 1>(a, b, p, num_sms, s);                                \
+  }
+#define SRB_CASE1(BN, MD, EP) \
+  if (block_n == BN && mode == MD && epi == EP) return launch_one<BN, MD, EP, 1>(a, b, p, num_sms, s);
   SRB_CASE(256, MODE_KK, EPI_STORE)
   SRB_CASE(192, MODE_KK, EPI_STORE)
   SRB_CASE(128, MODE_KK, EPI_STORE)
-  SRB_CASE(64, MODE_KK, EPI_STORE)
+  SRB_CASE1(64, MODE_KK, EPI_STORE)
   SRB_CASE(192, MODE_KK, EPI_MAXOUT3)
-  SRB_CASE(96, MODE_KK, EPI_MAXOUT3)
+  SRB_CASE1(96, MODE_KK, EPI_MAXOUT3)
   SRB_CASE(256, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE(128, MODE_MNMN, EPI_ATOMIC_F32)
-  SRB_CASE(64, MODE_MNMN, EPI_ATOMIC_F32)
-  SRB_CASE(256, MODE_KK, EPI_ATOMIC_F32)
-  SRB_CASE(128, MODE_KK, EPI_ATOMIC_F32)
+  SRB_CASE1(64, MODE_MNMN, EPI_ATOMIC_F32)
+  SRB_CASE1(256, MODE_KK, EPI_ATOMIC_F32)
+  SRB_CASE1(128, MODE_KK, EPI_ATOMIC_F32)
 #undef SRB_CASE
+#undef SRB_CASE1
   return cudaErrorInvalidValue;
 }
 

@@ -66,13 +66,14 @@ def test_hash_embed_fwd_bwd(ops, ref):
 # ---------------------------------------------------------------------------- tcgen05 GEMMs
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 256, 256, 256), (1000, 768, 192, 192),
                                       (257, 64, 128, 64), (4096, 384, 64, 128)])
-def test_tc_gemm_plain_nt(ops, M, N, K, bn):
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_tc_gemm_plain_nt(ops, M, N, K, bn, cluster):
     torch.manual_seed(1)
     A = torch.randn(M, K, device="cuda").bfloat16()
     B = torch.randn(N, K, device="cuda").bfloat16()
     bias = torch.randn(N, device="cuda").bfloat16()
     out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.tc_gemm(A, B, out, mode=0, epi=0, block_n=bn, M=M, N=N, K=K, bias=bias)
+    ops.tc_gemm(A, B, out, mode=0, epi=0, block_n=bn, M=M, N=N, K=K, bias=bias, cluster=cluster)
     torch.cuda.synchronize()
     want = A.float() @ B.float().t() + bias.float()
     _close(out, want, 2e-2, 2e-2 * math.sqrt(K), f"tc_gemm {M}x{N}x{K}")
@@ -123,7 +124,10 @@ def test_tc_window_dx_with_residual(ops, ref):
 
 
 @pytest.mark.parametrize("window", [0, 1])
-def test_tc_dw_mn_major_split_k(ops, ref, window):
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_tc_dw_mn_major_split_k(ops, ref, window, cluster):
+    ops = type(ops)("cuda:0")
+    ops.gemm_cluster = cluster
     torch.manual_seed(4)
     w, N = 128, 384
     X, mask = _padded_batch(tuple(range(2, 60)), w)

@@ -14,8 +14,8 @@
 //   split-K reduction straight into the flat gradient buffer (dW; both operands
 //   MN-major so no transposes are materialised).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
-// warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).
 #include "common.cuh"
 #include "gemm_launch.h"
 #include "gemm_tcgen05.cuh"
@@ -26,8 +26,9 @@ using namespace sm100;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 
 template <int BLOCK_N>
 struct Cfg {
@@ -38,7 +39,7 @@ struct Cfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/ + kMaxBiasN * 4;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -63,6 +64,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+  float* bias_s = (float*)(smem + C::kStages * C::kStage + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
@@ -84,10 +86,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (p.bias && warp >= 2) {                     // bias -> smem (fp32) once per CTA
+    for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
+  }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised too
   tc_fence_after();
@@ -182,60 +187,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ================================ epilogue =========================================
+    // 8 warps: warp -> TMEM lane quadrant (warp % 4) and column half ((warp - 2) / 4).  The MMA
+    // warp was measured spinning on tmem_empty (4 warps, per-element bias LDGs, one wait per
+    // tcgen05.ld): the epilogue, not the tensor pipe, paced the kernel.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;             // which half of the tile's columns
+    constexpr int HN = BLOCK_N / 2;
     int it = 0;
     for (int w = first_item; w < total_items; w += item_stride) {
       const int tile = w / splits;
       const int mg = tile / n_tiles;
-      const int m0 = (mg * CL + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BLOCK_N;
+      const int m0 = (mg * CL + (int)cta_rank) * BM, n0 = (tile % n_tiles) * BLOCK_N + half * HN;
       if (mg * CL * BM >= M) continue;
       const int acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
-      const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + acc * BLOCK_N + half * HN + ((uint32_t)(q * 32) << 16);
       if (EPI == EPI_STORE) {
         __nv_bfloat16* out = (__nv_bfloat16*)p.out;
         const float rs = (p.add_src && p.row_scale && row_ok) ? p.row_scale[row] : 1.f;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
-          float v[16];
-          tmem_ld_x16(t_base + c, v);
+        for (int c = 0; c < HN; c += 32) {
+          float v[32];
+          tmem_ld_x16_nowait(t_base + c, v);
+          if (c + 16 < HN) tmem_ld_x16_nowait(t_base + c + 16, v + 16);
+          tmem_ld_wait_regs<32>(v);
           if (row_ok) {
-            if (p.bias) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += bf2f(p.bias[n0 + c + i]);
+            for (int hh = 0; hh < 2; ++hh) {
+              if (c + hh * 16 >= HN) break;
+              float* vv = v + hh * 16;
+              const int cc = c + hh * 16;
+              if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vv[i] += bias_s[n0 + cc + i];
+              }
+              if (p.add_src) {
+                const bf16x8* src = (const bf16x8*)(p.add_src + (size_t)row * p.ld_add + n0 + cc);
+                bf16x8 s0 = src[0], s1 = src[1];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { vv[i] += rs * bf2f(s0.v[i]); vv[8 + i] += rs * bf2f(s1.v[i]); }
+              }
+              bf16x8 o0, o1;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { o0.v[i] = f2bf(vv[i]); o1.v[i] = f2bf(vv[8 + i]); }
+              bf16x8* dst = (bf16x8*)(out + (size_t)row * p.ldo + n0 + cc);
+              dst[0] = o0; dst[1] = o1;
             }
-            if (p.add_src) {
-              const bf16x8* src = (const bf16x8*)(p.add_src + (size_t)row * p.ld_add + n0 + c);
-              bf16x8 s0 = src[0], s1 = src[1];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { v[i] += rs * bf2f(s0.v[i]); v[8 + i] += rs * bf2f(s1.v[i]); }
-            }
-            bf16x8 o0, o1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { o0.v[i] = f2bf(v[i]); o1.v[i] = f2bf(v[8 + i]); }
-            bf16x8* dst = (bf16x8*)(out + (size_t)row * p.ldo + n0 + c);
-            dst[0] = o0; dst[1] = o1;
           }
         }
       } else if (EPI == EPI_MAXOUT3) {
         __nv_bfloat16* out = (__nv_bfloat16*)p.out;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 48) {
+        for (int c = 0; c < HN; c += 48) {
           float v[48];
-          tmem_ld_x16(t_base + c, v);
-          tmem_ld_x16(t_base + c + 16, v + 16);
-          tmem_ld_x16(t_base + c + 32, v + 32);
+          tmem_ld_x16_nowait(t_base + c, v);
+          tmem_ld_x16_nowait(t_base + c + 16, v + 16);
+          tmem_ld_x16_nowait(t_base + c + 32, v + 32);
+          tmem_ld_wait_regs<48>(v);
           if (row_ok) {
             bf16x8 h0, h1;
-            uint8_t wh[16];
+            __align__(16) uint8_t wh[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const int n = n0 + c + 3 * u;
               float a = v[3 * u], b = v[3 * u + 1], d = v[3 * u + 2];
-              if (p.bias) { a += bf2f(p.bias[n]); b += bf2f(p.bias[n + 1]); d += bf2f(p.bias[n + 2]); }
+              if (p.bias) { a += bias_s[n]; b += bias_s[n + 1]; d += bias_s[n + 2]; }
               float best = a; int bi = 0;
               if (b > best) { best = b; bi = 1; }
               if (d > best) { best = d; bi = 2; }
@@ -251,13 +270,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else {  // EPI_ATOMIC_F32: split-K partial sums reduced into the gradient buffer
         float* out = (float*)p.out;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 16) {
-          float v[16];
-          tmem_ld_x16(t_base + c, v);
+        for (int c = 0; c < HN; c += 32) {
+          float v[32];
+          tmem_ld_x16_nowait(t_base + c, v);
+          if (c + 16 < HN) tmem_ld_x16_nowait(t_base + c + 16, v + 16);
+          tmem_ld_wait_regs<32>(v);
           if (row_ok) {
             float* dst = out + (size_t)row * p.ldo + n0 + c;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 32; i += 4)
+              if (c + i < HN) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
         }
       }

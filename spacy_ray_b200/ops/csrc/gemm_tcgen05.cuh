@@ -140,6 +140,29 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Issue-only variant + explicit wait, so several loads are in flight before the one wait.
+__device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, float v[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// Wait, and tie the destination registers to the wait with "+f" operands: every later use of
+// v[] then depends on an asm that is ordered after the wait, so the compiler cannot schedule
+// arithmetic on the (asynchronously written) registers above it.
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_regs(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i += 8)
+    asm volatile("" : "+f"(v[i]), "+f"(v[i + 1]), "+f"(v[i + 2]), "+f"(v[i + 3]), "+f"(v[i + 4]), "+f"(v[i + 5]),
+                      "+f"(v[i + 6]), "+f"(v[i + 7])::"memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

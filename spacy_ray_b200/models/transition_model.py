@@ -38,6 +38,8 @@ class TransitionGold:
     # arc-eager
     heads: Optional[List[List[int]]] = None
     labels: Optional[List[List[int]]] = None
+    heads_flat: Optional[torch.Tensor] = None   # (T,) int32 doc-relative gold heads (self = root, -1 = missing)
+    labels_flat: Optional[torch.Tensor] = None  # (T,) int32 gold labels (-1 = unknown)
 
 
 @dataclass
@@ -45,7 +47,9 @@ class TransitionModelOutput:
     loss: Any = 0.0                       # float or 0-d tensor
     histories: Optional[List[List[int]]] = None     # per doc action sequence (host)
     actions_flat: Optional[torch.Tensor] = None     # BILUO: (T,) predicted action per token, doc order
-    states: Optional[list] = None                   # arc-eager final states
+    states: Optional[list] = None                   # arc-eager final states (host loop)
+    heads_flat: Optional[torch.Tensor] = None       # arc-eager on device: (T,) predicted heads (doc-relative)
+    labels_flat: Optional[torch.Tensor] = None      # ... and labels
     n_steps: int = 0
 
 
@@ -117,6 +121,7 @@ def build_transition_model(
         out = TransitionModelOutput(
             loss=rec.get("loss", 0.0), histories=rec.get("histories"),
             actions_flat=rec.get("actions_flat"), states=rec.get("states"), n_steps=rec["n_steps"],
+            heads_flat=rec.get("arc_heads"), labels_flat=rec.get("arc_labels"),
         )
         if not is_train or rec["n_steps"] == 0:
             return out
@@ -276,7 +281,9 @@ def _arc_steps_reference(system: ArcEagerSystem, Yf, params, batch, gold, is_tra
             costs = torch.tensor(cost_host, dtype=torch.int64, device=dev)
             masked = torch.where(valid, costs, torch.full_like(costs, 1 << 20))
             gold_mask = valid & (masked == masked.min(dim=1, keepdim=True).values)
-            d = _loss_grad(scores, valid, gold_mask) / float(len(live))
+            # per-step gradient scale 1 / #docs (constant per batch; the device kernel cannot know
+            # how many docs are still live at a given step without a grid-wide sync)
+            d = _loss_grad(scores, valid, gold_mask) / float(len(states))
             loss = loss + (d * d).sum()
             feats_l.append(feats)
             which_l.append(which.to(torch.uint8))

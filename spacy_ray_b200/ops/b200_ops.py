@@ -284,10 +284,12 @@ class B200Ops(TorchOps):
 
     # ------------------------------------------------------------------ K7
     def transition_steps(self, system, Yf, params, batch, gold, is_train):
-        from ..models.transitions import BiluoSystem
+        from ..models.transitions import ArcEagerSystem, BiluoSystem
 
+        if isinstance(system, ArcEagerSystem):
+            return self._arc_eager_steps(system, Yf, params, batch, gold, is_train)
         if not isinstance(system, BiluoSystem):
-            return None                       # arc-eager: reference loop (host state machine)
+            return None
         nO, nP = params["nO"], params["nP"]
         if nP != 2 or nO % 32 != 0 or (nO * nP) // 32 > 8 or system.n_actions > 256:
             return None
@@ -318,6 +320,44 @@ class B200Ops(TorchOps):
         if is_train and gold_t is not None:
             rec.update({"feats": feats, "which": which, "hid": hid, "d_scores": d_scores,
                         "n_steps": batch.n_tokens, "nA": system.n_actions})
+        return rec
+
+    def _arc_eager_steps(self, system, Yf, params, batch, gold, is_train):
+        """Arc-eager derivations of the whole batch in one kernel (parser_kernels.cu)."""
+        import numpy as np
+
+        from ..nn.batch import to_device
+
+        nO, nP = params["nO"], params["nP"]
+        max_len = max(batch.lengths) if batch.lengths else 0
+        if nO % 32 != 0 or nO // 32 not in (1, 2, 4) or nP not in (2, 3) or max_len > 128 or system.n_actions > 192:
+            return None                       # host state machine (reference loop)
+        dev = Yf.device
+        extra = batch.extra
+        if "tok_off" not in extra:
+            lens = batch.doc_lens.to(torch.int64)
+            extra["tok_off"] = (torch.cumsum(lens, 0) - lens).to(torch.int32)
+        if "step_off" not in extra:
+            extra["step_off"] = (extra["tok_off"] * 2).to(torch.int32)
+        train = bool(is_train and gold is not None and (gold.heads is not None or gold.heads_flat is not None))
+        gh = gl = None
+        if train:
+            gh, gl = gold.heads_flat, gold.labels_flat
+            if gh is None:
+                gh = to_device(np.asarray([h for doc in gold.heads for h in doc], dtype=np.int32), dev)
+                gl = to_device(np.asarray([l for doc in gold.labels for l in doc], dtype=np.int32), dev)
+        S_cap = 2 * batch.n_tokens
+        feats, which, hid, d_scores, history, heads, labels, n_steps, loss = self.k.arc_eager_steps(
+            Yf.contiguous(), params["pad"].contiguous(), params["b"].contiguous(), params["Wu"].contiguous(),
+            params["bu"].contiguous(), batch.doc_starts, batch.doc_lens, extra["tok_off"], extra["step_off"],
+            gh, gl, batch.n_tokens, S_cap, nO, nP, 1.0 / max(1, batch.n_docs), train,
+        )
+        self.launches += 1
+        rec: Dict[str, Any] = {"arc_heads": heads, "arc_labels": labels, "loss": loss, "n_steps": 0,
+                               "arc_history": history, "arc_n_steps": n_steps}
+        if train:
+            rec.update({"feats": feats, "which": which, "hid": hid, "d_scores": d_scores, "n_steps": S_cap,
+                        "nA": system.n_actions})
         return rec
 
     def transition_backward(self, rec, params, n_rows):

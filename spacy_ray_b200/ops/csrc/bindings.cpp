@@ -203,6 +203,45 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   return {feats, which, hid, d_scores, actions, loss};
 }
 
+std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const Tensor& b, const Tensor& Wu,
+                                    const Tensor& bu, const Tensor& doc_starts, const Tensor& doc_lens,
+                                    const Tensor& tok_off, const Tensor& step_off,
+                                    const c10::optional<Tensor>& gold_heads, const c10::optional<Tensor>& gold_labels,
+                                    int64_t n_tokens, int64_t n_steps_cap, int64_t nO, int64_t nP, double scale,
+                                    bool train) {
+  SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
+  c10::cuda::CUDAGuard guard(Yf.device());
+  const int64_t nA = Wu.size(0);
+  const int64_t nA_pad = (nA + 7) / 8 * 8;
+  auto o = Yf.options();
+  const int64_t S = train ? n_steps_cap : 0;
+  Tensor feats = at::empty({S, 8}, o.dtype(at::kInt));
+  Tensor which = at::empty({S, nO}, o.dtype(at::kByte));
+  Tensor hid = at::zeros({S, nO}, o);
+  Tensor d_scores = at::zeros({S, nA_pad}, o);
+  Tensor history = at::full({n_steps_cap}, -1, o.dtype(at::kInt));
+  Tensor heads = at::empty({n_tokens}, o.dtype(at::kInt));
+  Tensor labels = at::empty({n_tokens}, o.dtype(at::kInt));
+  Tensor n_steps = at::zeros({doc_lens.numel()}, o.dtype(at::kInt));
+  Tensor loss = at::zeros({}, o.dtype(at::kFloat));
+  srb::ArcArgs a{};
+  a.Yf = Yf.data_ptr(); a.pad = pad.data_ptr(); a.b = b.data_ptr(); a.Wu = Wu.data_ptr(); a.bu = bu.data_ptr();
+  a.doc_starts = doc_starts.data_ptr<int32_t>(); a.doc_lens = doc_lens.data_ptr<int32_t>();
+  a.tok_off = tok_off.data_ptr<int32_t>(); a.step_off = step_off.data_ptr<int32_t>();
+  const bool have_gold = gold_heads.has_value() && gold_heads->defined();
+  a.gold_heads = have_gold ? gold_heads->data_ptr<int32_t>() : nullptr;
+  a.gold_labels = have_gold ? gold_labels->data_ptr<int32_t>() : nullptr;
+  a.feats = feats.data_ptr<int32_t>(); a.which = which.data_ptr<uint8_t>(); a.hid = hid.data_ptr();
+  a.d_scores = d_scores.data_ptr(); a.history = history.data_ptr<int32_t>();
+  a.heads_out = heads.data_ptr<int32_t>(); a.labels_out = labels.data_ptr<int32_t>();
+  a.n_steps = n_steps.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
+  a.scale = (float)scale;
+  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad;
+  a.train = train ? 1 : 0;
+  TORCH_CHECK(srb::launch_arc_eager_steps(a, cur_stream()), "arc_eager_steps: unsupported hidden width / pieces / #actions");
+  return {feats, which, hid, d_scores, history, heads, labels, n_steps, loss};
+}
+
 void transition_scatter(const Tensor& d_hid, const Tensor& which, const Tensor& feats, Tensor dYf, Tensor dpad,
                         Tensor db, int64_t nF, int64_t nP) {
   SRB_CHECK_CUDA(d_hid); SRB_CHECK_BF16(d_hid);
@@ -225,6 +264,7 @@ TORCH_LIBRARY(srb, m) {
   m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");
   m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
   m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train) -> Tensor[]");
+  m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train) -> Tensor[]");
   m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
   srb::register_gemm_ops(m);
   srb::register_comm_ops(m);
@@ -241,6 +281,7 @@ TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("softmax_xent", softmax_xent);
   m.impl("adam_shard", adam_shard);
   m.impl("biluo_steps", biluo_steps);
+  m.impl("arc_eager_steps", arc_eager_steps);
   m.impl("transition_scatter", transition_scatter);
   srb::register_gemm_impls(m);
   srb::register_comm_impls(m);

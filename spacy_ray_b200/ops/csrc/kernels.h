@@ -98,4 +98,32 @@ void launch_biluo_steps(BiluoArgs a, cudaStream_t s);
 void launch_transition_scatter(const void* d_hid, const uint8_t* which, const int32_t* feats, float* dYf,
                                float* dpad, float* db, int S, int nF, int nO, int nP, cudaStream_t s);
 
+// K7 (parser): arc-eager transition loop with dynamic oracle, one warp per doc.
+struct ArcArgs {
+  const void* Yf;              // bf16 (Tp, 8*nOP)
+  const void* pad;             // bf16 (8, nOP)
+  const void* b;               // bf16 (nOP)
+  const void* Wu;              // bf16 (nA, nO)
+  const void* bu;              // bf16 (nA)
+  const int32_t* doc_starts;   // (B)
+  const int32_t* doc_lens;     // (B)
+  const int32_t* tok_off;      // (B) offset of the doc in unpadded token order
+  const int32_t* step_off;     // (B) offset of the doc's step records (capacity 2*len each)
+  const int32_t* gold_heads;   // (T) doc-relative gold head (self = root, -1 = missing) or nullptr
+  const int32_t* gold_labels;  // (T) gold label or -1
+  int32_t* feats;              // (S, 8)
+  uint8_t* which;              // (S, nO)
+  void* hid;                   // bf16 (S, nO)
+  void* d_scores;              // bf16 (S, nA_pad)
+  int32_t* history;            // (S) chosen action per step (optional)
+  int32_t* heads_out;          // (T) predicted head (doc-relative, root = self)
+  int32_t* labels_out;         // (T) predicted label or -1
+  int32_t* n_steps;            // (B)
+  float* loss;
+  float scale;                 // gradient scale per step (1 / #docs)
+  int B, nO, nP, nA, nA_pad, train;
+};
+bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s);
+int arc_eager_max_doc_len();
+
 }  // namespace srb

@@ -1,0 +1,301 @@
+// K7 (parser): the arc-eager transition loop with a dynamic oracle, ONE kernel per batch.
+//
+// Upstream this is spaCy's Cython/C++ `_parser_internals` driven per step from the host.
+// Here one warp owns one doc and runs its whole derivation on the device:
+//   state (stack, heads, labels, leftmost/rightmost children, stack membership) lives in
+//   shared memory; per step the warp
+//     * builds the 8 feature tokens [B0, B1, S0, S1, S2, L(B0), L(S0), R(S0)],
+//     * sums the 8 precomputed feature rows (Yf) + bias -> maxout -> upper layer (W_u^T in smem),
+//     * derives the valid-action mask from the state,
+//     * evaluates the dynamic oracle (Goldberg & Nivre 2012) warp-parallel: the two counts it
+//       needs (gold children of B0 among headless stack items; gold children of S0 in the
+//       buffer) are ballots over the doc's tokens,
+//     * d_scores = softmax(valid) - softmax(valid & min-cost), loss, arg-max valid action,
+//     * applies the predicted action.
+// Records (feature rows, winning pieces, hidden, d_scores) are written per step so the backward
+// pass is the same three batched GEMMs + scatter kernel as for NER.
+// Spec: models/transitions.py::ArcEagerSystem and transition_model.py::_arc_steps_reference.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srb {
+
+constexpr int kArcWarps = 4;
+constexpr int kArcMaxN = 128;      // tokens per doc handled on the device (longer docs: host path)
+
+struct ArcWarpState {
+  int stack[kArcMaxN];
+  int heads[kArcMaxN];
+  int labels[kArcMaxN];
+  int lc[kArcMaxN];
+  int rc[kArcMaxN];
+  int gh[kArcMaxN];                // gold head: -2 missing, -1 root, else doc-relative index
+  int gl[kArcMaxN];                // gold label or -1
+  unsigned char in_stack[kArcMaxN];
+};
+
+template <int NP, int UPL, int NJ>
+__global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs A) {
+  constexpr int PPL = NP * UPL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nO = A.nO, nOP = A.nO * NP, nA = A.nA;
+  float* WuT = (float*)smem_raw;                                  // [nO][nA_pad]
+  float* bu_s = WuT + (size_t)nO * A.nA_pad;                      // [nA_pad]
+  float* pad_s = bu_s + A.nA_pad;                                 // [8][nOP]
+  float* hid_s = pad_s + 8 * nOP;                                 // [warps][nO]
+  ArcWarpState* states = (ArcWarpState*)(hid_s + kArcWarps * nO);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* Wu = (const __nv_bfloat16*)A.Wu;
+  for (int i = threadIdx.x; i < nO * A.nA_pad; i += blockDim.x) {
+    const int o = i / A.nA_pad, a = i - o * A.nA_pad;
+    WuT[i] = a < nA ? bf2f(Wu[(size_t)a * nO + o]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < A.nA_pad; i += blockDim.x) bu_s[i] = i < nA ? bf2f(((const __nv_bfloat16*)A.bu)[i]) : 0.f;
+  for (int i = threadIdx.x; i < 8 * nOP; i += blockDim.x) pad_s[i] = bf2f(((const __nv_bfloat16*)A.pad)[i]);
+  __syncthreads();
+
+  const int d = blockIdx.x * kArcWarps + warp;
+  if (d >= A.B) return;
+  const int n = A.doc_lens[d];
+  const int row0 = A.doc_starts[d];
+  const int tok0 = A.tok_off[d];
+  const int rec0 = A.step_off[d];
+  ArcWarpState& S = states[warp];
+  float* hid_w = hid_s + warp * nO;
+  const bool have_gold = A.gold_heads != nullptr;
+  for (int t = lane; t < n && t < kArcMaxN; t += 32) {
+    S.heads[t] = -1; S.labels[t] = -1; S.lc[t] = -1; S.rc[t] = -1; S.in_stack[t] = 0;
+    int g = -2, l = -1;
+    if (have_gold) {
+      const int h = A.gold_heads[tok0 + t];
+      g = h < 0 ? -2 : (h == t ? -1 : h);
+      l = A.gold_labels[tok0 + t];
+    }
+    S.gh[t] = g; S.gl[t] = l;
+  }
+  __syncwarp();
+  float bias_r[PPL];
+#pragma unroll
+  for (int k = 0; k < PPL; ++k) bias_r[k] = bf2f(((const __nv_bfloat16*)A.b)[lane * PPL + k]);
+  const __nv_bfloat16* Yf = (const __nv_bfloat16*)A.Yf;
+
+  int sp = 0, b = 0, step = 0;
+  float loss_acc = 0.f;
+  const int max_steps = 2 * n;
+  while (!(b >= n && sp <= 1) && step < max_steps) {
+    const bool has_buf = b < n, has_stack = sp > 0;
+    const int b0 = has_buf ? b : -1;
+    const int b1 = (b + 1 < n) ? b + 1 : -1;
+    const int s0 = sp > 0 ? S.stack[sp - 1] : -1;
+    const int s1 = sp > 1 ? S.stack[sp - 2] : -1;
+    const int s2 = sp > 2 ? S.stack[sp - 3] : -1;
+    const int f[8] = {b0, b1, s0, s1, s2, b0 >= 0 ? S.lc[b0] : -1, s0 >= 0 ? S.lc[s0] : -1, s0 >= 0 ? S.rc[s0] : -1};
+    const bool s0_headed = s0 >= 0 && S.heads[s0] >= 0;
+    // ---- hidden ---------------------------------------------------------------------------
+    float pre[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) pre[k] = bias_r[k];
+#pragma unroll
+    for (int ff = 0; ff < 8; ++ff) {
+      if (f[ff] >= 0) {
+        const __nv_bfloat16* p = Yf + ((size_t)(row0 + f[ff]) * 8 + ff) * nOP + lane * PPL;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) pre[k] += bf2f(p[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) pre[k] += pad_s[ff * nOP + lane * PPL + k];
+      }
+    }
+    const size_t rec = (size_t)rec0 + step;
+#pragma unroll
+    for (int u = 0; u < UPL; ++u) {
+      float best = pre[u * NP];
+      int bi = 0;
+#pragma unroll
+      for (int q = 1; q < NP; ++q) if (pre[u * NP + q] > best) { best = pre[u * NP + q]; bi = q; }
+      const int o = lane * UPL + u;
+      hid_w[o] = best;
+      if (A.train) {
+        A.which[rec * nO + o] = (uint8_t)bi;
+        ((__nv_bfloat16*)A.hid)[rec * nO + o] = f2bf(best);
+      }
+    }
+    __syncwarp();
+    // ---- upper layer ----------------------------------------------------------------------
+    float sc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) sc[j] = bu_s[lane + 32 * j < A.nA_pad ? lane + 32 * j : 0];
+#pragma unroll 4
+    for (int o = 0; o < nO; ++o) {
+      const float h = hid_w[o];
+      const float* wrow = WuT + o * A.nA_pad + lane;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (j < NJ - 1 || lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
+    }
+    // ---- validity + arg-max ---------------------------------------------------------------
+    bool ok[NJ];
+    float mx = -3.0e38f;
+    int arg = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int a = lane + 32 * j;
+      bool v = false;
+      if (a < nA) {
+        if (a == 0) v = has_buf;
+        else if (a == 1) v = has_stack && (s0_headed || !has_buf);
+        else {
+          const bool right = ((a - 2) & 1) != 0;
+          v = has_stack && has_buf && (right || !s0_headed);
+        }
+      }
+      ok[j] = v;
+      if (v && sc[j] > mx) { mx = sc[j]; arg = a; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    if (A.train) {
+      // ---- dynamic oracle ------------------------------------------------------------------
+      int cnt_stack_b0 = 0, cnt_buf_s0 = 0;
+      if (have_gold) {
+        for (int t = lane; t < n; t += 32) {
+          const int g = S.gh[t];
+          if (b0 >= 0 && S.in_stack[t] && S.heads[t] < 0 && g == b0) cnt_stack_b0 += 1;
+          if (s0 >= 0 && t >= b && g == s0) cnt_buf_s0 += 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          cnt_stack_b0 += __shfl_xor_sync(0xffffffffu, cnt_stack_b0, o);
+          cnt_buf_s0 += __shfl_xor_sync(0xffffffffu, cnt_buf_s0, o);
+        }
+      }
+      const int gb = b0 >= 0 ? S.gh[b0] : -2, gs = s0 >= 0 ? S.gh[s0] : -2;
+      const bool gb_in_stack = gb >= 0 && S.in_stack[gb];
+      int c_shift = (gb_in_stack ? 1 : 0) + cnt_stack_b0;
+      int c_reduce = (s0 >= 0 && !s0_headed && !has_buf) ? 0 : cnt_buf_s0;
+      int c_left = cnt_buf_s0 + ((gs != -2 && gs != b0 && (gs == -1 || gs > b0)) ? 1 : 0);
+      int c_right = ((gb != -2 && gb != s0 && (gb == -1 || gb_in_stack || gb > b0)) ? 1 : 0) + cnt_stack_b0;
+      const int gl_s0 = s0 >= 0 ? S.gl[s0] : -1, gl_b0 = b0 >= 0 ? S.gl[b0] : -1;
+      int cost[NJ];
+      int cmin = 1 << 20;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int a = lane + 32 * j;
+        int c = 1 << 20;
+        if (ok[j]) {
+          if (!have_gold) c = 0;
+          else if (a == 0) c = c_shift;
+          else if (a == 1) c = c_reduce;
+          else {
+            const int lab = (a - 2) >> 1;
+            if ((a - 2) & 1) c = c_right + ((gb == s0 && gl_b0 >= 0 && gl_b0 != lab) ? 1 : 0);
+            else c = c_left + ((gs == b0 && gl_s0 >= 0 && gl_s0 != lab) ? 1 : 0);
+          }
+        }
+        cost[j] = c;
+        cmin = min(cmin, c);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      float e[NJ], eg[NJ];
+      float sum = 0.f, gsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        e[j] = ok[j] ? __expf(sc[j] - mx) : 0.f;
+        eg[j] = (ok[j] && cost[j] == cmin) ? e[j] : 0.f;
+        sum += e[j]; gsum += eg[j];
+      }
+      sum = warp_sum(sum); gsum = warp_sum(gsum);
+      const float inv = 1.f / sum, ginv = gsum > 0.f ? 1.f / gsum : 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int a = lane + 32 * j;
+        if (a < A.nA_pad) {
+          float dv = 0.f;
+          if (ok[j] && gsum > 0.f) dv = (e[j] * inv - eg[j] * ginv) * A.scale;
+          loss_acc += dv * dv;
+          ((__nv_bfloat16*)A.d_scores)[rec * A.nA_pad + a] = f2bf(dv);
+        }
+      }
+      if (lane < 8) {
+        const int fv = lane == 0 ? f[0] : lane == 1 ? f[1] : lane == 2 ? f[2] : lane == 3 ? f[3]
+                     : lane == 4 ? f[4] : lane == 5 ? f[5] : lane == 6 ? f[6] : f[7];
+        A.feats[rec * 8 + lane] = fv >= 0 ? row0 + fv : -1;
+      }
+    }
+    if (A.history && lane == 0) A.history[rec] = arg;
+    // ---- apply the predicted action -------------------------------------------------------------
+    if (lane == 0) {
+      if (arg == 0) { S.stack[sp] = b; S.in_stack[b] = 1; }
+      else if (arg == 1) { S.in_stack[s0] = 0; }
+      else {
+        const int lab = (arg - 2) >> 1;
+        if ((arg - 2) & 1) {            // RIGHT: S0 -> B0, push B0
+          S.heads[b0] = s0; S.labels[b0] = lab;
+          if (S.rc[s0] < b0) S.rc[s0] = b0;
+          S.stack[sp] = b0; S.in_stack[b0] = 1;
+        } else {                        // LEFT: B0 -> S0, pop S0
+          S.heads[s0] = b0; S.labels[s0] = lab;
+          if (S.lc[b0] < 0 || s0 < S.lc[b0]) S.lc[b0] = s0;
+          S.in_stack[s0] = 0;
+        }
+      }
+    }
+    if (arg == 0) { sp += 1; b += 1; }
+    else if (arg == 1) { sp -= 1; }
+    else if ((arg - 2) & 1) { sp += 1; b += 1; }
+    else { sp -= 1; }
+    step += 1;
+    __syncwarp();
+  }
+  for (int t = lane; t < n; t += 32) {
+    A.heads_out[tok0 + t] = S.heads[t] >= 0 ? S.heads[t] : t;
+    A.labels_out[tok0 + t] = S.labels[t];
+  }
+  if (lane == 0) A.n_steps[d] = step;
+  if (A.train) {
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0 && loss_acc != 0.f) atomicAdd(A.loss, loss_acc);
+  }
+}
+
+template <int NP, int UPL, int NJ>
+static void launch_arc(const ArcArgs& a, int blocks, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(arc_eager_steps_kernel<NP, UPL, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  arc_eager_steps_kernel<NP, UPL, NJ><<<blocks, kArcWarps * 32, smem, s>>>(a);
+}
+
+template <int NP, int UPL>
+static void launch_arc_nj(const ArcArgs& a, int blocks, size_t smem, cudaStream_t s) {
+  const int nj = (a.nA_pad + 31) / 32;
+  switch (nj) {
+    case 1: launch_arc<NP, UPL, 1>(a, blocks, smem, s); break;
+    case 2: launch_arc<NP, UPL, 2>(a, blocks, smem, s); break;
+    case 3: launch_arc<NP, UPL, 3>(a, blocks, smem, s); break;
+    case 4: launch_arc<NP, UPL, 4>(a, blocks, smem, s); break;
+    default: launch_arc<NP, UPL, 6>(a, blocks, smem, s); break;     // nA <= 192
+  }
+}
+
+bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s) {
+  if (a.B <= 0) return true;
+  if (a.nO % 32 != 0 || a.nA_pad > 192) return false;
+  const int upl = a.nO / 32;
+  const size_t smem = sizeof(float) * ((size_t)a.nO * a.nA_pad + a.nA_pad + 8 * a.nO * a.nP + kArcWarps * a.nO) +
+                      kArcWarps * sizeof(ArcWarpState);
+  const int blocks = (a.B + kArcWarps - 1) / kArcWarps;
+#define SRB_ARC(NP_, UPL_) \
+  if (a.nP == NP_ && upl == UPL_) { launch_arc_nj<NP_, UPL_>(a, blocks, smem, s); return true; }
+  SRB_ARC(2, 2) SRB_ARC(2, 4) SRB_ARC(3, 2) SRB_ARC(3, 4) SRB_ARC(2, 1) SRB_ARC(3, 1)
+#undef SRB_ARC
+  return false;
+}
+
+int arc_eager_max_doc_len() { return kArcMaxN; }
+
+}  // namespace srb

@@ -352,6 +352,11 @@ class DependencyParser(TrainablePipe):
         set_dropout_rate(self.model, drop)
         golds = [self._gold(eg.reference) for eg in examples]
         gold = TransitionGold(heads=[g[0] for g in golds], labels=[g[1] for g in golds])
+        if batch.device.type == "cuda":        # flat device copies for the on-device oracle
+            from ..nn.batch import to_device
+
+            gold.heads_flat = to_device(np.concatenate([self._gold_np(eg.reference)[0] for eg in examples]), batch.device)
+            gold.labels_flat = to_device(np.concatenate([self._gold_np(eg.reference)[1] for eg in examples]), batch.device)
         out = self.model.attrs["run"](batch, self.system, gold, True)
         if sgd not in (None, False):
             self.finish_update(sgd)
@@ -361,7 +366,27 @@ class DependencyParser(TrainablePipe):
     def predict(self, docs, batch):
         return self.model.attrs["run"](batch, self.system, None, False)
 
+    def _gold_np(self, ref: Doc):
+        key = ("dep_gold_np", self.name)
+        g = ref.user_data.get(key)
+        if g is None:
+            heads, labels = self._gold(ref)
+            # root = self; missing stays -1 (the list form marks roots as h == t already)
+            g = (np.asarray(heads, dtype=np.int32), np.asarray(labels, dtype=np.int32))
+            ref.user_data[key] = g
+        return g
+
     def set_annotations(self, docs, out) -> None:
+        if out.states is None and out.heads_flat is not None:     # derivations ran on the device
+            heads_all = out.heads_flat.to("cpu").tolist()
+            labs_all = out.labels_flat.to("cpu").tolist()
+            pos = 0
+            for doc in docs:
+                n = len(doc)
+                doc.heads = heads_all[pos:pos + n]
+                doc.deps = [self._labels[l] if l >= 0 else "ROOT" for l in labs_all[pos:pos + n]]
+                pos += n
+            return
         for doc, st in zip(docs, out.states):
             heads, labs = self.system.finalize(st)
             doc.heads = heads

@@ -1,0 +1,123 @@
+"""GPU arc-eager kernel (parser_kernels.cu) vs the host reference loop, and end-to-end parser /
+multi-task training on the sm_100a backend."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _projective(n, rng):
+    root = rng.randrange(n)
+    heads = []
+    for t in range(n):
+        if t == root:
+            heads.append(t)
+        elif t < root:
+            heads.append(root if rng.random() < 0.3 else t + 1)
+        else:
+            heads.append(root if rng.random() < 0.3 else t - 1)
+    return heads
+
+
+@pytest.mark.parametrize("nO,nP,n_labels", [(64, 2, 5), (128, 2, 9), (64, 3, 20)])
+def test_arc_eager_kernel_matches_reference_loop(nO, nP, n_labels):
+    from spacy_ray_b200.models.transition_model import TransitionGold, _arc_steps_reference, transition_backward
+    from spacy_ray_b200.models.transitions import ArcEagerSystem
+    from spacy_ray_b200.nn.batch import make_token_batch
+    from spacy_ray_b200.ops.b200_ops import B200Ops
+    from spacy_ray_b200.ops.torch_ops import TorchOps
+
+    ops, ref = B200Ops("cuda:0"), TorchOps("cuda:0", dtype=torch.float32)
+    rng = random.Random(0)
+    torch.manual_seed(0)
+    system = ArcEagerSystem([f"d{i}" for i in range(n_labels)])
+    lens = [rng.randint(1, 40) for _ in range(53)]
+    batch = make_token_batch([np.ones((n, 4), dtype=np.uint64) for n in lens], "cuda:0")
+    heads = [_projective(n, rng) for n in lens]
+    labels = [[rng.randrange(n_labels) if h != t else -1 for t, h in enumerate(hs)] for hs in heads]
+    gold = TransitionGold(heads=heads, labels=labels)
+    nF = 8
+    Tp = batch.n_rows
+    Yf = (torch.randn(Tp, nF * nO * nP, device="cuda") * batch.mask).bfloat16()
+    params = {
+        "pad": (torch.randn(nF, nO * nP, device="cuda") * 0.3).bfloat16(),
+        "b": (torch.randn(nO * nP, device="cuda") * 0.3).bfloat16(),
+        "Wu": (torch.randn(system.n_actions, nO, device="cuda") * 0.3).bfloat16(),
+        "bu": (torch.randn(system.n_actions, device="cuda") * 0.1).bfloat16(),
+        "nF": nF, "nO": nO, "nP": nP,
+    }
+    rec = ops.transition_steps(system, Yf, params, batch, gold, True)
+    assert rec is not None and "arc_heads" in rec
+    pf = {k: (v.float() if torch.is_tensor(v) else v) for k, v in params.items()}
+    rref = _arc_steps_reference(system, Yf.float(), pf, batch, gold, True)
+    torch.cuda.synchronize()
+    hist = rec["arc_history"].cpu().tolist()
+    nsteps = rec["arc_n_steps"].cpu().tolist()
+    heads_k = rec["arc_heads"].cpu().tolist()
+    same_docs, pos, tok = 0, 0, 0
+    for d, n in enumerate(lens):
+        mine = hist[2 * tok: 2 * tok + nsteps[d]]
+        theirs = rref["histories"][d]
+        assert len(mine) == nsteps[d] and 1 <= nsteps[d] <= 2 * n
+        if mine == theirs:
+            same_docs += 1
+            want_heads, _ = system.finalize(rref["states"][d])
+            assert heads_k[tok:tok + n] == want_heads
+        # every derivation must be a legal one: replay it through the host system
+        s = system.init_state(n)
+        for a in mine:
+            assert system.valid(s)[a], (d, a)
+            system.apply(s, a)
+        assert s.is_final
+        tok += n
+    assert same_docs / len(lens) > 0.7, same_docs       # bf16 vs fp32 near-ties diverge a few docs
+    d = rec["d_scores"].float()[:, : system.n_actions]
+    assert float(d.sum(dim=1).abs().max()) < 2e-2       # each row: softmax(valid) - softmax(gold) sums to 0
+    assert abs(float(rec["loss"]) - float(rref["loss"])) / max(float(rref["loss"]), 1e-6) < 0.3
+    g = ops.transition_backward(rec, params, Tp)
+    rec_f = {"d_scores": d, "hid": rec["hid"].float(), "which": rec["which"], "feats": rec["feats"].long()}
+    gr = transition_backward(ref, rec_f, pf, Tp)
+    for k in ("dYf", "dpad", "db", "dWu"):
+        err = (g[k].float() - gr[k].float()).abs()
+        assert float((err > 0.05 + 0.03 * gr[k].float().abs()).float().mean()) < 1e-3, k
+
+
+def _train_gpu(pipeline, steps, bs=64, width=64, hidden=64):
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.worker import Worker
+
+    cfg = Config().from_str(multi_cfg(pipeline, width=width, depth=2, n_docs=400, max_len=16, hidden=hidden),
+                            interpolate=False)
+    w = Worker(cfg, rank=0, num_workers=1, use_gpu=0, mode="sync", comm="auto")
+    w.set_proxy(None)
+    nlp = w.nlp
+    exs = list(w.train_corpus(nlp))
+    hist = []
+    for step in range(steps):
+        losses = {}
+        lo = (step * bs) % (len(exs) - bs)
+        nlp.update(exs[lo:lo + bs], drop=0.1, sgd=False, losses=losses)
+        w.proxy.step()
+        hist.append({k: float(v) for k, v in losses.items()})
+    w.proxy.comm.check()
+    return nlp, exs, hist
+
+
+def test_parser_trains_on_gpu_with_device_side_derivations():
+    nlp, exs, hist = _train_gpu(["parser"], steps=150)
+    first = sum(h["parser"] for h in hist[:5])
+    last = sum(h["parser"] for h in hist[-5:])
+    assert last < first, (first, last)
+    scores = nlp.evaluate(exs[:100])
+    assert scores["dep_uas"] > 0.5, scores
+
+
+def test_multitask_tagger_parser_ner_on_gpu():
+    nlp, exs, hist = _train_gpu(["tagger", "parser", "ner"], steps=60)
+    assert hist[-1]["tagger"] < hist[0]["tagger"]
+    scores = nlp.evaluate(exs[:60])
+    assert scores["tag_acc"] > 0.3 and scores["dep_uas"] is not None and scores["ents_f"] is not None

@@ -215,8 +215,9 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   const int64_t nA_pad = (nA + 7) / 8 * 8;
   auto o = Yf.options();
   const int64_t S = train ? n_steps_cap : 0;
-  Tensor feats = at::empty({S, 8}, o.dtype(at::kInt));
-  Tensor which = at::empty({S, nO}, o.dtype(at::kByte));
+  // record slots past a doc's last step stay inert: zero gradient, piece 0, "missing" features
+  Tensor feats = at::full({S, 8}, -1, o.dtype(at::kInt));
+  Tensor which = at::zeros({S, nO}, o.dtype(at::kByte));
   Tensor hid = at::zeros({S, nO}, o);
   Tensor d_scores = at::zeros({S, nA_pad}, o);
   Tensor history = at::full({n_steps_cap}, -1, o.dtype(at::kInt));

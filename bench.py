@@ -108,6 +108,9 @@ def main() -> int:
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--comm", default="auto")
+    ap.add_argument("--config", default=None,
+                    help="train a pipeline from a .cfg file (configs/*.cfg) instead of the flagship tok2vec+NER; "
+                         "its [corpora.train] must be a SyntheticCorpus (n_docs/seed are overridden per rank)")
     ap.add_argument("--engine", default="graph", choices=["graph", "eager"],
                     help="graph = CUDA-graph replay of the whole step; eager = same kernels launched from Python")
     args = ap.parse_args()
@@ -154,12 +157,20 @@ def main() -> int:
         print(json.dumps({"impl": args.impl, "unavailable": "rayproxy-emu runs under the actor runtime: "
                           "use benchmarks/bench_rayproxy.py"}))
         return 0
-    cfg = Config().from_str(flagship_config(args, rank), interpolate=False)
+    if args.config:
+        cfg = Config().from_str(Path(args.config).read_text(), interpolate=False)
+        cfg["corpora"]["train"]["n_docs"] = args.docs_per_gpu * 8
+        cfg["corpora"]["train"]["seed"] = 1000 + rank
+        cfg["training"]["max_steps"] = 0
+    else:
+        cfg = Config().from_str(flagship_config(args, rank), interpolate=False)
     worker = Worker(cfg, rank=rank, num_workers=world, use_gpu=local_rank, mode="sync", comm=comm,
                     fused_ops=True)
     worker.set_proxy(None)
     nlp, proxy = worker.nlp, worker.proxy
-    ops = nlp.get_pipe("ner").model.ops
+    from spacy_ray_b200.ops import get_current_ops
+
+    ops = get_current_ops()
     examples = list(worker.train_corpus(nlp))
     B = args.docs_per_gpu
     n_params = sum(proxy.layout.numel.values())
@@ -183,7 +194,6 @@ def main() -> int:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ner = nlp.get_pipe("ner")
     from spacy_ray_b200.engine import Trainer
 
     use_graphs = args.engine == "graph"
@@ -252,7 +262,7 @@ def main() -> int:
         ms_e = max_over_ranks(float(e0.elapsed_time(e1)))
         docs_e = sum_over_ranks(float(docs_local))
         e2e = {"value": docs_e / (ms_e / 1e3), "unit": "docs/s", "h2d_bytes_per_step": int(trainer.h2d_bytes_per_step),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps, "last_loss": loss_val,
+               "d2h_bytes_per_step": 4 * len(trainer.loss_names), "ms_per_step": ms_e / args.steps, "last_loss": loss_val,
                "api": "spacy_ray_b200.engine.Trainer.train_step"}
         if hasattr(proxy.comm, "check"):
             proxy.comm.check()
@@ -261,14 +271,16 @@ def main() -> int:
     if rank == 0:
         mean_len = words / max(docs, 1)
         out = {
-            "metric": "docs/sec (whole box, device-timed, max over ranks) en tok2vec+NER",
+            "metric": "docs/sec (whole box, device-timed, max over ranks) "
+                      + ("en tok2vec+NER" if not args.config else "+".join(nlp.pipe_names)),
             "value": value, "unit": "docs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic (SyntheticCorpus, random-init weights)",
             "impl": args.impl, "engine": args.engine,
             "config": {
-                "model": f"en tok2vec(MultiHashEmbed+MaxoutWindowEncoder width={args.width} depth={args.depth})+NER "
-                         f"(TransitionBasedParser hidden=64, 18 entity labels)",
+                "model": (f"en tok2vec(MultiHashEmbed+MaxoutWindowEncoder width={args.width} depth={args.depth})+NER "
+                          f"(TransitionBasedParser hidden=64, 18 entity labels)") if not args.config
+                else f"{args.config} pipeline={nlp.pipe_names}",
                 "global_batch": int(B * world), "docs_per_gpu": B, "seq_len": round(mean_len, 2),
                 "words_per_sec": words / (ms / 1e3), "params": int(n_params),
                 "parallelism": f"dp{world} + optimizer sharding by parameter ownership ({proxy.comm.name})",

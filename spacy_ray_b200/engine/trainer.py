@@ -16,8 +16,11 @@ issues a few hundred small launches per step from Python; on a B200 that is
   kernel - captured once per row-capacity bucket (rows rounded up to 1024);
 * **one 4-byte D2H read** of the loss.
 
-Supports pipelines whose trainable components have a device-side update (NER
-today); anything else should use the generic ``nlp.update`` path.
+Supports any pipeline made of the built-in trainable components - a shared
+``tok2vec`` plus ``tagger`` / ``ner`` / ``parser`` heads, each with its own or a listener
+tok2vec (the whole of SURVEY.md 2.6's component list) - as long as the transition heads fit
+their device kernels (``Trainer.unsupported_reason``).  Everything else uses the generic
+``nlp.update`` path.
 """
 from __future__ import annotations
 
@@ -39,17 +42,45 @@ def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
 
 
-class ExampleStore:
-    """Structure-of-arrays view of a list of Examples for one NER component."""
+def _kind(comp) -> Optional[str]:
+    return {"Tok2VecComponent": "tok2vec", "Tagger": "tagger", "EntityRecognizer": "ner",
+            "DependencyParser": "parser"}.get(comp.__class__.__name__)
 
-    def __init__(self, examples: Sequence[Any], ner) -> None:
+
+class ExampleStore:
+    """Structure-of-arrays view of a list of Examples: attribute ids plus one int32 gold
+    array per head.  ``slots[key] = (array, doc_off, padded)``: token-order arrays share
+    ``doc_off``; *padded* arrays carry one trailing ``-1`` per doc so that a plain per-doc
+    memcpy lands them in the padded-ragged row layout (the tagger's labels)."""
+
+    def __init__(self, examples: Sequence[Any], heads: Sequence[tuple]) -> None:
         lens = np.array([len(eg) for eg in examples], dtype=np.int64)
         self.doc_off = np.zeros(len(examples) + 1, dtype=np.int64)
         np.cumsum(lens, out=self.doc_off[1:])
+        self.doc_off_padded = self.doc_off + np.arange(len(examples) + 1, dtype=np.int64)
         self.attrs = np.ascontiguousarray(
             np.concatenate([eg.predicted.to_array() for eg in examples]).view(np.int64))
-        self.gold = np.ascontiguousarray(
-            np.concatenate([ner.gold_actions(eg.reference) for eg in examples]).astype(np.int32))
+        self.slots: Dict[str, tuple] = {}
+
+        def cat(parts):
+            return np.ascontiguousarray(np.concatenate(parts).astype(np.int32))
+
+        for name, comp, kind in heads:
+            if kind == "ner":
+                self.slots[name] = (cat([comp.gold_actions(eg.reference) for eg in examples]), self.doc_off, False)
+            elif kind == "parser":
+                g = [comp._gold_np(eg.reference) for eg in examples]
+                self.slots[name + ".heads"] = (cat([h for h, _ in g]), self.doc_off, False)
+                self.slots[name + ".labels"] = (cat([l for _, l in g]), self.doc_off, False)
+            elif kind == "tagger":
+                index = {l: i for i, l in enumerate(comp.labels)}
+                end = np.array([-1], dtype=np.int32)
+                parts = []
+                for eg in examples:
+                    tags = eg.reference.tags or [None] * len(eg.reference)
+                    parts.append(np.array([index.get(t, -1) if t else -1 for t in tags], dtype=np.int32))
+                    parts.append(end)
+                self.slots[name] = (cat(parts), self.doc_off_padded, True)
         self.lens = lens
         self.n_docs = len(examples)
         self.max_len = int(lens.max()) if len(lens) else 1
@@ -60,12 +91,13 @@ class _Layout:
     rows: int
     docs: int
     lmax: int
+    slots: tuple = ()
     off_attrs: int = 0
     off_mask: int = 0
     off_starts: int = 0
     off_lens: int = 0
     off_tok: int = 0
-    off_gold: int = 0
+    off_gold: Any = None
     off_inv: int = 0
     off_meta: int = 0
     nbytes: int = 0
@@ -77,7 +109,10 @@ class _Layout:
         self.off_starts = o; o = _align(o + self.docs * 4)
         self.off_lens = o; o = _align(o + self.docs * 4)
         self.off_tok = o; o = _align(o + self.docs * 4)
-        self.off_gold = o; o = _align(o + self.rows * 4)
+        self.off_gold = {}
+        for key in self.slots:
+            self.off_gold[key] = o; o = _align(o + self.rows * 4)
+        self.off_scratch = o; o = _align(o + self.docs * 4)
         self.off_inv = o; o = _align(o + self.lmax * 4)
         self.off_meta = o; o = _align(o + 16)
         self.nbytes = o
@@ -97,40 +132,106 @@ class _Views:
         self.starts = v(lay.off_starts, lay.docs, torch.int32)
         self.lens = v(lay.off_lens, lay.docs, torch.int32)
         self.tok_off = v(lay.off_tok, lay.docs, torch.int32)
-        self.gold = v(lay.off_gold, lay.rows, torch.int32)
+        self.gold = {k: v(off, lay.rows, torch.int32) for k, off in lay.off_gold.items()}
+        self.scratch = v(lay.off_scratch, lay.docs, torch.int32)
         self.inv_active = v(lay.off_inv, lay.lmax, torch.float32)
         self.meta = v(lay.off_meta, 4, torch.int32)
 
 
+def make_stage(lay: _Layout, store: ExampleStore, pin: bool = True) -> dict:
+    """One packed host staging buffer (pinned for the async H2D copy) + numpy views into it."""
+    hb = torch.zeros(lay.nbytes, dtype=torch.uint8, pin_memory=pin)
+    hv = _Views(lay, hb)
+    arrs = {k: getattr(hv, k).numpy() for k in
+            ("attrs", "mask", "starts", "lens", "tok_off", "inv_active", "meta", "scratch")}
+    arrs["gold"] = {k: t.numpy() for k, t in hv.gold.items()}
+    for key, (_arr, _off, padded) in store.slots.items():
+        if padded:
+            arrs["gold"][key][:] = -1              # rows past the batch carry "no gold"
+    return {"buf": hb, "np": arrs, "event": None, "rows": 0, "docs": 0, "words": 0}
+
+
+def fill_stage(st: ExampleStore, lay: _Layout, stage: dict, ids: np.ndarray) -> None:
+    """Gather docs ``ids`` into the packed staging buffer (native memcpy loops)."""
+    if stage["event"] is not None:
+        stage["event"].synchronize()               # previous H2D out of this buffer has completed
+    a = stage["np"]
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    rows = native.collate(st.attrs, st.doc_off, ids, a["attrs"], a["mask"], a["starts"], a["lens"])
+    words = int(st.lens[ids].sum())
+    first = True
+    for key, (arr, doc_off, padded) in st.slots.items():
+        out = a["gold"][key]
+        if padded:                                 # row 0 is the batch's leading pad row
+            out[0] = -1
+            used = native.collate_gold(arr, doc_off, ids, out[1:], a["scratch"])
+            out[1 + used: max(stage["rows"], 1 + used)] = -1
+        else:
+            native.collate_gold(arr, doc_off, ids, out, a["tok_off"] if first else a["scratch"])
+            first = False
+    if first:                                      # no token-order slot filled tok_off
+        lens_i = st.lens[ids]
+        a["tok_off"][: len(ids)] = (np.cumsum(lens_i) - lens_i).astype(np.int32)
+    if len(ids) < lay.docs:                        # partial batch: the unused doc slots are empty docs
+        a["lens"][len(ids):] = 0
+        a["starts"][len(ids):] = 0
+        a["tok_off"][len(ids):] = 0
+    lens = a["lens"][: len(ids)]
+    counts = (lens[None, :] > np.arange(lay.lmax, dtype=np.int32)[:, None]).sum(axis=1)
+    a["inv_active"][:] = 1.0 / np.maximum(counts, 1)
+    a["meta"][0] = rows
+    stage["rows"], stage["docs"], stage["words"] = int(rows), len(ids), int(words)
+
+
 class Trainer:
+    @staticmethod
+    def unsupported_reason(nlp, max_len: Optional[int] = None) -> Optional[str]:
+        """Why this pipeline cannot run device-resident (None = it can)."""
+        heads = [(n, c, _kind(c)) for n, c in nlp.pipeline if getattr(c, "is_trainable", False)]
+        if not heads:
+            return "no trainable component"
+        for name, comp, kind in heads:
+            if kind is None:
+                return f"component {name!r} ({comp.__class__.__name__}) has no device-side update"
+            if kind in ("ner", "parser"):
+                lower = comp.model.get_ref("lower").get_param("W")
+                _nF, nO, nP, _nI = lower.shape
+                nA = comp.system.n_actions
+                if kind == "ner" and (nP != 2 or nO % 32 or (nO * nP) // 32 > 8 or nA > 256):
+                    return f"{name}: hidden_width/maxout_pieces outside the BILUO kernel's range"
+                if kind == "parser" and (nO % 32 or nO // 32 not in (1, 2, 4) or nP not in (2, 3) or nA > 192):
+                    return f"{name}: hidden_width/maxout_pieces/labels outside the arc-eager kernel's range"
+                if kind == "parser" and max_len is not None and max_len > 128:
+                    return f"{name}: documents longer than 128 tokens"
+        if all(kind == "tok2vec" for _, _, kind in heads):
+            return "no head component"
+        return None
+
     def __init__(self, nlp, proxy, examples: Sequence[Any], *, docs_per_batch: int, dropout: float = 0.1,
-                 component: str = "ner", use_graphs: bool = True, bucket_rows: int = 1024, prefetch: bool = True,
-                 n_stage: int = 3):
+                 component: Optional[str] = None, use_graphs: bool = True, bucket_rows: int = 1024,
+                 prefetch: bool = True, n_stage: int = 3):
         self.nlp, self.proxy = nlp, proxy
-        self.ner = nlp.get_pipe(component)
-        self.ops = self.ner.model.ops
+        self.heads = [(n, c, _kind(c)) for n, c in nlp.pipeline if getattr(c, "is_trainable", False)]
+        self.loss_names = [n for n, _c, k in self.heads if k != "tok2vec"]
+        self.ops = self.heads[0][1].model.ops
         if self.ops.device.type != "cuda":
             raise ValueError("Trainer needs the CUDA backend; use nlp.update on CPU")
         self.device = self.ops.device
         self.dropout = float(dropout)
         self.B = int(docs_per_batch)
-        self.store = ExampleStore(examples, self.ner)
+        self.store = ExampleStore(examples, self.heads)
+        why = self.unsupported_reason(nlp, self.store.max_len)
+        if why is not None:
+            raise ValueError(f"pipeline not supported by the device-resident engine: {why}")
         self._doc_index = {id(eg.reference): i for i, eg in enumerate(examples)}
         self.bucket_rows = int(bucket_rows)
         rows_cap = _align(self.B * self.store.max_len + self.B + 1, self.bucket_rows)
-        self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64))
+        self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64),
+                           slots=tuple(self.store.slots))
         self.use_graphs = use_graphs
         self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
         self.dv = _Views(self.lay, self.dev_buf)
-        self.stages = []
-        for _ in range(n_stage):
-            hb = torch.zeros(self.lay.nbytes, dtype=torch.uint8, pin_memory=True)
-            hv = _Views(self.lay, hb)
-            self.stages.append({
-                "buf": hb, "np": {k: getattr(hv, k).numpy() for k in
-                                  ("attrs", "mask", "starts", "lens", "tok_off", "gold", "inv_active", "meta")},
-                "event": None, "rows": 0, "docs": 0, "words": 0,
-            })
+        self.stages = [make_stage(self.lay, self.store, pin=True) for _ in range(n_stage)]
         self._graphs: Dict[int, Any] = {}
         self._pool = torch.cuda.graph_pool_handle() if use_graphs else None
         self._warmed = False
@@ -150,23 +251,7 @@ class Trainer:
 
     # ------------------------------------------------------------------ host side
     def _fill(self, stage: dict, ids: np.ndarray) -> None:
-        """Gather docs ``ids`` into the packed pinned buffer (native memcpy loops)."""
-        if stage["event"] is not None:
-            stage["event"].synchronize()           # previous H2D out of this buffer has completed
-        a = stage["np"]
-        st = self.store
-        ids = np.ascontiguousarray(ids, dtype=np.int64)
-        rows = native.collate(st.attrs, st.doc_off, ids, a["attrs"], a["mask"], a["starts"], a["lens"])
-        words = native.collate_gold(st.gold, st.doc_off, ids, a["gold"], a["tok_off"])
-        if len(ids) < self.B:                       # partial batch: the unused doc slots are empty docs
-            a["lens"][len(ids):] = 0
-            a["starts"][len(ids):] = 0
-            a["tok_off"][len(ids):] = 0
-        lens = a["lens"][: len(ids)]
-        counts = (lens[None, :] > np.arange(self.lay.lmax, dtype=np.int32)[:, None]).sum(axis=1)
-        a["inv_active"][:] = 1.0 / np.maximum(counts, 1)
-        a["meta"][0] = rows
-        stage["rows"], stage["docs"], stage["words"] = int(rows), len(ids), int(words)
+        fill_stage(self.store, self.lay, stage, ids)
 
     def _prefetch_loop(self) -> None:
         while True:
@@ -199,15 +284,32 @@ class Trainer:
         )
         tb.extra["tok_off"] = dv.tok_off
         tb.extra["inv_active"] = dv.inv_active
-        return tb, TransitionGold(actions=dv.gold[:rows], offsets=None)
+        return tb
 
     def _step_fn(self, rows: int) -> torch.Tensor:
-        tb, gold = self._batch_views(rows)
+        """Forward + backward of every component, then the gradient exchange + optimizer.
+        Returns the per-head losses as one small device vector (``loss_names`` order)."""
+        tb = self._batch_views(rows)
+        gold = self.dv.gold
         self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
-        set_dropout_rate(self.ner.model, self.dropout)
-        out = self.ner.model.attrs["run"](tb, self.ner.system, gold, True)
+        losses = []
+        for name, comp, kind in self.heads:
+            if kind == "tok2vec":
+                # forward now; its backward fires when the last listener returns its gradient
+                comp.update((), batch=tb, drop=self.dropout, sgd=False, losses=None)
+                continue
+            set_dropout_rate(comp.model, self.dropout)
+            if kind == "tagger":
+                loss, _ = comp.model.attrs["update_with_labels"](tb, gold[name][:rows].to(torch.int64))
+            elif kind == "ner":
+                g = TransitionGold(actions=gold[name][:rows], offsets=None)
+                loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
+            else:
+                g = TransitionGold(heads_flat=gold[name + ".heads"][:rows], labels_flat=gold[name + ".labels"][:rows])
+                loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
+            losses.append(loss.reshape(()).to(torch.float32))
         self.proxy.step()
-        return out.loss
+        return losses[0].reshape(1) if len(losses) == 1 else torch.stack(losses)
 
     def _bucket(self, rows: int) -> int:
         return min(self.lay.rows, _align(rows, self.bucket_rows))
@@ -284,7 +386,10 @@ class Trainer:
         """The public one-call step: (collate if ``ids`` given) -> H2D -> step -> loss (D2H)."""
         if ids is not None:
             self.prepare(ids)
-        return float(self.step_async().item())
+        return float(self.step_async().sum().item())
+
+    def losses_dict(self, loss_vec: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {n: loss_vec[i] for i, n in enumerate(self.loss_names)}
 
     def ids_for(self, examples: Sequence[Any]) -> Optional[np.ndarray]:
         """Store indices of ``examples`` (matched by the identity of their reference Doc), or

@@ -317,7 +317,8 @@ class Language:
             # CUDA-graph replay of forward+backward+gradient exchange+optimizer
             loss = trainer.update_examples(examples)
             if loss is not None:
-                C._add_loss(losses, trainer.ner.name, loss)
+                for head, value in trainer.losses_dict(loss).items():
+                    C._add_loss(losses, head, value)
                 self._trainer_stepped = True
                 return losses
         batch = self.make_batch([eg.predicted for eg in examples])

@@ -334,27 +334,29 @@ class Worker:
 
     def _maybe_install_trainer(self) -> None:
         """On the B200 backend with the fused comm, serve ``nlp.update`` from the
-        device-resident engine when the pipeline is one it supports (a single NER head
-        today).  ``SRB_FAST_PATH=0`` keeps the generic per-op path."""
+        device-resident engine when the pipeline is one it supports (any mix of tok2vec /
+        tagger / ner / parser components whose heads fit the device kernels).
+        ``SRB_FAST_PATH=0`` keeps the generic per-op path."""
         ops = get_current_ops()
         if os.environ.get("SRB_FAST_PATH", "1") == "0" or not getattr(ops, "fused", False):
             return
         if getattr(self.proxy.comm, "name", "") != "fused":
-            return
-        pipes = [(n, c) for n, c in self.nlp.pipeline if getattr(c, "is_trainable", False)]
-        if len(pipes) != 1 or pipes[0][1].__class__.__name__ != "EntityRecognizer":
             return
         if set(self.T["frozen_components"]) or set(self.T["annotating_components"]):
             return
         try:
             from .engine import Trainer
 
+            why = Trainer.unsupported_reason(self.nlp)
+            if why is not None:
+                logger.info("rank %d: generic training path (%s)", self.rank, why)
+                return
             examples = list(self.train_corpus(self.nlp))
             if not examples:
                 return
             cap = int(os.environ.get("SRB_FAST_PATH_MAX_DOCS", 2048))
             self.nlp._trainer = Trainer(self.nlp, self.proxy, examples, docs_per_batch=min(cap, len(examples)),
-                                        dropout=float(self.T["dropout"]), component=pipes[0][0], prefetch=False)
+                                        dropout=float(self.T["dropout"]), prefetch=False)
             logger.info("rank %d: device-resident training engine enabled", self.rank)
         except Exception as e:       # never fatal: the generic path is always available
             logger.warning("rank %d: fast path unavailable (%s); using the generic path", self.rank, e)

@@ -121,3 +121,58 @@ def test_multitask_tagger_parser_ner_on_gpu():
     assert hist[-1]["tagger"] < hist[0]["tagger"]
     scores = nlp.evaluate(exs[:60])
     assert scores["tag_acc"] > 0.3 and scores["dep_uas"] is not None and scores["ents_f"] is not None
+
+
+def _shared_tok2vec_cfg(n_docs=300):
+    from pathlib import Path
+
+    text = (Path(__file__).resolve().parent.parent / "configs" / "multitask_w512.cfg").read_text()
+    text = text.replace("width = 512", "width = 64").replace("depth = 8", "depth = 2")
+    text = text.replace("hidden_width = 128", "hidden_width = 64").replace("n_docs = 20000", f"n_docs = {n_docs}")
+    return text.replace("max_len = 40", "max_len = 16")
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_engine_serves_multi_head_pipelines_like_the_generic_path(shared):
+    """engine.Trainer (packed staging buffer -> CUDA-graph step) must train a tagger+parser+ner
+    pipeline - with per-head tok2vecs and with one shared tok2vec + listeners - to the same losses
+    as the generic nlp.update path on the same batches."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.engine import Trainer
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.worker import Worker
+
+    text = _shared_tok2vec_cfg() if shared else multi_cfg(["tagger", "parser", "ner"], width=64, depth=2, n_docs=300,
+                                                          max_len=16, hidden=64)
+
+    def make():
+        fix_random_seed(0)
+        w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0, mode="sync",
+                   comm="auto")
+        w.set_proxy(None)
+        return w, list(w.train_corpus(w.nlp))
+
+    bs, steps = 32, 12
+    w_gen, exs = make()
+    generic = []
+    for step in range(steps):
+        losses = {}
+        w_gen.nlp.update(exs[step * 8: step * 8 + bs], drop=0.0, sgd=False, losses=losses)
+        w_gen.proxy.step()
+        generic.append({k: float(v) for k, v in losses.items()})
+    w_fast, exs2 = make()
+    trainer = Trainer(w_fast.nlp, w_fast.proxy, exs2, docs_per_batch=bs, dropout=0.0, prefetch=False)
+    assert trainer.loss_names == ["tagger", "parser", "ner"]
+    fast = []
+    for step in range(steps):
+        ids = np.arange(step * 8, step * 8 + bs)
+        trainer.prepare(ids)
+        vec = trainer.step_async()
+        fast.append({n: float(v) for n, v in trainer.losses_dict(vec).items()})
+    assert len(trainer._graphs) >= 1
+    trainer.close()
+    for g, f in zip(generic, fast):
+        for head in ("tagger", "parser", "ner"):
+            assert abs(g[head] - f[head]) <= 0.08 * abs(g[head]) + 0.02, (head, generic, fast)
+    assert fast[-1]["tagger"] < fast[0]["tagger"]

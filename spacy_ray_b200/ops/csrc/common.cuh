@@ -25,11 +25,27 @@ __device__ __forceinline__ void hash_rows(uint64_t id, uint64_t seed, uint32_t n
   rows[3] = (uint32_t)(h2 >> 32) % n_rows;
 }
 
-// Counter-based dropout (must match TorchOps.dropout_mask): keep iff u >= p.
+// Counter-based dropout (must match TorchOps.dropout_mask).  Elements are hashed in groups of
+// four: one fmix64 per group, 16 bits per element; keep iff u16 >= thr, thr = floor(p * 2^16).
+__host__ __device__ __forceinline__ uint32_t dropout_thr(float p) { return (uint32_t)(p * 65536.0f); }
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
-  uint64_t h = fmix64(idx + seed * kGolden);
-  float u = (float)(h >> 40) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+  const uint64_t h = fmix64((idx >> 2) + seed * kGolden);
+  const uint32_t u = (uint32_t)(h >> (16 * (uint32_t)(idx & 3))) & 0xFFFFu;
+  return u >= dropout_thr(p) ? inv_keep : 0.0f;
+}
+// Eight consecutive elements starting at idx (idx % 8 == 0): two hashes.
+__device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep,
+                                               float out[8]) {
+  const uint64_t base = (idx >> 2) + seed * kGolden;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const uint64_t h = fmix64(base + g);
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+    out[g * 4 + 0] = (lo & 0xFFFFu) >= thr ? inv_keep : 0.f;
+    out[g * 4 + 1] = (lo >> 16) >= thr ? inv_keep : 0.f;
+    out[g * 4 + 2] = (hi & 0xFFFFu) >= thr ? inv_keep : 0.f;
+    out[g * 4 + 3] = (hi >> 16) >= thr ? inv_keep : 0.f;
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

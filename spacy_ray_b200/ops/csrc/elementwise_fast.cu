@@ -13,8 +13,13 @@ namespace srb {
 
 // ------------------------------------------------------------------------------------------
 // forward: Z (Tp, nO*NP) [+bias] -> maxout -> LN -> dropout -> (+X) -> mask
+//
+// One warp per row, a lane owns UPL contiguous units.  A row is only 16-48 B per lane, so a
+// warp walks R rows per iteration and issues every load of all R rows before the first use:
+// that is what keeps enough bytes in flight per SM to cover HBM latency (the one-row version
+// sat at ~35% of copy bandwidth with 24 resident warps x 1 KB).
 // ------------------------------------------------------------------------------------------
-template <int NP, int UPL>
+template <int NP, int UPL, int R>
 __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
     const __nv_bfloat16* __restrict__ Z, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ G,
     const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
@@ -27,96 +32,115 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const uint32_t thr = dropout_thr(drop_p);
   const bool has_ln = G != nullptr;
   const int u0 = lane * UPL;
-  float gk[UPL], bk[UPL], bz[ZPL];
+  float gk[UPL], bk[UPL];
 #pragma unroll
   for (int j = 0; j < UPL; ++j) { gk[j] = has_ln ? bf2f(G[u0 + j]) : 1.f; bk[j] = has_ln ? bf2f(beta[u0 + j]) : 0.f; }
+  const int ngroups = (Tp + R - 1) / R;
+  for (int grp = gwarp; grp < ngroups; grp += nwarps) {
+    const int row0 = grp * R;
+    // ---- phase 1: every load of the R rows (pad rows are valid memory, loaded unconditionally)
+    bf16x8 zraw[R][ZPL / 8];
+    bf16x8 xraw[R][UPL / 8];
+    float mk[R];
 #pragma unroll
-  for (int j = 0; j < ZPL; ++j) bz[j] = bias ? bf2f(bias[u0 * NP + j]) : 0.f;
-  for (int row = gwarp; row < Tp; row += nwarps) {
-    const size_t ro = (size_t)row * nO + u0;
-    if (mask[row] == 0.0f) {
-      bf16x8 zero;
+    for (int r = 0; r < R; ++r) {
+      const int row = min(row0 + r, Tp - 1);
+      mk[r] = mask[row];
+      const bf16x8* zp = (const bf16x8*)(Z + (size_t)row * nO * NP + u0 * NP);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+      for (int v = 0; v < ZPL / 8; ++v) zraw[r][v] = zp[v];
+      if (Xres) {
+        const bf16x8* xp = (const bf16x8*)(Xres + (size_t)row * nO + u0);
+#pragma unroll
+        for (int v = 0; v < UPL / 8; ++v) xraw[r][v] = xp[v];
+      }
+    }
+    // ---- phase 2: one row at a time out of registers
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= Tp) break;
+      const size_t ro = (size_t)row * nO + u0;
+      if (mk[r] == 0.0f) {
+        bf16x8 zero;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+#pragma unroll
+        for (int v = 0; v < UPL / 8; ++v) {
+          *(bf16x8*)(Y + ro + v * 8) = zero;
+          if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = zero;
+          if (which) *(uint2*)(which + ro + v * 8) = make_uint2(0u, 0u);
+        }
+        if (lane == 0 && rstd_out) rstd_out[row] = 0.f;
+        continue;
+      }
+      float h[UPL];
+      uint8_t wh[UPL];
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < UPL; ++j) {
+        float best = 0.f;
+        int bi = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int e = j * NP + p;
+          float zv = bf2f(zraw[r][e / 8].v[e % 8]);
+          if (bias) zv += bf2f(bias[u0 * NP + e]);
+          if (p == 0 || zv > best) { best = zv; bi = p; }
+        }
+        h[j] = best; wh[j] = (uint8_t)bi; sum += best;
+      }
+      float mu = 0.f, rstd = 1.f;
+      if (has_ln) {
+        mu = warp_sum(sum) * (1.f / nO);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) { const float d = h[j] - mu; sq += d * d; }
+        rstd = rsqrtf(warp_sum(sq) * (1.f / nO) + 1e-8f);
+      }
 #pragma unroll
       for (int v = 0; v < UPL / 8; ++v) {
-        *(bf16x8*)(Y + ro + v * 8) = zero;
-        if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = zero;
-        if (which) *(uint2*)(which + ro + v * 8) = make_uint2(0u, 0u);
+        bf16x8 yo, xo;
+        __align__(8) uint8_t w8[8];
+        float keep[8];
+        if (drop_p > 0.f) dropout_scale8(seed, ro + v * 8, thr, inv_keep, keep);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = v * 8 + i;
+          const float xh = (h[j] - mu) * rstd;
+          float n = has_ln ? xh * gk[j] + bk[j] : h[j];
+          if (drop_p > 0.f) n *= keep[i];
+          if (Xres) n += bf2f(xraw[r][v].v[i]);
+          yo.v[i] = f2bf(n);
+          xo.v[i] = f2bf(xh);
+          w8[i] = wh[j];
+        }
+        *(bf16x8*)(Y + ro + v * 8) = yo;
+        if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = xo;
+        if (which) *(uint2*)(which + ro + v * 8) = *(const uint2*)w8;
       }
-      if (lane == 0 && rstd_out) rstd_out[row] = 0.f;
-      continue;
+      if (lane == 0 && rstd_out) rstd_out[row] = rstd;
     }
-    float z[ZPL];
-    const bf16x8* zp = (const bf16x8*)(Z + (size_t)row * nO * NP + u0 * NP);
-#pragma unroll
-    for (int v = 0; v < ZPL / 8; ++v) {
-      bf16x8 t = zp[v];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) z[v * 8 + i] = bf2f(t.v[i]) + bz[v * 8 + i];
-    }
-    float h[UPL];
-    uint8_t wh[UPL];
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < UPL; ++j) {
-      float best = z[j * NP];
-      int bi = 0;
-#pragma unroll
-      for (int p = 1; p < NP; ++p) if (z[j * NP + p] > best) { best = z[j * NP + p]; bi = p; }
-      h[j] = best; wh[j] = (uint8_t)bi; sum += best;
-    }
-    float mu = 0.f, rstd = 1.f;
-    if (has_ln) {
-      mu = warp_sum(sum) * (1.f / nO);
-      float sq = 0.f;
-#pragma unroll
-      for (int j = 0; j < UPL; ++j) { const float d = h[j] - mu; sq += d * d; }
-      rstd = rsqrtf(warp_sum(sq) * (1.f / nO) + 1e-8f);
-    }
-    float xr[UPL];
-#pragma unroll
-    for (int j = 0; j < UPL; ++j) xr[j] = 0.f;
-    if (Xres) {
-#pragma unroll
-      for (int v = 0; v < UPL / 8; ++v) {
-        bf16x8 t = *(const bf16x8*)(Xres + ro + v * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xr[v * 8 + i] = bf2f(t.v[i]);
-      }
-    }
-#pragma unroll
-    for (int v = 0; v < UPL / 8; ++v) {
-      bf16x8 yo, xo;
-      __align__(8) uint8_t w8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = v * 8 + i;
-        const float xh = (h[j] - mu) * rstd;
-        float n = has_ln ? xh * gk[j] + bk[j] : h[j];
-        if (drop_p > 0.f) n *= dropout_scale(seed, ro + j, drop_p, inv_keep);
-        n += xr[j];
-        yo.v[i] = f2bf(n);
-        xo.v[i] = f2bf(xh);
-        w8[i] = wh[j];
-      }
-      *(bf16x8*)(Y + ro + v * 8) = yo;
-      if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = xo;
-      if (which) *(uint2*)(which + ro + v * 8) = *(const uint2*)w8;
-    }
-    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
   }
+}
+
+// rows per warp iteration: aim at ~128 B of loads in flight per lane
+constexpr int rows_per_iter(int bytes_per_lane_row) {
+  return bytes_per_lane_row <= 32 ? 4 : (bytes_per_lane_row <= 64 ? 2 : 1);
 }
 
 template <int NP, int UPL>
 static void launch_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
                            const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, float drop_p,
                            uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
-  int blocks = (Tp + 7) / 8;
+  constexpr int R = rows_per_iter((UPL * NP + UPL) * 2);
+  int blocks = (Tp + 8 * R - 1) / (8 * R);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  maxout_ln_fwd_vec_kernel<NP, UPL><<<blocks, 256, 0, s>>>(
+  if (blocks < 1) blocks = 1;
+  maxout_ln_fwd_vec_kernel<NP, UPL, R><<<blocks, 256, 0, s>>>(
       (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta,
       (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, drop_p, seed,
       seed_dev);
@@ -137,8 +161,9 @@ bool try_launch_maxout_ln_fwd_vec(const void* Z, const void* bias, const void* G
 
 // ------------------------------------------------------------------------------------------
 // backward: dY -> dropout -> LN backward -> routed dZ; accumulates dG, dbeta, db
+// (same R-rows-per-iteration load batching as the forward kernel)
 // ------------------------------------------------------------------------------------------
-template <int NP, int UPL>
+template <int NP, int UPL, int R>
 __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
     const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ xhat, const float* __restrict__ rstd_in,
     const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
@@ -151,6 +176,7 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const uint32_t thr = dropout_thr(drop_p);
   const int u0 = lane * UPL;
   float gk[UPL];
 #pragma unroll
@@ -160,64 +186,85 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
   for (int j = 0; j < UPL; ++j) { accG[j] = 0.f; accB[j] = 0.f; }
 #pragma unroll
   for (int j = 0; j < ZPL; ++j) accb[j] = 0.f;
-  for (int row = gwarp; row < Tp; row += nwarps) {
-    const size_t ro = (size_t)row * nO + u0;
-    bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
-    if (mask[row] == 0.0f) {
-      bf16x8 zero;
+  const int ngroups = (Tp + R - 1) / R;
+  for (int grp = gwarp; grp < ngroups; grp += nwarps) {
+    const int row0 = grp * R;
+    bf16x8 draw[R][UPL / 8], xraw[R][UPL / 8];
+    uint2 wraw[R][UPL / 8];
+    float mk[R], rs[R];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+    for (int r = 0; r < R; ++r) {
+      const int row = min(row0 + r, Tp - 1);
+      const size_t ro = (size_t)row * nO + u0;
+      mk[r] = mask[row];
+      rs[r] = has_ln ? rstd_in[row] : 1.f;
 #pragma unroll
-      for (int v = 0; v < ZPL / 8; ++v) zout[v] = zero;
-      continue;
+      for (int v = 0; v < UPL / 8; ++v) {
+        draw[r][v] = *(const bf16x8*)(dY + ro + v * 8);
+        if (has_ln) xraw[r][v] = *(const bf16x8*)(xhat + ro + v * 8);
+        wraw[r][v] = *(const uint2*)(which + ro + v * 8);
+      }
     }
-    float dn[UPL], xh[UPL];
-    uint8_t wh[UPL];
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < UPL / 8; ++v) {
-      bf16x8 d8 = *(const bf16x8*)(dY + ro + v * 8);
-      bf16x8 x8;
-      if (has_ln) x8 = *(const bf16x8*)(xhat + ro + v * 8);
-      const uint2 w2 = *(const uint2*)(which + ro + v * 8);
-      const uint8_t* wb = (const uint8_t*)&w2;
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= Tp) break;
+      const size_t ro = (size_t)row * nO + u0;
+      bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
+      if (mk[r] == 0.0f) {
+        bf16x8 zero;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = v * 8 + i;
-        float d = bf2f(d8.v[i]);
-        if (drop_p > 0.f) d *= dropout_scale(seed, ro + j, drop_p, inv_keep);
-        wh[j] = wb[i];
-        if (has_ln) {
-          xh[j] = bf2f(x8.v[i]);
-          accG[j] += d * xh[j];
-          accB[j] += d;
-          d *= gk[j];
-          s1 += d; s2 += d * xh[j];
-        } else {
-          xh[j] = 0.f;
+        for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+#pragma unroll
+        for (int v = 0; v < ZPL / 8; ++v) zout[v] = zero;
+        continue;
+      }
+      float dn[UPL], xh[UPL];
+      uint8_t wh[UPL];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < UPL / 8; ++v) {
+        const uint8_t* wb = (const uint8_t*)&wraw[r][v];
+        float keep[8];
+        if (drop_p > 0.f) dropout_scale8(seed, ro + v * 8, thr, inv_keep, keep);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = v * 8 + i;
+          float d = bf2f(draw[r][v].v[i]);
+          if (drop_p > 0.f) d *= keep[i];
+          wh[j] = wb[i];
+          if (has_ln) {
+            xh[j] = bf2f(xraw[r][v].v[i]);
+            accG[j] += d * xh[j];
+            accB[j] += d;
+            d *= gk[j];
+            s1 += d; s2 += d * xh[j];
+          } else {
+            xh[j] = 0.f;
+          }
+          dn[j] = d;
         }
-        dn[j] = d;
       }
-    }
-    float rstd = 1.f;
-    if (has_ln) {
-      rstd = rstd_in[row];
-      s1 = warp_sum(s1) * (1.f / nO);
-      s2 = warp_sum(s2) * (1.f / nO);
-    }
-    __align__(16) __nv_bfloat16 zo[ZPL];
-#pragma unroll
-    for (int j = 0; j < UPL; ++j) {
-      const float dH = has_ln ? rstd * (dn[j] - s1 - xh[j] * s2) : dn[j];
-#pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        const float val = (q == wh[j]) ? dH : 0.f;
-        zo[j * NP + q] = f2bf(val);
-        accb[j * NP + q] += val;
+      float rstd = 1.f;
+      if (has_ln) {
+        rstd = rs[r];
+        s1 = warp_sum(s1) * (1.f / nO);
+        s2 = warp_sum(s2) * (1.f / nO);
       }
-    }
+      __align__(16) __nv_bfloat16 zo[ZPL];
 #pragma unroll
-    for (int v = 0; v < ZPL / 8; ++v) zout[v] = *(const bf16x8*)(zo + v * 8);
+      for (int j = 0; j < UPL; ++j) {
+        const float dH = has_ln ? rstd * (dn[j] - s1 - xh[j] * s2) : dn[j];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const float val = (q == wh[j]) ? dH : 0.f;
+          zo[j * NP + q] = f2bf(val);
+          accb[j * NP + q] += val;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < ZPL / 8; ++v) zout[v] = *(const bf16x8*)(zo + v * 8);
+    }
   }
   // combine the 8 warps of the block through shared memory, then one atomic per element
   extern __shared__ float sred[];                  // [8][nO*(NP+2)]
@@ -243,16 +290,17 @@ template <int NP, int UPL>
 static void launch_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G, const uint8_t* which,
                            const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, float drop_p,
                            uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s) {
+  constexpr int R = rows_per_iter(UPL * 5);          // dY + xhat (2 B each) + which (1 B) per unit
   int blocks = (Tp + 31) / 32;                       // >= 4 rows per warp so the flush is amortised
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   const size_t smem = sizeof(float) * 8 * 32 * UPL * (NP + 2);
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {
-    cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  maxout_ln_bwd_vec_kernel<NP, UPL><<<blocks, 256, smem, s>>>(
+  maxout_ln_bwd_vec_kernel<NP, UPL, R><<<blocks, 256, smem, s>>>(
       (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,
       (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln);
 }

@@ -197,13 +197,18 @@ class TorchOps:
 
     # ------------------------------------------------------------------ dropout
     def dropout_mask(self, seed: int, n_rows: int, n_cols: int, p: float) -> torch.Tensor:
-        """Counter-based Bernoulli mask, scaled by 1/(1-p).  Element (r, c) uses
-        ``u = top24(fmix64(seed*GOLDEN + r*n_cols + c)) / 2^24``; keep iff u >= p.
-        Stateless so a CUDA kernel regenerates the same mask in backward."""
+        """Counter-based Bernoulli mask, scaled by 1/(1-p).  Elements are hashed in groups of
+        four: ``h = fmix64(seed*GOLDEN + (idx >> 2))`` with ``idx = r*n_cols + c``; element ``idx``
+        takes bits ``16*(idx & 3) .. +16`` of ``h`` and is kept iff that value ``>= floor(p * 2^16)``
+        (float32 product, as the kernels compute it).  Stateless, so a CUDA kernel regenerates
+        the same mask in backward."""
+        import numpy as np
+
         idx = torch.arange(n_rows * n_cols, dtype=torch.int64, device=self.device)
-        h = _fmix64(idx + _s64(seed * _GOLDEN))
-        u = _lsr(h, 40).to(torch.float32) * (1.0 / (1 << 24))
-        keep = (u >= p).to(torch.float32) * (1.0 / (1.0 - p))
+        h = _fmix64((idx >> 2) + _s64(seed * _GOLDEN))
+        u = (h >> (16 * (idx & 3))) & 0xFFFF      # sign extension only touches the masked-off bits
+        thr = int(np.float32(p) * np.float32(65536.0))
+        keep = (u >= thr).to(torch.float32) * (1.0 / (1.0 - p))
         return keep.view(n_rows, n_cols)
 
     # ------------------------------------------------------------------ K2+K3+K4+K5 fused block

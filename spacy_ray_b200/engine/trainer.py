@@ -24,6 +24,7 @@ their device kernels (``Trainer.unsupported_reason``).  Everything else uses the
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 from dataclasses import dataclass
@@ -60,6 +61,15 @@ class ExampleStore:
         self.doc_off_padded = self.doc_off + np.arange(len(examples) + 1, dtype=np.int64)
         self.attrs = np.ascontiguousarray(
             np.concatenate([eg.predicted.to_array() for eg in examples]).view(np.int64))
+        # dense per-column vocabulary indices: lets the collate thread group each batch's rows by
+        # id with a counting sort (native.group_rows) instead of a device-side radix sort
+        n_attr = self.attrs.shape[1]
+        self.gid = np.empty(self.attrs.shape, dtype=np.int32)
+        self.n_groups = np.zeros(n_attr, dtype=np.int32)
+        for c in range(n_attr):
+            uniq, inv = np.unique(self.attrs[:, c], return_inverse=True)
+            self.gid[:, c] = inv.reshape(-1)
+            self.n_groups[c] = len(uniq)
         self.slots: Dict[str, tuple] = {}
 
         def cat(parts):
@@ -92,6 +102,8 @@ class _Layout:
     docs: int
     lmax: int
     slots: tuple = ()
+    bucket: int = 1024
+    n_attr: int = 4
     off_attrs: int = 0
     off_mask: int = 0
     off_starts: int = 0
@@ -113,6 +125,7 @@ class _Layout:
         for key in self.slots:
             self.off_gold[key] = o; o = _align(o + self.rows * 4)
         self.off_scratch = o; o = _align(o + self.docs * 4)
+        self.off_perm = o; o = _align(o + self.n_attr * self.rows * 4)
         self.off_inv = o; o = _align(o + self.lmax * 4)
         self.off_meta = o; o = _align(o + 16)
         self.nbytes = o
@@ -134,6 +147,7 @@ class _Views:
         self.tok_off = v(lay.off_tok, lay.docs, torch.int32)
         self.gold = {k: v(off, lay.rows, torch.int32) for k, off in lay.off_gold.items()}
         self.scratch = v(lay.off_scratch, lay.docs, torch.int32)
+        self.perm = v(lay.off_perm, lay.n_attr * lay.rows, torch.int32)
         self.inv_active = v(lay.off_inv, lay.lmax, torch.float32)
         self.meta = v(lay.off_meta, 4, torch.int32)
 
@@ -143,8 +157,9 @@ def make_stage(lay: _Layout, store: ExampleStore, pin: bool = True) -> dict:
     hb = torch.zeros(lay.nbytes, dtype=torch.uint8, pin_memory=pin)
     hv = _Views(lay, hb)
     arrs = {k: getattr(hv, k).numpy() for k in
-            ("attrs", "mask", "starts", "lens", "tok_off", "inv_active", "meta", "scratch")}
+            ("attrs", "mask", "starts", "lens", "tok_off", "inv_active", "meta", "scratch", "perm")}
     arrs["gold"] = {k: t.numpy() for k, t in hv.gold.items()}
+    arrs["hist"] = np.zeros(int(store.n_groups.sum()) + len(store.n_groups), dtype=np.int32)
     for key, (_arr, _off, padded) in store.slots.items():
         if padded:
             arrs["gold"][key][:] = -1              # rows past the batch carry "no gold"
@@ -180,6 +195,10 @@ def fill_stage(st: ExampleStore, lay: _Layout, stage: dict, ids: np.ndarray) -> 
     counts = (lens[None, :] > np.arange(lay.lmax, dtype=np.int32)[:, None]).sum(axis=1)
     a["inv_active"][:] = 1.0 / np.maximum(counts, 1)
     a["meta"][0] = rows
+    # HashEmbed backward: rows grouped by id per attribute column, laid out for the row bucket
+    # the step will run with (the captured graph reads perm as (n_attr, rb))
+    rb = min(lay.rows, _align(int(rows), lay.bucket))
+    native.group_rows(st.gid, st.n_groups, st.doc_off, ids, rb, a["perm"], a["hist"])
     stage["rows"], stage["docs"], stage["words"] = int(rows), len(ids), int(words)
 
 
@@ -227,7 +246,9 @@ class Trainer:
         self.bucket_rows = int(bucket_rows)
         rows_cap = _align(self.B * self.store.max_len + self.B + 1, self.bucket_rows)
         self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64),
-                           slots=tuple(self.store.slots))
+                           slots=tuple(self.store.slots), bucket=self.bucket_rows,
+                           n_attr=int(self.store.attrs.shape[1]))
+        self.host_grouping = os.environ.get("SRB_HOST_GROUP", "1") != "0"
         self.use_graphs = use_graphs
         self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
         self.dv = _Views(self.lay, self.dev_buf)
@@ -284,6 +305,9 @@ class Trainer:
         )
         tb.extra["tok_off"] = dv.tok_off
         tb.extra["inv_active"] = dv.inv_active
+        if self.host_grouping:
+            n_attr = self.lay.n_attr
+            tb.extra["embed_perm"] = dv.perm[: n_attr * rows].view(n_attr, rows)
         return tb
 
     def _step_fn(self, rows: int) -> torch.Tensor:

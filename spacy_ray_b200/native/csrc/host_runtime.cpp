@@ -10,6 +10,7 @@
 // Plain C ABI (loaded with ctypes), no Python headers needed.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 #include <string>
 
 namespace {
@@ -119,5 +120,41 @@ int64_t srb_collate_gold(const int32_t* store, const int64_t* doc_off, const int
   return pos;
 }
 
-int srb_abi_version() { return 1; }
+// HashEmbed-backward grouping, done on the collate thread so the training step needs no
+// device-side sort.  `gid` is the corpus-wide (n_tokens, n_cols) array of dense per-column
+// vocabulary indices (built once with the ExampleStore).  For the docs `ids` of one batch this
+// writes, per column c, out[c*rb ...]: the padded-layout row of every token of the batch, ordered
+// so that equal ids are adjacent (counting sort by vocabulary index - two linear passes, the
+// histograms stay cache resident).  The tail [n_tokens, rb) is filled with row 0 (a pad row:
+// mask 0, skipped by the kernel).  `hist` is caller scratch of sum(n_groups) + n_cols ints.
+int64_t srb_group_rows(const int32_t* gid, const int64_t* doc_off, const int64_t* ids, int64_t B, int32_t n_cols,
+                       const int32_t* n_groups, int64_t rb, int32_t* out, int32_t* hist) {
+  if (n_cols > 8) return -1;
+  int32_t* h[8];
+  int64_t pos = 0;
+  for (int32_t c = 0; c < n_cols; ++c) { h[c] = hist + pos; pos += n_groups[c] + 1; }
+  std::memset(hist, 0, sizeof(int32_t) * (size_t)pos);
+  int64_t n_tok = 0;
+  for (int64_t d = 0; d < B; ++d) {
+    const int64_t a = doc_off[ids[d]], e = doc_off[ids[d] + 1];
+    for (int64_t t = a; t < e; ++t)
+      for (int32_t c = 0; c < n_cols; ++c) ++h[c][gid[t * n_cols + c] + 1];
+    n_tok += e - a;
+  }
+  if (n_tok + B + 1 > rb) return -1;
+  for (int32_t c = 0; c < n_cols; ++c)
+    for (int32_t g = 0; g < n_groups[c]; ++g) h[c][g + 1] += h[c][g];      // exclusive starts in h[c][g]
+  int64_t row = 1;
+  for (int64_t d = 0; d < B; ++d) {
+    const int64_t a = doc_off[ids[d]], e = doc_off[ids[d] + 1];
+    for (int64_t t = a; t < e; ++t, ++row)
+      for (int32_t c = 0; c < n_cols; ++c) out[(size_t)c * rb + h[c][gid[t * n_cols + c]]++] = (int32_t)row;
+    ++row;                                                                  // the pad row between docs
+  }
+  for (int32_t c = 0; c < n_cols; ++c)
+    std::memset(out + (size_t)c * rb + n_tok, 0, sizeof(int32_t) * (size_t)(rb - n_tok));
+  return n_tok;
+}
+
+int srb_abi_version() { return 2; }
 }

@@ -31,8 +31,12 @@ def _load() -> Optional[ctypes.CDLL]:
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         lib.srb_collate_gold.restype = ctypes.c_int64
         lib.srb_abi_version.restype = ctypes.c_int
-        if lib.srb_abi_version() != 1:
+        if lib.srb_abi_version() != 2:
             return None
+        lib.srb_group_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+        lib.srb_group_rows.restype = ctypes.c_int64
         _lib = lib
     except OSError:
         _lib = None
@@ -110,3 +114,33 @@ def collate_gold(store: np.ndarray, doc_off: np.ndarray, ids: np.ndarray, out: n
         out[pos:pos + n] = store[a:b]
         pos += n
     return pos
+
+
+def group_rows(gid: np.ndarray, n_groups: np.ndarray, doc_off: np.ndarray, ids: np.ndarray, rb: int,
+               out: np.ndarray, scratch: np.ndarray) -> int:
+    """HashEmbed-backward grouping for one batch (see ``srb_group_rows``): per attribute column,
+    ``out[c*rb : (c+1)*rb]`` lists the padded-layout rows of the batch's tokens with equal ids
+    adjacent; the tail is row 0 (a pad row).  ``gid`` holds dense per-column vocabulary indices."""
+    n_cols = gid.shape[1]
+    assert gid.dtype == np.int32 and gid.flags.c_contiguous and out.dtype == np.int32 and out.size >= n_cols * rb
+    lib = _load()
+    if lib is not None:
+        n = lib.srb_group_rows(gid.ctypes.data, doc_off.ctypes.data, ids.ctypes.data, len(ids), n_cols,
+                               n_groups.ctypes.data, rb, out.ctypes.data, scratch.ctypes.data)
+        if n < 0:
+            raise ValueError("group_rows: batch does not fit the row capacity")
+        return int(n)
+    rows, toks, row = [], [], 1
+    for i in ids:
+        a, b = int(doc_off[i]), int(doc_off[i + 1])
+        rows.append(np.arange(row, row + (b - a), dtype=np.int32))
+        toks.append(np.arange(a, b))
+        row += (b - a) + 1
+    rows_a = np.concatenate(rows) if rows else np.zeros((0,), dtype=np.int32)
+    toks_a = np.concatenate(toks) if toks else np.zeros((0,), dtype=np.int64)
+    n = len(rows_a)
+    for c in range(n_cols):
+        order = np.argsort(gid[toks_a, c], kind="stable")
+        out[c * rb: c * rb + n] = rows_a[order]
+        out[c * rb + n: (c + 1) * rb] = 0
+    return n

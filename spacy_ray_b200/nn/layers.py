@@ -198,7 +198,8 @@ def MultiHashEmbed(
             if bufs is not None and any(b is None for b in bufs):
                 bufs = None
             grads = ops.multi_hash_embed_backward(
-                d_concat, batch.attrs, batch.mask, [int(t.shape[0]) for t in tables], seeds, cols, out=bufs
+                d_concat, batch.attrs, batch.mask, [int(t.shape[0]) for t in tables], seeds, cols, out=bufs,
+                perm=batch.extra.get("embed_perm"),
             )
             for e, g in zip(embeds, grads):
                 e.inc_grad("E", g)

@@ -123,7 +123,7 @@ class B200Ops(TorchOps):
         self.launches += 1
         return self.k.hash_embed_fwd(attrs, _mask1d(mask), list(tables), list(seeds), list(columns))
 
-    def multi_hash_embed_backward(self, dY, attrs, mask, n_rows, seeds, columns, out=None):
+    def multi_hash_embed_backward(self, dY, attrs, mask, n_rows, seeds, columns, out=None, perm=None):
         nO = dY.shape[1] // len(n_rows)
         grads = list(out) if out is not None else [
             torch.zeros((nV, nO), dtype=torch.float32, device=dY.device) for nV in n_rows
@@ -132,6 +132,15 @@ class B200Ops(TorchOps):
             # sort each table's attribute column once; the kernel then reduces runs of equal
             # ids in registers and touches each table row once per run (no hot-row contention)
             cols = tuple(int(c) for c in columns)
+            if perm is not None:
+                # rows already grouped by id per attribute column (host counting sort shipped with
+                # the batch by engine.Trainer): no device-side sort at all
+                if cols != tuple(range(perm.shape[0])):
+                    perm = torch.stack([perm[c] for c in cols], dim=0)
+                self.k.hash_embed_bwd_sorted(dY.contiguous(), attrs, perm.contiguous(), _mask1d(mask), grads,
+                                             list(seeds), list(columns))
+                self.launches += 1
+                return grads
             if cols == tuple(range(attrs.shape[1])):
                 keys = attrs.t().contiguous()                          # (n_tables, R)
             else:                                                      # no host->device index copy (graph-safe)

@@ -67,7 +67,8 @@ void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& p
                            std::vector<Tensor> grads, std::vector<int64_t> seeds, std::vector<int64_t> columns) {
   SRB_CHECK_CUDA(dY); SRB_CHECK_BF16(dY); SRB_CHECK_CUDA(keys); SRB_CHECK_CUDA(perm);
   // keys: the raw (R, n_attr) attribute array; perm: (n_tables, R) row order sorted per table
-  TORCH_CHECK(keys.scalar_type() == at::kLong && perm.scalar_type() == at::kLong && keys.dim() == 2);
+  TORCH_CHECK(keys.scalar_type() == at::kLong && keys.dim() == 2 && perm.is_contiguous() &&
+              (perm.scalar_type() == at::kLong || perm.scalar_type() == at::kInt));
   TORCH_CHECK(perm.size(0) == (int64_t)grads.size() && perm.size(1) == keys.size(0) && grads[0].size(1) <= 512);
   c10::cuda::CUDAGuard guard(dY.device());
   auto t = make_tables(grads, seeds, columns, (int)keys.size(1));
@@ -76,7 +77,8 @@ void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& p
     TORCH_CHECK(grads[a].scalar_type() == at::kFloat, "table gradients must be fp32");
     t.grad[a] = grads[a].data_ptr<float>();
   }
-  srb::launch_hash_embed_bwd_sorted(keys.data_ptr<int64_t>(), perm.data_ptr<int64_t>(), mask.data_ptr<float>(), t,
+  srb::launch_hash_embed_bwd_sorted(keys.data_ptr<int64_t>(), perm.data_ptr(), perm.scalar_type() == at::kInt,
+                                    mask.data_ptr<float>(), t,
                                     dY.data_ptr(), (int)perm.size(1), cur_stream());
 }
 

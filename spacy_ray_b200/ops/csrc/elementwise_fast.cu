@@ -326,11 +326,16 @@ __device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-constexpr int kSortChunk = 64;     // sorted positions per warp
+constexpr int kSortChunk = 32;     // sorted positions per warp (one per lane in the prologue)
 
-// keys: (n_tables, R) sorted attribute ids; perm: (n_tables, R) row of each sorted position.
+// keys: the raw (R, n_attr) attribute array; perm: (n_tables, R) rows grouped by id per table
+// (device radix sort on truncated keys, or the host-side grouping shipped with the batch).
+// Equal ids are adjacent; runs are split on the FULL 64-bit id.  A warp owns kSortChunk sorted
+// positions: the dependent perm -> mask/key loads happen once, lane-parallel, in the prologue;
+// the walk itself only waits on the dY row loads, which are issued four positions at a time.
+template <typename PermT>
 __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_t* __restrict__ keys,
-                                                                    const int64_t* __restrict__ perm,
+                                                                    const PermT* __restrict__ perm,
                                                                     const float* __restrict__ mask, HashEmbedTables t,
                                                                     const __nv_bfloat16* __restrict__ dY, int R) {
   const int a = blockIdx.y;
@@ -338,13 +343,19 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
   const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int p0 = chunk * kSortChunk;
   if (p0 >= R) return;
-  const int p1 = min(R, p0 + kSortChunk);
+  const int n = min(R, p0 + kSortChunk) - p0;
   const int C = t.n_tables * t.width;
   const int nvec = t.width / 8;                      // 16-byte vectors per table row (<= 64)
-  // `keys` is the raw (R, n_attr) attribute array: the sort ran on truncated 32-bit keys (half
-  // the radix passes); equal ids are still adjacent, and runs are split on the FULL 64-bit id.
-  const int64_t* pm = perm + (size_t)a * R;
+  const PermT* pm = perm + (size_t)a * R;
   const int col = t.column[a];
+  int my_row = 0;
+  float my_mask = 0.f;
+  int64_t my_key = 0;
+  if (lane < n) {
+    my_row = (int)pm[p0 + lane];
+    my_mask = mask[my_row];
+    my_key = keys[(size_t)my_row * t.n_attr + col];
+  }
   float acc[2][8];
 #pragma unroll
   for (int v = 0; v < 2; ++v)
@@ -372,30 +383,53 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
       }
     }
   };
-  for (int p = p0; p < p1; ++p) {
-    const int64_t row = pm[p];
-    if (mask[row] == 0.0f) continue;
-    const int64_t key = keys[(size_t)row * t.n_attr + col];
-    if (have && key != cur) flush();
-    cur = key; have = true;
+  constexpr int kBatch = 4;
+  for (int i0 = 0; i0 < n; i0 += kBatch) {
+    int rowb[kBatch];
+    float mb[kBatch];
+    int64_t keyb[kBatch];
+    bf16x8 g[kBatch][2];
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int vec = lane + 32 * v;
-      if (vec < nvec) {
-        bf16x8 g = *(const bf16x8*)(dY + (size_t)row * C + a * t.width + vec * 8);
+    for (int j = 0; j < kBatch; ++j) {
+      const int src = min(i0 + j, kSortChunk - 1);
+      rowb[j] = __shfl_sync(0xffffffffu, my_row, src);
+      mb[j] = (i0 + j < n) ? __shfl_sync(0xffffffffu, my_mask, src) : 0.f;
+      keyb[j] = __shfl_sync(0xffffffffu, my_key, src);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[v][i] += bf2f(g.v[i]);
+      for (int v = 0; v < 2; ++v) {
+        const int vec = lane + 32 * v;
+        if (vec < nvec && mb[j] != 0.f)
+          g[j][v] = *(const bf16x8*)(dY + (size_t)rowb[j] * C + a * t.width + vec * 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      if (mb[j] == 0.f) continue;                   // warp-uniform
+      if (have && keyb[j] != cur) flush();
+      cur = keyb[j]; have = true;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int vec = lane + 32 * v;
+        if (vec < nvec) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[v][i] += bf2f(g[j][v].v[i]);
+        }
       }
     }
   }
   flush();
 }
 
-void launch_hash_embed_bwd_sorted(const int64_t* keys, const int64_t* perm, const float* mask, HashEmbedTables t,
-                                  const void* dY, int R, cudaStream_t s) {
+void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool perm_is_i32, const float* mask,
+                                  HashEmbedTables t, const void* dY, int R, cudaStream_t s) {
   if (R <= 0) return;
   dim3 grid((R + kSortChunk * 4 - 1) / (kSortChunk * 4), t.n_tables);
-  hash_embed_bwd_sorted_kernel<<<grid, 128, 0, s>>>(keys, perm, mask, t, (const __nv_bfloat16*)dY, R);
+  if (perm_is_i32)
+    hash_embed_bwd_sorted_kernel<int32_t><<<grid, 128, 0, s>>>(keys, (const int32_t*)perm, mask, t,
+                                                               (const __nv_bfloat16*)dY, R);
+  else
+    hash_embed_bwd_sorted_kernel<int64_t><<<grid, 128, 0, s>>>(keys, (const int64_t*)perm, mask, t,
+                                                               (const __nv_bfloat16*)dY, R);
 }
 
 }  // namespace srb

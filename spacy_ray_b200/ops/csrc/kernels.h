@@ -47,7 +47,7 @@ bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float*
                                   float* dbeta, int Tp, int nO, int nP, float drop_p, uint64_t seed,
                                   const int64_t* seed_dev, int has_ln, cudaStream_t s);
 // K1 backward over ids sorted per table: keys/perm are (n_tables, R).
-void launch_hash_embed_bwd_sorted(const int64_t* keys, const int64_t* perm, const float* mask, HashEmbedTables t,
+void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool perm_is_i32, const float* mask, HashEmbedTables t,
                                   const void* dY, int R, cudaStream_t s);
 
 // K4 helpers for the library-GEMM path: materialised window / its transpose-add.

@@ -143,6 +143,7 @@ class TorchOps:
         seeds: Sequence[int],
         columns: Sequence[int],
         out: Optional[Sequence[torch.Tensor]] = None,
+        perm: Optional[torch.Tensor] = None,     # rows pre-grouped by id (used by the CUDA backend)
     ) -> List[torch.Tensor]:
         """``dE_a[rows_a[t, k]] += mask[t] * dY[t, a-block]`` for k in 0..3 (fp32)."""
         dY = dY.to(torch.float32) * mask.to(torch.float32)

@@ -51,6 +51,17 @@ def test_packed_buffer_matches_generic_batch_and_gold():
                                       np.concatenate([parser._gold_np(eg.reference)[0] for eg in chosen]))
         np.testing.assert_array_equal(a["gold"]["parser.labels"][:words],
                                       np.concatenate([parser._gold_np(eg.reference)[1] for eg in chosen]))
+        # HashEmbed-backward grouping: per attribute column, every token row exactly once with
+        # equal ids adjacent; the tail points at pad row 0
+        rb = min(lay.rows, -(-rows // lay.bucket) * lay.bucket)
+        token_rows = np.nonzero(a["mask"][:rows])[0]
+        for c in range(4):
+            perm = a["perm"][c * rb: (c + 1) * rb]
+            assert sorted(perm[:words].tolist()) == token_rows.tolist()
+            assert (perm[words:] == 0).all()
+            col_ids = a["attrs"][perm[:words], c]
+            n_runs = int((col_ids[1:] != col_ids[:-1]).sum()) + 1
+            assert n_runs == len(np.unique(col_ids))
         lens = np.array([len(eg) for eg in chosen])
         np.testing.assert_array_equal(a["tok_off"][: len(ids)], np.cumsum(lens) - lens)
     # typed views of the same bytes on the "device" side

@@ -61,6 +61,19 @@ def test_hash_embed_fwd_bwd(ops, ref):
     gr = ref.multi_hash_embed_backward(dY.float(), attrs, mask, rows, seeds, cols)
     for a, b in zip(g, gr):
         _close(a, b, 1e-3, 1e-3, "hash_embed_bwd")
+    # rows pre-grouped on the host (int32, what engine.Trainer ships with each batch); masked rows
+    # may appear anywhere (the kernel skips them) and the tail repeats row 0
+    host = attrs.cpu().numpy()
+    perm = np.stack([np.argsort(host[:, c], kind="stable") for c in range(4)]).astype(np.int32)
+    g2 = ops.multi_hash_embed_backward(dY, attrs, mask, rows, seeds, cols, perm=torch.from_numpy(perm).cuda())
+    for a, b in zip(g2, gr):
+        _close(a, b, 1e-3, 1e-3, "hash_embed_bwd(host perm)")
+    # a permuted table<->column assignment must pick the matching perm rows
+    cols2 = [3, 2, 1, 0]
+    g3 = ops.multi_hash_embed_backward(dY, attrs, mask, rows, seeds, cols2, perm=torch.from_numpy(perm).cuda())
+    gr3 = ref.multi_hash_embed_backward(dY.float(), attrs, mask, rows, seeds, cols2)
+    for a, b in zip(g3, gr3):
+        _close(a, b, 1e-3, 1e-3, "hash_embed_bwd(host perm, permuted columns)")
 
 
 # ---------------------------------------------------------------------------- tcgen05 GEMMs

@@ -10,7 +10,8 @@ issues a few hundred small launches per step from Python; on a B200 that is
 * **native collate** (``native/csrc/host_runtime.cpp``) gathers the docs of a batch
   into ONE packed pinned staging buffer (padded-ragged layout + gold + per-step
   scalars), on a prefetch thread that runs while the GPU executes the previous step;
-* **one H2D copy** of that buffer into a static device buffer;
+* **one H2D copy** of that buffer, issued on a side stream the moment the batch is collated
+  (so it overlaps the previous step), then a device-to-device move into the static graph input;
 * **one CUDA-graph replay** of the entire step - hash-embed, every tcgen05 GEMM,
   the BILUO kernel, the backward pass and the fused reduce-scatter/Adam/all-gather
   kernel - captured once per row-capacity bucket (rows rounded up to 1024);
@@ -253,6 +254,12 @@ class Trainer:
         self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
         self.dv = _Views(self.lay, self.dev_buf)
         self.stages = [make_stage(self.lay, self.store, pin=True) for _ in range(n_stage)]
+        for stage in self.stages:
+            # device landing buffer of this stage: the H2D copy runs on a side stream as soon as the
+            # batch is collated (i.e. while the previous step still executes); the step itself
+            # only does a device-to-device copy into the static graph input
+            stage["land"] = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
+            stage["consumed"] = None
         self._graphs: Dict[int, Any] = {}
         self._pool = torch.cuda.graph_pool_handle() if use_graphs else None
         self._warmed = False
@@ -274,7 +281,18 @@ class Trainer:
     def _fill(self, stage: dict, ids: np.ndarray) -> None:
         fill_stage(self.store, self.lay, stage, ids)
 
+    def _upload(self, stage: dict) -> None:
+        """Async H2D of a filled staging buffer into its landing buffer, on the side stream."""
+        with torch.cuda.stream(self._side):
+            if stage["consumed"] is not None:
+                self._side.wait_event(stage["consumed"])   # the step that read this landing buffer is done with it
+            stage["land"].copy_(stage["buf"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        stage["event"] = ev
+
     def _prefetch_loop(self) -> None:
+        torch.cuda.set_device(self.device)
         while True:
             item = self._q_in.get()
             if item is None:
@@ -282,6 +300,7 @@ class Trainer:
             stage, ids = item
             try:
                 self._fill(stage, ids)
+                self._upload(stage)
                 self._q_out.put((stage, None))
             except BaseException as e:          # surface in the training thread
                 self._q_out.put((stage, e))
@@ -294,6 +313,7 @@ class Trainer:
             self._q_in.put((stage, ids))
         else:
             self._fill(stage, ids)
+            self._upload(stage)
             self._q_out.put((stage, None))
 
     # ------------------------------------------------------------------ device side
@@ -397,10 +417,12 @@ class Trainer:
         stage, err = self._q_out.get()
         if err is not None:
             raise err
-        self.dev_buf.copy_(stage["buf"], non_blocking=True)         # ONE packed H2D copy
-        ev = torch.cuda.Event()
-        ev.record()
-        stage["event"] = ev
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(stage["event"])                              # the packed H2D copy (side stream)
+        self.dev_buf.copy_(stage["land"], non_blocking=True)        # D2D into the static graph input
+        done = torch.cuda.Event()
+        done.record(cur)
+        stage["consumed"] = done
         loss = self._run(stage["rows"])
         self.steps += 1
         self.last = {"docs": stage["docs"], "words": stage["words"], "rows": stage["rows"]}

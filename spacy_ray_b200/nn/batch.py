@@ -33,7 +33,9 @@ class TokenBatch:
 
     @property
     def n_docs(self) -> int:
-        return len(self.lengths)
+        # device-resident batches (engine.Trainer) carry no host-side lengths: their doc count is
+        # the static doc capacity of the staging buffer
+        return len(self.lengths) if self.lengths else int(self.doc_lens.shape[0])
 
     @property
     def device(self) -> torch.device:

@@ -2,6 +2,7 @@
 (``TorchOps``) of the same op.  Run on a B200: ``pytest -m gpu``."""
 import math
 
+import numpy as np
 import pytest
 import torch
 

@@ -131,7 +131,7 @@ def build_transition_model(
         upper.inc_grad("b", g["dbu"])
         lower.inc_grad("b", g["db"].reshape(nO_, nP_))
         lower.inc_grad("pad", g["dpad"].reshape(1, nF_, nO_, nP_))
-        dH, dWl2, _ = ops.linear_backward(g["dYf"], H, Wl2)
+        dH, dWl2, _ = ops.linear_backward(g["dYf"], H, Wl2, need_db=False)      # the precompute layer has no bias
         lower.inc_grad("W", dWl2.reshape(nF_, nO_, nP_, nI_))
         bp_t2v(bp_lin(dH))
         return out

@@ -23,7 +23,7 @@ from .torch_ops import TorchOps
 _LIB = Path(__file__).parent / "_srb_cuda.so"
 _loaded = False
 
-MODE_KK, MODE_MNMN = 0, 1
+MODE_KK, MODE_MNMN, MODE_KMN = 0, 1, 2
 EPI_STORE, EPI_MAXOUT3, EPI_ATOMIC_F32 = 0, 1, 2
 
 
@@ -187,8 +187,28 @@ class B200Ops(TorchOps):
                "has_ln": G is not None, "xhat": xhat, "rstd": rstd, "G": G, "drop": drop, "seed": seed}
         return Y, ctx
 
-    def _wt(self, W2: torch.Tensor) -> torch.Tensor:
-        return W2.t().contiguous()
+    def colsum(self, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 column sums of a (T, C) bf16 matrix (bias gradients), one kernel."""
+        C = X.shape[1]
+        if out is None:
+            out = torch.zeros((C,), dtype=torch.float32, device=X.device)
+        if X.dtype == torch.bfloat16 and C % 8 == 0 and C <= 2048 and X.stride(1) == 1 and X.stride(0) % 8 == 0:
+            self.k.colsum_acc(X, out)
+            self.launches += 1
+        else:
+            out.add_(X.to(torch.float32).sum(dim=0))
+        return out
+
+    def _dx_tc(self, dY: torch.Tensor, W: torch.Tensor) -> Optional[torch.Tensor]:
+        """dX = dY @ W on the tensor cores with W (nO, nI) as stored (MODE_KMN)."""
+        M, K = dY.shape
+        N = W.shape[1]
+        bn = self._pick_block_n(N)
+        if not (self._tc_ok(K) and bn and dY.dtype == torch.bfloat16 and W.dtype == torch.bfloat16):
+            return None
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=dY.device)
+        self.tc_gemm(dY, W.contiguous(), out, mode=MODE_KMN, epi=EPI_STORE, block_n=bn, M=M, N=N, K=K)
+        return out
 
     def maxout_block_backward(self, dY, ctx, grad_out: Optional[Dict[str, torch.Tensor]] = None):
         W = ctx["W"]
@@ -232,15 +252,17 @@ class B200Ops(TorchOps):
         # ---- dX ----------------------------------------------------------
         bn = self._pick_block_n(w_in)
         if self._tc_ok(N, w_in) and bn:
-            WT = self._wt(W2)                                     # (nI, N): K-major over the reduction dim N
+            # B = the weights as stored, (N, nI) = (K, N) row-major -> MN-major UMMA operand: no
+            # per-step transpose of W (it changes every step, so a cached W^T is useless)
+            W2c = W2.contiguous()
             dX = torch.empty((Tp, w_in), dtype=torch.bfloat16, device=dev)
             if window:
-                self.tc_gemm(dZ, WT, dX, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
-                             a_row_shift=(1, 0, -1), a_col_off=(0, 0, 0), b_row_off=(0, w_in, 2 * w_in),
-                             b_col_off=(0, 0, 0), add_src=dY if ctx["residual"] else None,
+                self.tc_gemm(dZ, W2c, dX, mode=MODE_KMN, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
+                             a_row_shift=(1, 0, -1), a_col_off=(0, 0, 0), b_row_off=(0, 0, 0),
+                             b_col_off=(0, w_in, 2 * w_in), add_src=dY if ctx["residual"] else None,
                              row_scale=ctx["mask"] if ctx["residual"] else None)
             else:
-                self.tc_gemm(dZ, WT, dX, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
+                self.tc_gemm(dZ, W2c, dX, mode=MODE_KMN, epi=EPI_STORE, block_n=bn, M=Tp, N=w_in, K=N,
                              add_src=dY if ctx["residual"] else None,
                              row_scale=ctx["mask"] if ctx["residual"] else None)
         else:
@@ -263,16 +285,16 @@ class B200Ops(TorchOps):
         Y = X @ W.t()
         return Y + b if b is not None else Y
 
-    def linear_backward(self, dY, X, W, need_dX: bool = True):
+    def linear_backward(self, dY, X, W, need_dX: bool = True, need_db: bool = True):
         dY = dY.to(torch.bfloat16).contiguous() if dY.dtype != torch.bfloat16 else dY.contiguous()
         X = X.contiguous()
         dW = self._dw_tc(dY, X, 0) if dY.shape[1] % 128 == 0 else None
         if dW is None:
             dW = _mm_f32(dY.t(), X)
-        db = dY.to(torch.float32).sum(dim=0)
+        db = self.colsum(dY) if need_db else None
         dX = None
         if need_dX:
-            dX = self._linear_tc(dY, W.t().contiguous(), None)
+            dX = self._dx_tc(dY, W)
             if dX is None:
                 dX = dY @ W
         return dX, dW, db
@@ -287,7 +309,7 @@ class B200Ops(TorchOps):
         d, guesses, loss = self.k.softmax_xent(logits.contiguous(), labels.contiguous())
         self.launches += 1
         dW = _mm_f32(d.t(), X)
-        db = d.to(torch.float32).sum(dim=0)
+        db = self.colsum(d)
         dX = d @ W
         return loss, d, guesses, dX, dW, db
 
@@ -325,7 +347,7 @@ class B200Ops(TorchOps):
             batch.n_tokens, nO, nP, system.n_labels, bool(is_train and gold_t is not None),
         )
         self.launches += 1
-        rec: Dict[str, Any] = {"actions_flat": actions.to(torch.int64), "loss": loss, "n_steps": 0}
+        rec: Dict[str, Any] = {"actions_flat": actions, "loss": loss, "n_steps": 0}      # int32
         if is_train and gold_t is not None:
             rec.update({"feats": feats, "which": which, "hid": hid, "d_scores": d_scores,
                         "n_steps": batch.n_tokens, "nA": system.n_actions})
@@ -378,7 +400,7 @@ class B200Ops(TorchOps):
         hid = rec["hid"]
         dev = d.device
         dWu = _mm_f32(d.t(), hid)[:nA]
-        dbu = d.to(torch.float32).sum(dim=0)[:nA]
+        dbu = self.colsum(d)[:nA]
         Wu = params["Wu"]
         Wu_pad = Wu if Wu.shape[0] == d.shape[1] else torch.cat(
             [Wu, torch.zeros((d.shape[1] - Wu.shape[0], Wu.shape[1]), dtype=Wu.dtype, device=dev)], 0)

@@ -82,6 +82,17 @@ void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& p
                                     dY.data_ptr(), (int)perm.size(1), cur_stream());
 }
 
+// out (C,) fp32 += column sums of X (T, C) bf16
+void colsum_acc(const Tensor& X, Tensor out) {
+  SRB_CHECK_CUDA(X); SRB_CHECK_BF16(X); SRB_CHECK_CUDA(out);
+  TORCH_CHECK(X.dim() == 2 && X.stride(1) == 1 && out.scalar_type() == at::kFloat && out.is_contiguous() &&
+              out.numel() >= X.size(1));
+  c10::cuda::CUDAGuard guard(X.device());
+  const bool ok = srb::try_launch_colsum_bf16(X.data_ptr(), out.data_ptr<float>(), (int)X.size(0), (int)X.size(1),
+                                              (int)X.stride(0), cur_stream());
+  TORCH_CHECK(ok, "colsum_acc: unsupported shape (C must be a multiple of 8, <= 2048)");
+}
+
 std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
                                   const c10::optional<Tensor>& beta, const c10::optional<Tensor>& Xres,
                                   const Tensor& mask, int64_t nO, int64_t nP, double drop_p, int64_t seed,
@@ -260,6 +271,7 @@ TORCH_LIBRARY(srb, m) {
   m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns) -> Tensor");
   m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
   m.def("hash_embed_bwd_sorted(Tensor dY, Tensor keys, Tensor perm, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
+  m.def("colsum_acc(Tensor X, Tensor(a!) out) -> ()");
   m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed, Tensor? seed_dev) -> Tensor[]");
   m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta, Tensor? seed_dev) -> Tensor");
   m.def("seq2col(Tensor X) -> Tensor");
@@ -277,6 +289,7 @@ TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("hash_embed_fwd", hash_embed_fwd);
   m.impl("hash_embed_bwd", hash_embed_bwd);
   m.impl("hash_embed_bwd_sorted", hash_embed_bwd_sorted);
+  m.impl("colsum_acc", colsum_acc);
   m.impl("maxout_ln_fwd", maxout_ln_fwd);
   m.impl("maxout_ln_bwd", maxout_ln_bwd);
   m.impl("seq2col", seq2col);

@@ -46,6 +46,10 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
     // with a 2-CTA cluster each CTA loads (and multicasts) half of the B rows of a tile
     r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64,
                            (uint32_t)(block_n / cluster));
+  } else if (mode == MODE_KMN) {
+    TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major B needs block_n % 64 == 0");
+    r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);
+    r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64, 64);
   } else {
     TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major mode needs block_n % 64 == 0");
     r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 64);

@@ -7,7 +7,11 @@
 
 namespace srb {
 
-enum { MODE_KK = 0, MODE_MNMN = 1 };
+// MODE_KK:   A (M,K) and B (N,K) both K-major ("NT")           - forward / plain linear
+// MODE_MNMN: A (K,M) and B (K,N) both MN-major ("TN")          - dW straight from (T,.) arrays
+// MODE_KMN:  A (M,K) K-major, B (K,N) MN-major ("NN")          - dX = dY @ W with W as stored,
+//            no per-step transpose of the weights; b_row_off = K (row) offset, b_col_off = N offset
+enum { MODE_KK = 0, MODE_MNMN = 1, MODE_KMN = 2 };
 enum { EPI_STORE = 0, EPI_MAXOUT3 = 1, EPI_ATOMIC_F32 = 2 };
 
 struct GemmParams {
@@ -15,8 +19,8 @@ struct GemmParams {
   int n_shifts;             // MODE_KK: 1 (plain) or 3 (window)
   int a_row_shift[3];       // added to the A row (M) coordinate
   int a_col_off[3];         // added to the A K coordinate
-  int b_row_off[3];         // added to the B row (N) coordinate
-  int b_col_off[3];         // added to the B K coordinate
+  int b_row_off[3];         // added to the B row coordinate (N for MODE_KK, K for MODE_KMN)
+  int b_col_off[3];         // added to the B column coordinate (K for MODE_KK, N for MODE_KMN)
   int splits;               // split-K factor (EPI_ATOMIC_F32)
   int win_w;                // MODE_MNMN: >0 = B is the window-expanded view of a (T, win_w) array
   const int* m_dev;         // optional device-side row count (<= M) for fixed-shape CUDA graphs

@@ -71,7 +71,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = p.N / BLOCK_N;
   const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
-  const int total_kb = (MODE == MODE_KK ? p.n_shifts : 1) * kpb;
+  const int total_kb = (MODE != MODE_MNMN ? p.n_shifts : 1) * kpb;
   const int splits = p.splits > 0 ? p.splits : 1;
   const int m_groups = (m_tiles + CL - 1) / CL;              // a cluster takes CL vertically adjacent M tiles
   const int total_items = m_groups * n_tiles * splits;
@@ -123,6 +123,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d_mcast(b_dst + cta_rank * (kHalfRows * BK * 2), &tmB, full_bar + stage,
                                 p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s] + (int)cta_rank * kHalfRows, kMask);
             }
+          } else if (MODE == MODE_KMN) {
+            // A as in MODE_KK; B = the weight matrix as stored, (K, N) row-major: one 64-column
+            // (N) atom per TMA box, BK rows of K each
+            const int s = kb / kpb, kk = kb - s * kpb;
+            tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
+            const int krow = p.b_row_off[s] + kk * BK, c0 = p.b_col_off[s] + n0;
+            if (CL == 1) {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, krow);
+            } else {
+              constexpr int kAtoms = BLOCK_N / 64 / CL;
+#pragma unroll
+              for (int jj = 0; jj < kAtoms; ++jj) {
+                const int j = (int)cta_rank * kAtoms + jj;
+                tma_load_2d_mcast(b_dst + j * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, krow, kMask);
+              }
+            }
           } else {
             const int t0 = kb * BK;
             int c0 = n0, tshift = 0;
@@ -149,7 +167,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ================================ MMA issuer =======================================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BLOCK_N, MODE == MODE_MNMN, MODE == MODE_MNMN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BLOCK_N, MODE == MODE_MNMN, MODE != MODE_KK);
       int stage = 0, phase = 0, it = 0;
       for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
@@ -171,6 +189,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (MODE == MODE_KK) {
               adesc = make_smem_desc(a_addr + k * 32, 0, 1024);
               bdesc = make_smem_desc(b_addr + k * 32, 0, 1024);
+            } else if (MODE == MODE_KMN) {
+              adesc = make_smem_desc(a_addr + k * 32, 0, 1024);
+              bdesc = make_smem_desc(b_addr + k * 16 * 128, BK * 128, 1024);
             } else {
               adesc = make_smem_desc(a_addr + k * 16 * 128, BK * 128, 1024);
               bdesc = make_smem_desc(b_addr + k * 16 * 128, BK * 128, 1024);
@@ -362,6 +383,7 @@ bool gemm_supports_cluster(int block_n, int mode, int epi) {
   if (mode == MODE_KK && (epi == EPI_STORE) && (block_n == 256 || block_n == 192 || block_n == 128)) return true;
   if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
   if (mode == MODE_MNMN && epi == EPI_ATOMIC_F32 && (block_n == 256 || block_n == 128)) return true;
+  if (mode == MODE_KMN && epi == EPI_STORE && (block_n == 256 || block_n == 128)) return true;
   return false;
 }
 
@@ -385,6 +407,10 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
   SRB_CASE1(64, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE1(256, MODE_KK, EPI_ATOMIC_F32)
   SRB_CASE1(128, MODE_KK, EPI_ATOMIC_F32)
+  SRB_CASE(256, MODE_KMN, EPI_STORE)
+  SRB_CASE1(192, MODE_KMN, EPI_STORE)
+  SRB_CASE(128, MODE_KMN, EPI_STORE)
+  SRB_CASE1(64, MODE_KMN, EPI_STORE)
 #undef SRB_CASE
 #undef SRB_CASE1
   return cudaErrorInvalidValue;

@@ -50,6 +50,9 @@ bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float*
 void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool perm_is_i32, const float* mask, HashEmbedTables t,
                                   const void* dY, int R, cudaStream_t s);
 
+// out[c] += sum_t X[t, c]  (bf16 in, fp32 accumulate); false = shape not supported.
+bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, cudaStream_t s);
+
 // K4 helpers for the library-GEMM path: materialised window / its transpose-add.
 void launch_seq2col(const void* X, void* Xw, int Tp, int nI, cudaStream_t s);
 // dX = col2seq(dXw) (+ residual dY*mask)

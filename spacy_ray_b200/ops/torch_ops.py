@@ -300,10 +300,11 @@ class TorchOps:
             Y = Y + b.to(torch.float32)
         return Y.to(self.dtype)
 
-    def linear_backward(self, dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor, need_dX: bool = True):
+    def linear_backward(self, dY: torch.Tensor, X: torch.Tensor, W: torch.Tensor, need_dX: bool = True,
+                        need_db: bool = True):
         dYf = dY.to(torch.float32)
         dW = dYf.t() @ X.to(torch.float32)
-        db = dYf.sum(dim=0)
+        db = dYf.sum(dim=0) if need_db else None
         dX = dYf @ W.to(torch.float32) if need_dX else None
         return dX, dW, db
 

@@ -137,6 +137,54 @@ def test_tc_window_dx_with_residual(ops, ref):
     _close(dX, want, 2e-2, 0.1, "window dX")
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 256, 768, 256), (1000, 192, 192, 192),
+                                      (257, 64, 128, 64), (4096, 512, 64, 256)])
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_tc_gemm_nn_weights_as_stored(ops, M, N, K, bn, cluster):
+    """MODE_KMN: A (M,K) K-major x B (K,N) row-major (MN-major UMMA operand) - dX = dY @ W without W^T."""
+    torch.manual_seed(11)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(K, N, device="cuda").bfloat16()
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.tc_gemm(A, B, out, mode=2, epi=0, block_n=bn, M=M, N=N, K=K, cluster=cluster)
+    torch.cuda.synchronize()
+    _close(out, A.float() @ B.float(), 2e-2, 2e-2 * math.sqrt(K), f"tc_gemm NN {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_tc_window_dx_nn_with_residual(ops, ref, cluster):
+    torch.manual_seed(3)
+    w, N = 256, 768
+    dZ, mask = _padded_batch((7, 2, 33, 12, 40, 1), N)
+    dZb = dZ.bfloat16()
+    Tp = dZ.shape[0]
+    W2 = (torch.randn(N, 3 * w, device="cuda") * 0.1).bfloat16()
+    dY = (torch.randn(Tp, w, device="cuda")).bfloat16()
+    dX = torch.empty(Tp, w, device="cuda", dtype=torch.bfloat16)
+    ops.tc_gemm(dZb, W2, dX, mode=2, epi=0, block_n=256, M=Tp, N=w, K=N, a_row_shift=(1, 0, -1),
+                a_col_off=(0, 0, 0), b_row_off=(0, 0, 0), b_col_off=(0, w, 2 * w), add_src=dY,
+                row_scale=mask.reshape(-1), cluster=cluster)
+    torch.cuda.synchronize()
+    dXw = dZb.float() @ W2.float()
+    want = ref.backprop_seq2col(dXw, 1) + dY.float() * mask
+    _close(dX, want, 2e-2, 0.15, "window dX (NN)")
+
+
+@pytest.mark.parametrize("T,C", [(1, 64), (777, 96), (25000, 64), (5000, 768), (333, 2048)])
+def test_colsum_kernel(ops, T, C):
+    torch.manual_seed(5)
+    X = torch.randn(T, C, device="cuda").bfloat16()
+    got = ops.colsum(X)
+    launched = ops.launches
+    _close(got, X.float().sum(0), 1e-3, 1e-3 * math.sqrt(T), "colsum")
+    acc = torch.ones(C, device="cuda")
+    ops.colsum(X[:, : C // 2 // 8 * 8 or 8], out=acc)        # strided view, accumulates into `out`
+    assert ops.launches == launched + 1
+    Ch = C // 2 // 8 * 8 or 8
+    _close(acc[:Ch], 1 + X[:, :Ch].float().sum(0), 1e-3, 1e-3 * math.sqrt(T), "colsum acc")
+    assert float((acc[Ch:] - 1).abs().max()) == 0.0 if Ch < C else True
+
+
 @pytest.mark.parametrize("window", [0, 1])
 @pytest.mark.parametrize("cluster", [1, 2])
 def test_tc_dw_mn_major_split_k(ops, ref, window, cluster):

@@ -84,7 +84,7 @@ void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& p
 
 // out (C,) fp32 += column sums of X (T, C) bf16
 void colsum_acc(const Tensor& X, Tensor out) {
-  SRB_CHECK_CUDA(X); SRB_CHECK_BF16(X); SRB_CHECK_CUDA(out);
+  TORCH_CHECK(X.is_cuda(), "X must be a CUDA tensor"); SRB_CHECK_BF16(X); SRB_CHECK_CUDA(out);   // X rows may be strided
   TORCH_CHECK(X.dim() == 2 && X.stride(1) == 1 && out.scalar_type() == at::kFloat && out.is_contiguous() &&
               out.numel() >= X.size(1));
   c10::cuda::CUDAGuard guard(X.device());

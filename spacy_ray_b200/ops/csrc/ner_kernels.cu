@@ -17,6 +17,7 @@
 // models/transition_model.py::_biluo_steps_reference, which the tests diff against.
 #include "common.cuh"
 #include "kernels.h"
+#include "transition_common.cuh"
 
 namespace srb {
 
@@ -33,15 +34,7 @@ __device__ __forceinline__ bool biluo_valid(int a, int ent_label, bool is_open, 
 template <int PPL>
 __device__ __forceinline__ void load_slot(const __nv_bfloat16* __restrict__ Yf, int row, int slot, int nOP, int lane,
                                           float out[PPL]) {
-  const __nv_bfloat16* p = Yf + ((size_t)row * 3 + slot) * nOP + lane * PPL;
-  if (PPL == 4) {
-    const uint2 raw = *(const uint2*)p;
-    const __nv_bfloat162 lo = *(const __nv_bfloat162*)&raw.x, hi = *(const __nv_bfloat162*)&raw.y;
-    out[0] = __low2float(lo); out[1] = __high2float(lo); out[2] = __low2float(hi); out[3] = __high2float(hi);
-  } else {
-#pragma unroll
-    for (int k = 0; k < PPL; ++k) out[k] = bf2f(p[k]);
-  }
+  load_bf16_vec<PPL>(Yf + ((size_t)row * 3 + slot) * nOP + lane * PPL, out);
 }
 
 // NJ = ceil(nA / 32) actions per lane, PPL = nO*nP/32 pre-activations per lane (nP == 2).
@@ -50,17 +43,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int UPL = PPL / 2;
   const int nO = A.nO, nOP = A.nO * 2, nA = A.nA;
-  float* WuT = (float*)smem_raw;                                  // [nO][nA_pad]
-  float* bu_s = WuT + (size_t)nO * A.nA_pad;                      // [nA_pad]
+  float4* Wu4 = (float4*)smem_raw;                                // [nO/4][nA_pad] x float4
+  float* bu_s = (float*)smem_raw + (size_t)nO * A.nA_pad;         // [nA_pad]
   float* hid_s = bu_s + A.nA_pad;                                 // [warps][nO]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* Wu = (const __nv_bfloat16*)A.Wu;
-  for (int i = threadIdx.x; i < nO * A.nA_pad; i += blockDim.x) {
-    const int o = i / A.nA_pad, a = i - o * A.nA_pad;
-    WuT[i] = a < nA ? bf2f(Wu[(size_t)a * nO + o]) : 0.f;
-  }
-  for (int i = threadIdx.x; i < A.nA_pad; i += blockDim.x)
-    bu_s[i] = i < nA ? bf2f(((const __nv_bfloat16*)A.bu)[i]) : 0.f;
+  stage_upper_weights(Wu4, bu_s, (const __nv_bfloat16*)A.Wu, (const __nv_bfloat16*)A.bu, nO, nA, A.nA_pad);
   __syncthreads();
 
   const int d = blockIdx.x * kWarpsPerBlock + warp;
@@ -116,31 +103,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
 #pragma unroll
     for (int k = 0; k < PPL; ++k) pre[k] = bias_r[k] + nx0[k] + (is_open ? (e1[k] + l2[k]) : pad12[k]);
     const size_t tok = (size_t)tok0 + i;
+    float best_u[UPL];
+    uint8_t which_u[UPL];
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
       float best = pre[2 * u];
       int bi = 0;
       if (pre[2 * u + 1] > best) { best = pre[2 * u + 1]; bi = 1; }
-      const int o = lane * UPL + u;
-      hid_w[o] = best;
-      if (A.train) {
-        A.which[tok * nO + o] = (uint8_t)bi;
-        ((__nv_bfloat16*)A.hid)[tok * nO + o] = f2bf(best);
-      }
+      best_u[u] = best; which_u[u] = (uint8_t)bi;
+      hid_w[lane * UPL + u] = best;
     }
+    if (A.train) store_hidden_record<UPL>(A.which + tok * nO + lane * UPL, (__nv_bfloat16*)A.hid + tok * nO + lane * UPL,
+                                          best_u, which_u);
     __syncwarp();
-    // ---- upper layer: o-outer / action-inner (NJ independent FMA chains per lane) ---------
+    // ---- upper layer: one LDS.128 of weights per four FMAs (transition_common.cuh) --------
     float sc[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) sc[j] = bu_s[lane + 32 * j < A.nA_pad ? lane + 32 * j : 0];
-#pragma unroll 4
-    for (int o = 0; o < nO; ++o) {
-      const float h = hid_w[o];
-      const float* wrow = WuT + o * A.nA_pad + lane;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (j < NJ - 1 || lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
-    }
+    upper_layer<NJ>(Wu4, bu_s, hid_w, nO, A.nA_pad, lane, sc);
     bool ok[NJ];
     float mx = -3.0e38f;
     int arg = 0;

@@ -17,6 +17,7 @@
 // Spec: models/transitions.py::ArcEagerSystem and transition_model.py::_arc_steps_reference.
 #include "common.cuh"
 #include "kernels.h"
+#include "transition_common.cuh"
 
 namespace srb {
 
@@ -39,18 +40,13 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
   constexpr int PPL = NP * UPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nO = A.nO, nOP = A.nO * NP, nA = A.nA;
-  float* WuT = (float*)smem_raw;                                  // [nO][nA_pad]
-  float* bu_s = WuT + (size_t)nO * A.nA_pad;                      // [nA_pad]
+  float4* Wu4 = (float4*)smem_raw;                                // [nO/4][nA_pad] x float4
+  float* bu_s = (float*)smem_raw + (size_t)nO * A.nA_pad;         // [nA_pad]
   float* pad_s = bu_s + A.nA_pad;                                 // [8][nOP]
   float* hid_s = pad_s + 8 * nOP;                                 // [warps][nO]
   ArcWarpState* states = (ArcWarpState*)(hid_s + kArcWarps * nO);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* Wu = (const __nv_bfloat16*)A.Wu;
-  for (int i = threadIdx.x; i < nO * A.nA_pad; i += blockDim.x) {
-    const int o = i / A.nA_pad, a = i - o * A.nA_pad;
-    WuT[i] = a < nA ? bf2f(Wu[(size_t)a * nO + o]) : 0.f;
-  }
-  for (int i = threadIdx.x; i < A.nA_pad; i += blockDim.x) bu_s[i] = i < nA ? bf2f(((const __nv_bfloat16*)A.bu)[i]) : 0.f;
+  stage_upper_weights(Wu4, bu_s, (const __nv_bfloat16*)A.Wu, (const __nv_bfloat16*)A.bu, nO, nA, A.nA_pad);
   for (int i = threadIdx.x; i < 8 * nOP; i += blockDim.x) pad_s[i] = bf2f(((const __nv_bfloat16*)A.pad)[i]);
   __syncthreads();
 
@@ -92,47 +88,45 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
     const int f[8] = {b0, b1, s0, s1, s2, b0 >= 0 ? S.lc[b0] : -1, s0 >= 0 ? S.lc[s0] : -1, s0 >= 0 ? S.rc[s0] : -1};
     const bool s0_headed = s0 >= 0 && S.heads[s0] >= 0;
     // ---- hidden ---------------------------------------------------------------------------
+    // all eight feature rows are requested before the first one is used (missing features
+    // read the doc's first row - valid memory - and are replaced by the pad vector below)
+    float fv[8][PPL];
+#pragma unroll
+    for (int ff = 0; ff < 8; ++ff) {
+      const int fi = f[ff] >= 0 ? f[ff] : 0;
+      load_bf16_vec<PPL>(Yf + ((size_t)(row0 + fi) * 8 + ff) * nOP + lane * PPL, fv[ff]);
+    }
     float pre[PPL];
 #pragma unroll
     for (int k = 0; k < PPL; ++k) pre[k] = bias_r[k];
 #pragma unroll
     for (int ff = 0; ff < 8; ++ff) {
       if (f[ff] >= 0) {
-        const __nv_bfloat16* p = Yf + ((size_t)(row0 + f[ff]) * 8 + ff) * nOP + lane * PPL;
 #pragma unroll
-        for (int k = 0; k < PPL; ++k) pre[k] += bf2f(p[k]);
+        for (int k = 0; k < PPL; ++k) pre[k] += fv[ff][k];
       } else {
 #pragma unroll
         for (int k = 0; k < PPL; ++k) pre[k] += pad_s[ff * nOP + lane * PPL + k];
       }
     }
     const size_t rec = (size_t)rec0 + step;
+    float best_u[UPL];
+    uint8_t which_u[UPL];
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
       float best = pre[u * NP];
       int bi = 0;
 #pragma unroll
       for (int q = 1; q < NP; ++q) if (pre[u * NP + q] > best) { best = pre[u * NP + q]; bi = q; }
-      const int o = lane * UPL + u;
-      hid_w[o] = best;
-      if (A.train) {
-        A.which[rec * nO + o] = (uint8_t)bi;
-        ((__nv_bfloat16*)A.hid)[rec * nO + o] = f2bf(best);
-      }
+      best_u[u] = best; which_u[u] = (uint8_t)bi;
+      hid_w[lane * UPL + u] = best;
     }
+    if (A.train) store_hidden_record<UPL>(A.which + rec * nO + lane * UPL, (__nv_bfloat16*)A.hid + rec * nO + lane * UPL,
+                                          best_u, which_u);
     __syncwarp();
     // ---- upper layer ----------------------------------------------------------------------
     float sc[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) sc[j] = bu_s[lane + 32 * j < A.nA_pad ? lane + 32 * j : 0];
-#pragma unroll 4
-    for (int o = 0; o < nO; ++o) {
-      const float h = hid_w[o];
-      const float* wrow = WuT + o * A.nA_pad + lane;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (j < NJ - 1 || lane + 32 * j < A.nA_pad) sc[j] = fmaf(h, wrow[32 * j], sc[j]);
-    }
+    upper_layer<NJ>(Wu4, bu_s, hid_w, nO, A.nA_pad, lane, sc);
     // ---- validity + arg-max ---------------------------------------------------------------
     bool ok[NJ];
     float mx = -3.0e38f;

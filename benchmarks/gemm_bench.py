@@ -77,19 +77,19 @@ def main() -> int:
         rows.append({"kernel": name, "us": round(us, 2), "tflops": round(tf, 1), "frac_of_cublas_peak": round(tf / peak_tf, 3)})
         print(f"{name:58s} {us:8.1f} us  {tf:7.1f} TFLOP/s  {100 * tf / peak_tf:5.1f}% of cuBLAS sustained peak")
 
-    for cl in (1, 2):
+    for cl in (1, 2, 3):
         report(f"fwd  window+bias+maxout  bn=192 cluster={cl}", timeit(lambda: ops.tc_gemm(
             X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=T, N=N, K=w, a_row_shift=(-1, 0, 1),
             a_col_off=(0, 0, 0), b_row_off=(0, 0, 0), b_col_off=(0, w, 2 * w), bias=bias, which=which, cluster=cl)))
     report("fwd  cuBLAS (T,3w)@(3w,N) on a materialised window", timeit(lambda: torch.matmul(Xw, W2.t())))
     for bn in (256, 128):
-        for cl in (1, 2):
+        for cl in (1, 2, 3):
             report(f"dX   weights-as-stored window+residual bn={bn} cluster={cl}", timeit(lambda: ops.tc_gemm(
                 dZ, W2, dX, mode=MODE_KMN, epi=EPI_STORE, block_n=bn, M=T, N=w, K=N, a_row_shift=(1, 0, -1),
                 a_col_off=(0, 0, 0), b_row_off=(0, 0, 0), b_col_off=(0, w, 2 * w), add_src=dY, row_scale=mask,
                 cluster=cl)))
     report("dX   cuBLAS (T,N)@(N,3w) (window still to be folded)", timeit(lambda: torch.matmul(dZ, W2)))
-    for cl in (1, 2):
+    for cl in (1, 2, 3):
         ops.gemm_cluster = cl
         report(f"dW   MN-major split-K fp32 red cluster={cl}", timeit(lambda: ops._dw_tc(dZ, X, 1, out=dW)))
     report("dW   cuBLAS (N,T)@(T,3w) fp32 out", timeit(lambda: torch.mm(dZ.t(), Xw, out_dtype=torch.float32)))

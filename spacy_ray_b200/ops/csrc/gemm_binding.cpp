@@ -38,14 +38,14 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   TORCH_CHECK(n_shifts >= 1 && n_shifts <= 3 && a_col_off.size() == a_row_shift.size() &&
               b_row_off.size() == a_row_shift.size() && b_col_off.size() == a_row_shift.size());
   c10::cuda::CUDAGuard guard(A.device());
-  if (cluster != 2 || !gemm_supports_cluster((int)block_n, (int)mode, (int)epi)) cluster = 1;
+  if ((cluster != 2 && cluster != 3) || !gemm_supports_cluster((int)block_n, (int)mode, (int)epi)) cluster = 1;
   CUtensorMap ta, tb;
   int r1, r2;
   if (mode == MODE_KK) {
     r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);
     // with a 2-CTA cluster each CTA loads (and multicasts) half of the B rows of a tile
     r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64,
-                           (uint32_t)(block_n / cluster));
+                           (uint32_t)(cluster > 1 ? block_n / 2 : block_n));
   } else if (mode == MODE_KMN) {
     TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major B needs block_n % 64 == 0");
     r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);

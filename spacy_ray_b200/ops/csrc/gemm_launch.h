@@ -35,8 +35,9 @@ struct GemmParams {
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
-// cluster: 1, or 2 = pairs of CTAs on adjacent M tiles sharing the B operand by TMA multicast
-// (the B tensor map must then be encoded with box rows block_n / 2).
+// cluster: 1; 2 = pairs of CTAs on adjacent M tiles sharing the B operand by TMA multicast;
+// 3 = the same pairs issuing one tcgen05.mma.cta_group::2 (M = 256), each CTA holding half of B.
+// (For 2 and 3 the K-major B tensor map must be encoded with box rows block_n / 2.)
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
                         int cluster, int num_sms, cudaStream_t s);
 bool gemm_supports_cluster(int block_n, int mode, int epi);

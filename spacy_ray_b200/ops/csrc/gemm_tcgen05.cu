@@ -30,10 +30,12 @@ constexpr int kNumThreads = 320;          // TMA warp + MMA warp + 8 epilogue wa
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 
-template <int BLOCK_N>
+// PAIR (cta_group::2): a CTA stores only its half of the B tile, so a stage is smaller and the
+// ring is deeper - more bytes in flight per SM for the same shared memory.
+template <int BLOCK_N, bool PAIR = false>
 struct Cfg {
   static constexpr int kStageA = BM * BK * 2;            // 16 KB
-  static constexpr int kStageB = BLOCK_N * BK * 2;
+  static constexpr int kStageB = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStagesRaw = kSmemBudget / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -51,10 +53,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // each CTA TMA-loads half of the B tile and multicasts it into both CTAs' shared memory, so B
 // crosses L2 -> SM once per cluster instead of once per CTA (the single-CTA kernels measured
 // ~55-60 % tensor-pipe activity with L2 -> smem traffic as the limiter).
-template <int BLOCK_N, int MODE, int EPI, int CL>
+//
+// PAIR = the two CTAs additionally issue ONE tcgen05.mma.cta_group::2 per k-step (M = 256: each
+// CTA contributes its 128 A rows and HALF of the B tile from its own shared memory; each CTA's
+// TMEM receives its own 128 accumulator rows).  Per SM and per FLOP that halves the B bytes
+// stored AND fetched, which is what the L2 -> smem-bound single-CTA kernels were missing.  Both
+// CTAs run a TMA producer (completion bytes are signalled on the leader's barriers), only the
+// leader (cluster rank 0) runs the MMA issuer, both run their own epilogue.
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  using C = Cfg<BLOCK_N>;
+  static_assert(!PAIR || CL == 2, "the pair MMA needs a 2-CTA cluster");
+  using C = Cfg<BLOCK_N, PAIR>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
@@ -85,11 +95,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 8); }
+    // PAIR: one MMA issuer (the leader) frees a stage in both CTAs; its tmem_empty barrier
+    // collects the epilogue warps of BOTH CTAs
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, PAIR ? 1 : CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, PAIR ? 16 : 8); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr); else tmem_alloc<C::kTmemCols>(tmem_ptr); }
   if (p.bias && warp >= 2) {                     // bias -> smem (fp32) once per CTA
     for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
   }
@@ -110,9 +122,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb0 = (int)((long long)total_kb * split / splits), kb1 = (int)((long long)total_kb * (split + 1) / splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + stage, C::kStage);
           unsigned char* a_dst = sA + stage * C::kStageA;
           unsigned char* b_dst = sB + stage * C::kStageB;
+          if (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's full barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * C::kStage);
+            const uint32_t fb = map_to_cta(full_bar + stage, 0);
+            int s = 0, kk = kb;
+            if (MODE != MODE_MNMN) { s = kb / kpb; kk = kb - s * kpb; }
+            if (MODE == MODE_KK) {
+              constexpr int kHalfRows = BLOCK_N / 2;
+              tma_load_2d_2sm(a_dst, &tmA, fb, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
+              tma_load_2d_2sm(b_dst, &tmB, fb, p.b_col_off[s] + kk * BK, n0 + p.b_row_off[s] + (int)cta_rank * kHalfRows);
+            } else {
+              constexpr int kAtoms = BLOCK_N / 64 / 2;            // my 64-column atoms of the B tile
+              int c0, krow;
+              if (MODE == MODE_KMN) {
+                tma_load_2d_2sm(a_dst, &tmA, fb, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
+                krow = p.b_row_off[s] + kk * BK; c0 = p.b_col_off[s] + n0;
+              } else {
+                const int t0 = kb * BK;
+                int tshift = 0;
+                c0 = n0;
+                if (p.win_w > 0) { const int sw = n0 / p.win_w; c0 = n0 - sw * p.win_w; tshift = sw - 1; }
+                krow = t0 + tshift;
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * (BK * 128), &tmA, fb, m0 + j * 64, t0);
+              }
+#pragma unroll
+              for (int jj = 0; jj < kAtoms; ++jj)
+                tma_load_2d_2sm(b_dst + jj * (BK * 128), &tmB, fb, c0 + ((int)cta_rank * kAtoms + jj) * 64, krow);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar + stage, C::kStage);
           if (MODE == MODE_KK) {
             const int s = kb / kpb, kk = kb - s * kpb;
             tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[s] + kk * BK, m0 + p.a_row_shift[s]);
@@ -166,8 +210,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =======================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BLOCK_N, MODE == MODE_MNMN, MODE != MODE_KK);
+    if ((!PAIR || cta_rank == 0) && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BLOCK_N, MODE == MODE_MNMN, MODE != MODE_KK);
       int stage = 0, phase = 0, it = 0;
       for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
@@ -196,13 +240,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               adesc = make_smem_desc(a_addr + k * 16 * 128, BK * 128, 1024);
               bdesc = make_smem_desc(b_addr + k * 16 * 128, BK * 128, 1024);
             }
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(empty_bar + stage);
+          if (PAIR) umma_commit_pair(empty_bar + stage, kMask);
+          else if (CL == 1) umma_commit(empty_bar + stage);
           else umma_commit_mcast(empty_bar + stage, kMask);     // frees the stage in every CTA of the cluster
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tmem_full + acc);
+        if (PAIR) umma_commit_pair(tmem_full + acc, kMask);    // both CTAs' epilogues own rows of this tile
+        else umma_commit(tmem_full + acc);
         ++it;
       }
     }
@@ -306,13 +353,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        if (PAIR && cta_rank != 0) mbar_arrive_cluster(map_to_cta(tmem_empty + acc, 0));   // the leader issues the MMAs
+        else mbar_arrive(tmem_empty + acc);
+      }
       ++it;
     }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while a peer may still write to it
-  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair<C::kTmemCols>(tmem_base); else tmem_dealloc<C::kTmemCols>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -348,12 +398,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N, int MODE, int EPI, int CL>
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR = false>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int num_sms, cudaStream_t s) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -374,7 +424,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL>, a, b, p);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR>, a, b, p);
 }
 
 int gemm_block_k() { return BK; }
@@ -391,6 +441,7 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
                         int cluster, int num_sms, cudaStream_t s) {
 #define SRB_CASE(BN, MD, EP)                                                              \
   if (block_n == BN && mode == MD && epi == EP) {                                         \
+    if (cluster == 3) return launch_one<BN, MD, EP, 2, true>(a, b, p, num_sms, s);        \
     if (cluster == 2) return launch_one<BN, MD, EP, 2>(a, b, p, num_sms, s);              \
     return launch_one<BN, MD, EP, 1>(a, b, p, num_sms, s);                                \
   }

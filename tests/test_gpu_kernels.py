@@ -80,7 +80,7 @@ def test_hash_embed_fwd_bwd(ops, ref):
 # ---------------------------------------------------------------------------- tcgen05 GEMMs
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 256, 256, 256), (1000, 768, 192, 192),
                                       (257, 64, 128, 64), (4096, 384, 64, 128)])
-@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("cluster", [1, 2, 3])
 def test_tc_gemm_plain_nt(ops, M, N, K, bn, cluster):
     torch.manual_seed(1)
     A = torch.randn(M, K, device="cuda").bfloat16()
@@ -139,7 +139,7 @@ def test_tc_window_dx_with_residual(ops, ref):
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 256, 768, 256), (1000, 192, 192, 192),
                                       (257, 64, 128, 64), (4096, 512, 64, 256)])
-@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("cluster", [1, 2, 3])
 def test_tc_gemm_nn_weights_as_stored(ops, M, N, K, bn, cluster):
     """MODE_KMN: A (M,K) K-major x B (K,N) row-major (MN-major UMMA operand) - dX = dY @ W without W^T."""
     torch.manual_seed(11)
@@ -151,7 +151,7 @@ def test_tc_gemm_nn_weights_as_stored(ops, M, N, K, bn, cluster):
     _close(out, A.float() @ B.float(), 2e-2, 2e-2 * math.sqrt(K), f"tc_gemm NN {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("cluster", [1, 2, 3])
 def test_tc_window_dx_nn_with_residual(ops, ref, cluster):
     torch.manual_seed(3)
     w, N = 256, 768
@@ -186,7 +186,7 @@ def test_colsum_kernel(ops, T, C):
 
 
 @pytest.mark.parametrize("window", [0, 1])
-@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("cluster", [1, 2, 3])
 def test_tc_dw_mn_major_split_k(ops, ref, window, cluster):
     ops = type(ops)("cuda:0")
     ops.gemm_cluster = cluster

@@ -64,8 +64,9 @@ class B200Ops(TorchOps):
         env_dw = os.environ.get("SRB_TC_DW")
         self.tc_dw = (env_dw != "0") if tc_dw is None else tc_dw
         self.sorted_embed_bwd = os.environ.get("SRB_SORTED_EMBED", "1") != "0"
-        # 2 = thread-block clusters of 2 CTAs sharing the weight operand by TMA multicast
-        self.gemm_cluster = int(os.environ.get("SRB_GEMM_CLUSTER", "2"))
+        # 3 = 2-CTA clusters issuing tcgen05.mma.cta_group::2 (M = 256, each CTA holds half of B);
+        # 2 = 2-CTA clusters with single-CTA MMAs sharing B by TMA multicast; 1 = no clusters
+        self.gemm_cluster = int(os.environ.get("SRB_GEMM_CLUSTER", "3"))
         self.launches = 0            # our kernels launched (bench.py reports this)
         # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
         # replays draw fresh masks although the per-call seeds were baked in at capture time

@@ -72,6 +72,13 @@ class B200Ops(TorchOps):
         # replays draw fresh masks although the per-call seeds were baked in at capture time
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._wt_cache: Dict[int, Tuple[int, torch.Tensor]] = {}
+        # weight-gradient GEMMs that accumulate straight into the flat gradient bucket run on a side
+        # stream: nothing in the backward pass reads them, and their CTAs fill the SMs the dX GEMM
+        # leaves idle in its last, partial wave (201 M-tiles on 148 SMs = 1.36 waves).  The
+        # consumer of the bucket (ShardedSyncProxy.step) joins the stream.
+        self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
+        self._side: Optional[torch.cuda.Stream] = None
+        self._side_pending = False
 
     # ------------------------------------------------------------------ GEMM helpers
     def _tc_ok(self, *dims: int) -> bool:
@@ -188,6 +195,24 @@ class B200Ops(TorchOps):
                "has_ln": G is not None, "xhat": xhat, "rstd": rstd, "G": G, "drop": drop, "seed": seed}
         return Y, ctx
 
+    def _fork_side(self, *tensors: torch.Tensor) -> "torch.cuda.Stream":
+        """Side stream ordered after everything issued so far on the current stream."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        for t in tensors:
+            t.record_stream(self._side)          # the allocator must not recycle them under the side kernels
+        self._side_pending = True
+        return self._side
+
+    def join_side(self) -> None:
+        """Make the current stream wait for the side-stream gradient GEMMs (no-op if none ran)."""
+        if self._side_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_pending = False
+
     def colsum(self, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 column sums of a (T, C) bf16 matrix (bias gradients), one kernel."""
         C = X.shape[1]
@@ -243,7 +268,13 @@ class B200Ops(TorchOps):
         dW_dst = go.get("W")
         if dW_dst is not None and not (dW_dst.dtype == torch.float32 and dW_dst.is_contiguous()):
             dW_dst = None
-        dW = self._dw_tc(dZ, X, window, out=dW_dst.view(nO * nP, nI) if dW_dst is not None else None)
+        if dW_dst is not None and self.side_dw and self.use_tc and self.tc_dw:
+            with torch.cuda.stream(self._fork_side(dZ, X)):
+                dW = self._dw_tc(dZ, X, window, out=dW_dst.view(nO * nP, nI))
+            if dW is None:
+                self.join_side()
+        else:
+            dW = self._dw_tc(dZ, X, window, out=dW_dst.view(nO * nP, nI) if dW_dst is not None else None)
         if dW is None:
             Xw = self.k.seq2col(X) if window else X
             dW = _mm_f32(dZ.t(), Xw)

@@ -100,7 +100,10 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster_addr) : "memory");
+  // default semantics (release at CTA scope): the arrive only has to order this warp's TMEM reads,
+  // which tcgen05.wait::ld + fence::before_thread_sync already did - a cluster-scope release
+  // compiled to MEMBAR.ALL.GPU and made every epilogue warp wait for its global stores
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");

@@ -27,6 +27,7 @@ from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tupl
 
 import torch
 
+from ..ops import get_current_ops
 from .util import KeyT, divide_params, divide_params_balanced, make_key
 
 ALIGN = 128  # elements; keeps every key 256 B (bf16) / 512 B (fp32) aligned for TMA + vector loads
@@ -268,6 +269,9 @@ class ShardedSyncProxy:
     # ---- the step --------------------------------------------------------------
     def step(self) -> None:
         """Gradient exchange + sharded optimizer + weight publication."""
+        join = getattr(get_current_ops(), "join_side", None)
+        if join is not None:
+            join()            # gradient GEMMs the backend ran on a side stream write into grad_flat
         fused = getattr(self.comm, "fused_step", None)
         if fused is not None:
             fused(self)

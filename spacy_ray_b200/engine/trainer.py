@@ -273,6 +273,9 @@ class Trainer:
         self._q_out: "queue.Queue" = queue.Queue()
         self._thread: Optional[threading.Thread] = None
         self._side = torch.cuda.Stream(device=self.device)
+        # the captured step runs at high stream priority: the backend's side-stream work (weight-
+        # gradient GEMMs, default priority) then only takes SMs the dependent chain leaves idle
+        self._hp = torch.cuda.Stream(device=self.device, priority=-1)
         if prefetch:
             self._thread = threading.Thread(target=self._prefetch_loop, daemon=True)
             self._thread.start()
@@ -387,7 +390,7 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         l0, c0 = self.ops.launches, getattr(comm, "launches", 0)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self._pool):
+        with torch.cuda.graph(g, pool=self._pool, stream=self._hp):
             loss = self._step_fn(rb)
         self._launches_per_replay[rb] = (self.ops.launches - l0, getattr(comm, "launches", 0) - c0)
         self.ops.launches = l0

@@ -260,6 +260,10 @@ class Trainer:
             # only does a device-to-device copy into the static graph input
             stage["land"] = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
             stage["consumed"] = None
+        self._loss_slots = [{"buf": torch.zeros(max(8, len(self.loss_names)), dtype=torch.float32, pin_memory=True),
+                             "ev": torch.cuda.Event(),
+                             "n": 0} for _ in range(2)]
+        self._pending_loss: Optional[dict] = None
         self._graphs: Dict[int, Any] = {}
         self._pool = torch.cuda.graph_pool_handle() if use_graphs else None
         self._warmed = False
@@ -431,11 +435,37 @@ class Trainer:
         self.last = {"docs": stage["docs"], "words": stage["words"], "rows": stage["rows"]}
         return loss
 
-    def train_step(self, ids: Optional[np.ndarray] = None) -> float:
-        """The public one-call step: (collate if ``ids`` given) -> H2D -> step -> loss (D2H)."""
+    def train_step(self, ids: Optional[np.ndarray] = None, *, lag: int = 1) -> float:
+        """The public one-call step: (collate if ``ids`` given) -> H2D -> step -> loss (D2H).
+
+        Every step's per-head losses are copied to pinned host memory right behind the step
+        (async D2H on the step's stream).  With ``lag=1`` (default) the call returns the loss of
+        the PREVIOUS step - whose copy has long finished - so the host never stalls the device
+        between steps (the first call returns its own loss); ``lag=0`` blocks on this step.
+        ``flush_loss()`` returns the one still in flight."""
         if ids is not None:
             self.prepare(ids)
-        return float(self.step_async().sum().item())
+        loss = self.step_async()
+        slot = self._loss_slots[self.steps % len(self._loss_slots)]
+        slot["buf"][: loss.numel()].copy_(loss, non_blocking=True)
+        slot["n"] = int(loss.numel())
+        slot["ev"].record()
+        if lag <= 0:
+            prev, self._pending_loss = slot, None
+        else:
+            prev, self._pending_loss = self._pending_loss, slot
+            if prev is None:                           # first call: nothing older to report
+                prev = slot
+        prev["ev"].synchronize()
+        return float(prev["buf"][: prev["n"]].sum())
+
+    def flush_loss(self) -> Optional[float]:
+        """Loss of the most recent step (blocks until it has been computed)."""
+        slot = self._pending_loss
+        if slot is None:
+            return None
+        slot["ev"].synchronize()
+        return float(slot["buf"][: slot["n"]].sum())
 
     def losses_dict(self, loss_vec: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {n: loss_vec[i] for i, n in enumerate(self.loss_names)}

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
     }
     if (A.history && lane == 0) A.history[rec] = arg;
     // ---- apply the predicted action -------------------------------------------------------------
+    __syncwarp();      // every lane has finished reading the state (oracle ballots) before lane 0 mutates it
     if (lane == 0) {
       if (arg == 0) { S.stack[sp] = b; S.in_stack[b] = 1; }
       else if (arg == 1) { S.in_stack[s0] = 0; }

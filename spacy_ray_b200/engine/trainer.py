@@ -250,6 +250,8 @@ class Trainer:
                            slots=tuple(self.store.slots), bucket=self.bucket_rows,
                            n_attr=int(self.store.attrs.shape[1]))
         self.host_grouping = os.environ.get("SRB_HOST_GROUP", "1") != "0"
+        self.head_streams = os.environ.get("SRB_HEAD_STREAMS", "1") != "0"
+        self._head_streams: List[torch.cuda.Stream] = []
         self.use_graphs = use_graphs
         self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
         self.dv = _Views(self.lay, self.dev_buf)
@@ -343,24 +345,47 @@ class Trainer:
         tb = self._batch_views(rows)
         gold = self.dv.gold
         self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
+        shared = [c for _n, c, k in self.heads if k == "tok2vec"]
+        n_heads = sum(1 for _n, _c, k in self.heads if k != "tok2vec")
+        # heads that listen to ONE shared tok2vec are independent of each other: run each on its own
+        # stream (the transition kernels occupy ~7 % of the SMs), then sum their gradients and run
+        # the tok2vec backward once on the main stream
+        concurrent = self.head_streams and len(shared) == 1 and n_heads >= 2
+        main = torch.cuda.current_stream(self.device)
+        forked = []
         losses = []
         for name, comp, kind in self.heads:
             if kind == "tok2vec":
                 # forward now; its backward fires when the last listener returns its gradient
-                comp.update((), batch=tb, drop=self.dropout, sgd=False, losses=None)
+                comp.update((), batch=tb, drop=self.dropout, sgd=False, losses=None, defer_backprop=concurrent)
                 continue
-            set_dropout_rate(comp.model, self.dropout)
-            if kind == "tagger":
-                loss, _ = comp.model.attrs["update_with_labels"](tb, gold[name][:rows].to(torch.int64))
-            elif kind == "ner":
-                g = TransitionGold(actions=gold[name][:rows], offsets=None)
-                loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
-            else:
-                g = TransitionGold(heads_flat=gold[name + ".heads"][:rows], labels_flat=gold[name + ".labels"][:rows])
-                loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
-            losses.append(loss.reshape(()).to(torch.float32))
+            stream = main
+            if concurrent:
+                stream = self._head_stream(len(forked))
+                stream.wait_stream(main)
+                forked.append(stream)
+            with torch.cuda.stream(stream):
+                set_dropout_rate(comp.model, self.dropout)
+                if kind == "tagger":
+                    loss, _ = comp.model.attrs["update_with_labels"](tb, gold[name][:rows].to(torch.int64))
+                elif kind == "ner":
+                    g = TransitionGold(actions=gold[name][:rows], offsets=None)
+                    loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
+                else:
+                    g = TransitionGold(heads_flat=gold[name + ".heads"][:rows], labels_flat=gold[name + ".labels"][:rows])
+                    loss = comp.model.attrs["run"](tb, comp.system, g, True).loss
+                losses.append(loss.reshape(()).to(torch.float32))
+        if concurrent:
+            for stream in forked:
+                main.wait_stream(stream)
+            shared[0].finish_backprop()
         self.proxy.step()
         return losses[0].reshape(1) if len(losses) == 1 else torch.stack(losses)
+
+    def _head_stream(self, i: int) -> "torch.cuda.Stream":
+        while len(self._head_streams) <= i:
+            self._head_streams.append(torch.cuda.Stream(device=self.device, priority=-1))
+        return self._head_streams[i]
 
     def _bucket(self, rows: int) -> int:
         return min(self.lay.rows, _align(rows, self.bucket_rows))

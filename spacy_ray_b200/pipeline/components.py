@@ -134,15 +134,22 @@ class Tok2VecComponent(TrainablePipe):
     def set_annotations(self, docs, preds) -> None:
         pass
 
-    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None, defer_backprop: bool = False):
         """Run the forward pass now; the backward pass runs when the *last*
-        listener has handed its gradient back (spaCy's listener protocol)."""
+        listener has handed its gradient back (spaCy's listener protocol).
+
+        ``defer_backprop=True`` (engine.Trainer, heads on concurrent streams): listeners only
+        deposit their gradients; the caller sums them and runs the backward pass with
+        ``finish_backprop()`` once every head's stream has been joined."""
         set_dropout_rate(self.model, drop)
         outputs, bp = self.model.begin_update(batch)
         n_listeners = len(self.listeners)
-        state = {"d": None, "count": 0}
+        state = {"d": None, "count": 0, "parts": []}
 
         def accumulate(dY):
+            if defer_backprop:
+                state["parts"].append(dY)
+                return
             state["d"] = dY.clone() if state["d"] is None else state["d"].add_(dY)
             state["count"] += 1
             if state["count"] == n_listeners:
@@ -150,11 +157,28 @@ class Tok2VecComponent(TrainablePipe):
                 if sgd not in (None, False):
                     self.finish_update(sgd)
 
+        def finish():
+            parts = state["parts"]
+            if parts:
+                d = parts[0].clone()
+                for extra in parts[1:]:
+                    d.add_(extra)
+                bp(d)
+            state["parts"] = []
+
+        self._finish_backprop = finish
         for l in self.listeners:
             l.attrs["receive"](batch, outputs, accumulate)
         if losses is not None:
             losses.setdefault(self.name, 0.0)
         return losses
+
+    def finish_backprop(self) -> None:
+        """Sum the deposited listener gradients and run the deferred backward pass."""
+        fn = getattr(self, "_finish_backprop", None)
+        if fn is not None:
+            fn()
+            self._finish_backprop = None
 
 
 # ============================================================================

@@ -330,9 +330,12 @@ constexpr int kSortChunk = 32;     // sorted positions per warp (one per lane in
 
 // keys: the raw (R, n_attr) attribute array; perm: (n_tables, R) rows grouped by id per table
 // (device radix sort on truncated keys, or the host-side grouping shipped with the batch).
-// Equal ids are adjacent; runs are split on the FULL 64-bit id.  A warp owns kSortChunk sorted
-// positions: the dependent perm -> mask/key loads happen once, lane-parallel, in the prologue;
-// the walk itself only waits on the dY row loads, which are issued four positions at a time.
+// Equal ids are adjacent; runs are split on the FULL 64-bit id.  A warp owns kSortChunk grouped
+// positions: the dependent perm -> mask/key loads happen once, lane-parallel, in the prologue.
+// One table row is only width/8 16-byte vectors, so the warp is split into G = 32/(width/8)
+// lane groups, each walking its own contiguous slice of the chunk (its own runs, its own
+// flushes) - with width 64 that is four positions in flight per step instead of one with 24
+// idle lanes.  dY row loads are issued four positions deep per group.
 template <typename PermT>
 __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_t* __restrict__ keys,
                                                                     const PermT* __restrict__ perm,
@@ -346,6 +349,11 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
   const int n = min(R, p0 + kSortChunk) - p0;
   const int C = t.n_tables * t.width;
   const int nvec = t.width / 8;                      // 16-byte vectors per table row (<= 64)
+  // lanes per position: nvec if it is a power of two below 32, else the whole warp (2 vectors/lane max)
+  const int gsize = (nvec < 32 && (nvec & (nvec - 1)) == 0) ? nvec : 32;
+  const int S = gsize;                               // positions per group = 32 / (32 / gsize)
+  const int g0 = (lane / gsize) * S;                 // first chunk position of my group
+  const int vl = lane % gsize;                       // my vector within the row
   const PermT* pm = perm + (size_t)a * R;
   const int col = t.column[a];
   int my_row = 0;
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
     hash_rows((uint64_t)cur, t.seed[a], t.n_rows[a], rows);
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-      const int vec = lane + 32 * v;
+      const int vec = vl + 32 * v;
       if (vec < nvec) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -384,32 +392,34 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
     }
   };
   constexpr int kBatch = 4;
-  for (int i0 = 0; i0 < n; i0 += kBatch) {
+  for (int j0 = 0; j0 < S; j0 += kBatch) {           // same trip count in every group: the shuffles are warp-wide
     int rowb[kBatch];
     float mb[kBatch];
     int64_t keyb[kBatch];
     bf16x8 g[kBatch][2];
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
-      const int src = min(i0 + j, kSortChunk - 1);
+      const int pos = g0 + j0 + j;                   // < 32 because S divides 32 and kBatch divides S or S < kBatch
+      const int src = min(pos, kSortChunk - 1);
       rowb[j] = __shfl_sync(0xffffffffu, my_row, src);
-      mb[j] = (i0 + j < n) ? __shfl_sync(0xffffffffu, my_mask, src) : 0.f;
+      const float m = __shfl_sync(0xffffffffu, my_mask, src);
       keyb[j] = __shfl_sync(0xffffffffu, my_key, src);
+      mb[j] = (j0 + j < S && pos < n) ? m : 0.f;
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const int vec = lane + 32 * v;
+        const int vec = vl + 32 * v;
         if (vec < nvec && mb[j] != 0.f)
           g[j][v] = *(const bf16x8*)(dY + (size_t)rowb[j] * C + a * t.width + vec * 8);
       }
     }
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) {
-      if (mb[j] == 0.f) continue;                   // warp-uniform
+      if (mb[j] == 0.f) continue;                   // uniform within the lane group
       if (have && keyb[j] != cur) flush();
       cur = keyb[j]; have = true;
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const int vec = lane + 32 * v;
+        const int vec = vl + 32 * v;
         if (vec < nvec) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[v][i] += bf2f(g[j][v].v[i]);

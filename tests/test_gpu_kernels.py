@@ -44,9 +44,10 @@ def _close(a, b, rtol, atol, name=""):
 
 
 # ---------------------------------------------------------------------------- K1
-def test_hash_embed_fwd_bwd(ops, ref):
+@pytest.mark.parametrize("w", [64, 96, 256, 16])
+def test_hash_embed_fwd_bwd(ops, ref, w):
     torch.manual_seed(0)
-    Tp, w = 301, 64
+    Tp = 301
     attrs = torch.randint(-(1 << 62), 1 << 62, (Tp, 4), dtype=torch.int64, device="cuda")
     attrs[:, 0] = attrs[torch.randint(0, 20, (Tp,), device="cuda"), 0]      # heavy collisions
     mask = (torch.rand(Tp, 1, device="cuda") > 0.1).float()

@@ -76,9 +76,6 @@ class B200Ops(TorchOps):
         # stream: nothing in the backward pass reads them, and their CTAs fill the SMs the dX GEMM
         # leaves idle in its last, partial wave (201 M-tiles on 148 SMs = 1.36 waves).  The
         # consumer of the bucket (ShardedSyncProxy.step) joins the stream.
-        # LayerNorm fused into the forward GEMM kernel (extra LN warps per CTA, EPI_MAXOUT3_LN)
-        self.fused_ln = os.environ.get("SRB_FUSED_LN", "1") != "0"
-        self._ln_cnt: Dict[int, torch.Tensor] = {}
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
@@ -183,24 +180,11 @@ class B200Ops(TorchOps):
                               b_col_off=(0, w_in, 2 * w_in))
             else:
                 shifts = {}
-            if self.fused_ln and G is not None and nO == 256 and (not residual or w_in == nO):
-                # ONE kernel: GEMM + bias + maxout -> H, and LayerNorm/dropout/residual of finished
-                # row blocks by four extra warps per CTA while the remaining tiles are still computed
-                Y = torch.empty((Tp, nO), dtype=torch.bfloat16, device=X.device)
-                xhat = torch.empty((Tp, nO), dtype=torch.bfloat16, device=X.device)
-                rstd = torch.empty((Tp,), dtype=torch.float32, device=X.device)
-                sh = shifts or dict(a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,), b_col_off=(0,))
-                self.k.tc_gemm_maxout_ln(X, W2, H, which, b.reshape(-1), G, beta, X if residual else None, m1, Y, xhat,
-                                         rstd, self._ln_counters(Tp), Tp, nO * nP, w_in, list(sh["a_row_shift"]),
-                                         list(sh["a_col_off"]), list(sh["b_row_off"]), list(sh["b_col_off"]), drop,
-                                         seed, self.seed_dev, self.gemm_cluster)
-                self.launches += 1
-            else:
-                self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
-                             bias=b.reshape(-1), which=which, **shifts)
-                Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop,
-                                                           seed, self.seed_dev)
-                self.launches += 1
+            self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
+                         bias=b.reshape(-1), which=which, **shifts)
+            Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed,
+                                                       self.seed_dev)
+            self.launches += 1
         else:
             Xw = self.k.seq2col(X) if window else X
             Z = Xw @ W2.t()
@@ -210,17 +194,6 @@ class B200Ops(TorchOps):
         ctx = {"X": X, "W": W, "which": which, "window": window, "residual": residual, "mask": m1, "nP": nP,
                "has_ln": G is not None, "xhat": xhat, "rstd": rstd, "G": G, "drop": drop, "seed": seed}
         return Y, ctx
-
-    def _ln_counters(self, rows: int) -> torch.Tensor:
-        """Row-block completion counters of the fused GEMM+LN kernel (self-resetting; one buffer per
-        stream so concurrent launches never share counters)."""
-        key = int(torch.cuda.current_stream(self.device).cuda_stream)
-        need = (rows + 127) // 128 + 2
-        buf = self._ln_cnt.get(key)
-        if buf is None or buf.shape[1] < need:
-            buf = torch.zeros((2, max(need, 512)), dtype=torch.int32, device=self.device)
-            self._ln_cnt[key] = buf
-        return buf
 
     def _fork_side(self, *tensors: torch.Tensor) -> "torch.cuda.Stream":
         """Side stream ordered after everything issued so far on the current stream."""

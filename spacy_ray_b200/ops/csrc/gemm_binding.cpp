@@ -21,12 +21,12 @@ int num_sms_for(int device) {
   return cache[device];
 }
 
-void tc_gemm_impl(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t epi, int64_t block_n, int64_t M,
-                  int64_t N, int64_t K, std::vector<int64_t> a_row_shift, std::vector<int64_t> a_col_off,
-                  std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off, int64_t splits, int64_t win_w,
-                  const c10::optional<Tensor>& bias, const c10::optional<Tensor>& which,
-                  const c10::optional<Tensor>& add_src, const c10::optional<Tensor>& row_scale,
-                  const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster, const LnFuse* ln) {
+void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t epi, int64_t block_n, int64_t M,
+             int64_t N, int64_t K, std::vector<int64_t> a_row_shift, std::vector<int64_t> a_col_off,
+             std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off, int64_t splits, int64_t win_w,
+             const c10::optional<Tensor>& bias, const c10::optional<Tensor>& which,
+             const c10::optional<Tensor>& add_src, const c10::optional<Tensor>& row_scale,
+             const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && out.is_cuda());
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "tc_gemm: bf16 operands");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "tc_gemm: row-major 2D operands");
@@ -74,13 +74,8 @@ void tc_gemm_impl(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, in
   }
   p.bias = bias.has_value() && bias->defined() ? (const __nv_bfloat16*)bias->data_ptr() : nullptr;
   p.which = which.has_value() && which->defined() ? which->data_ptr<uint8_t>() : nullptr;
-  if (epi == EPI_MAXOUT3 || epi == EPI_MAXOUT3_LN) {
+  if (epi == EPI_MAXOUT3) {
     TORCH_CHECK(p.which != nullptr, "tc_gemm: maxout epilogue needs `which`");
-  }
-  if (epi == EPI_MAXOUT3_LN) {
-    TORCH_CHECK(ln != nullptr && (128 % (N / block_n)) == 0 && (128 / (N / block_n)) % 4 == 0 && N / 3 == 256,
-                "tc_gemm: fused LayerNorm needs width 256 and an N tile count dividing 32");
-    p.ln = *ln;
   }
   p.add_src = add_src.has_value() && add_src->defined() ? (const __nv_bfloat16*)add_src->data_ptr() : nullptr;
   p.ld_add = p.add_src ? (int)add_src->stride(0) : 0;
@@ -93,68 +88,14 @@ void tc_gemm_impl(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, in
               " mode=", mode, " epi=", epi, ")");
 }
 
-void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t epi, int64_t block_n, int64_t M,
-             int64_t N, int64_t K, std::vector<int64_t> a_row_shift, std::vector<int64_t> a_col_off,
-             std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off, int64_t splits, int64_t win_w,
-             const c10::optional<Tensor>& bias, const c10::optional<Tensor>& which,
-             const c10::optional<Tensor>& add_src, const c10::optional<Tensor>& row_scale,
-             const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster) {
-  TORCH_CHECK(epi != EPI_MAXOUT3_LN, "tc_gemm: use tc_gemm_maxout_ln for the fused LayerNorm epilogue");
-  tc_gemm_impl(A, B, out, mode, epi, block_n, M, N, K, a_row_shift, a_col_off, b_row_off, b_col_off, splits, win_w,
-               bias, which, add_src, row_scale, m_dev, max_ctas, cluster, nullptr);
-}
-
-// (window) GEMM + bias + maxout(3) -> H, `which`; then, inside the same kernel, LayerNorm / dropout /
-// residual / mask of finished rows -> Y, xhat, rstd.  `counters`: int32 (2, >= ceil(M/128)+1), zeroed once.
-void tc_gemm_maxout_ln(const Tensor& A, const Tensor& B, Tensor H, Tensor which, const c10::optional<Tensor>& bias,
-                       const c10::optional<Tensor>& G, const c10::optional<Tensor>& beta,
-                       const c10::optional<Tensor>& Xres, const Tensor& mask, Tensor Y, Tensor xhat, Tensor rstd,
-                       Tensor counters, int64_t M, int64_t N, int64_t K, std::vector<int64_t> a_row_shift,
-                       std::vector<int64_t> a_col_off, std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off,
-                       double drop_p, int64_t seed, const c10::optional<Tensor>& seed_dev, int64_t cluster) {
-  const int64_t nO = N / 3;
-  TORCH_CHECK(Y.is_cuda() && Y.is_contiguous() && Y.scalar_type() == at::kBFloat16 && Y.size(1) == nO);
-  TORCH_CHECK(xhat.is_contiguous() && xhat.scalar_type() == at::kBFloat16 && rstd.scalar_type() == at::kFloat);
-  TORCH_CHECK(H.is_contiguous() && H.size(1) == nO && mask.scalar_type() == at::kFloat && mask.is_contiguous());
-  TORCH_CHECK(counters.scalar_type() == at::kInt && counters.dim() == 2 && counters.size(0) == 2 &&
-              counters.size(1) >= (M + 127) / 128 + 1 && counters.is_contiguous());
-  LnFuse ln{};
-  const bool has_ln = G.has_value() && G->defined();
-  ln.g = has_ln ? (const __nv_bfloat16*)G->data_ptr() : nullptr;
-  ln.beta = has_ln ? (const __nv_bfloat16*)beta->data_ptr() : nullptr;
-  if (Xres.has_value() && Xres->defined()) {
-    TORCH_CHECK(Xres->is_contiguous() && Xres->size(1) == nO && Xres->scalar_type() == at::kBFloat16);
-    ln.xres = (const __nv_bfloat16*)Xres->data_ptr();
-  }
-  ln.mask = mask.data_ptr<float>();
-  ln.y = (__nv_bfloat16*)Y.data_ptr();
-  ln.xhat = (__nv_bfloat16*)xhat.data_ptr();
-  ln.rstd = rstd.data_ptr<float>();
-  ln.done = counters.data_ptr<int>();
-  ln.consumed = counters.data_ptr<int>() + counters.size(1);
-  ln.drop_p = (float)drop_p;
-  ln.seed = (unsigned long long)seed;
-  ln.seed_dev = seed_dev.has_value() && seed_dev->defined() ? (const long long*)seed_dev->data_ptr<int64_t>() : nullptr;
-  tc_gemm_impl(A, B, H, MODE_KK, EPI_MAXOUT3_LN, 192, M, N, K, a_row_shift, a_col_off, b_row_off, b_col_off, 1, 0, bias,
-               which, c10::nullopt, c10::nullopt, c10::nullopt, 0, cluster, &ln);
-}
-
 }  // namespace
 
 void register_gemm_ops(torch::Library& m) {
-  m.def(
-      "tc_gemm_maxout_ln(Tensor A, Tensor B, Tensor(a!) H, Tensor(b!) which, Tensor? bias, Tensor? G, Tensor? beta, "
-      "Tensor? Xres, Tensor mask, Tensor(c!) Y, Tensor(d!) xhat, Tensor(e!) rstd, Tensor(f!) counters, int M, int N, "
-      "int K, int[] a_row_shift, int[] a_col_off, int[] b_row_off, int[] b_col_off, float drop_p, int seed, "
-      "Tensor? seed_dev, int cluster) -> ()");
   m.def(
       "tc_gemm(Tensor A, Tensor B, Tensor(a!) out, int mode, int epi, int block_n, int M, int N, int K, "
       "int[] a_row_shift, int[] a_col_off, int[] b_row_off, int[] b_col_off, int splits, int win_w, "
       "Tensor? bias, Tensor? which, Tensor? add_src, Tensor? row_scale, Tensor? m_dev, int max_ctas, int cluster) -> ()");
 }
-void register_gemm_impls(torch::Library& m) {
-  m.impl("tc_gemm", tc_gemm);
-  m.impl("tc_gemm_maxout_ln", tc_gemm_maxout_ln);
-}
+void register_gemm_impls(torch::Library& m) { m.impl("tc_gemm", tc_gemm); }
 
 }  // namespace srb

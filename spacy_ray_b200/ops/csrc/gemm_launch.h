@@ -12,30 +12,7 @@ namespace srb {
 // MODE_KMN:  A (M,K) K-major, B (K,N) MN-major ("NN")          - dX = dY @ W with W as stored,
 //            no per-step transpose of the weights; b_row_off = K (row) offset, b_col_off = N offset
 enum { MODE_KK = 0, MODE_MNMN = 1, MODE_KMN = 2 };
-// EPI_MAXOUT3_LN: EPI_MAXOUT3, plus four extra warps per CTA that apply LayerNorm / dropout /
-// residual to finished rows while the GEMM is still running (see LnFuse).
-enum { EPI_STORE = 0, EPI_MAXOUT3 = 1, EPI_ATOMIC_F32 = 2, EPI_MAXOUT3_LN = 3 };
-
-// LayerNorm fused behind the maxout epilogue.  A 128-row block of H = maxout(XW+b) is complete once
-// the epilogue warps of all N tiles covering it have stored their part (`done[m_tile]` counts them,
-// release/acquire at GPU scope).  Each CTA's LN warps then normalise the 128/n_tiles rows matching
-// the CTA's own N tile of that block - reading H back through L2 - so the work is spread over the
-// same CTAs that produced the block and finishes a few microseconds after the last MMA instead of
-// running as a separate memory-bound kernel.  `done`/`consumed` reset themselves.
-struct LnFuse {
-  const __nv_bfloat16* g;       // (nO) gamma, or null = no LayerNorm (dropout/residual only)
-  const __nv_bfloat16* beta;
-  const __nv_bfloat16* xres;    // (T, nO) residual input or null
-  const float* mask;            // (T)
-  __nv_bfloat16* y;             // (T, nO) block output
-  __nv_bfloat16* xhat;          // (T, nO) normalised activations (for backward) or null
-  float* rstd;                  // (T) or null
-  int* done;                    // (m_tiles) zero-initialised once
-  int* consumed;                // (m_tiles) zero-initialised once
-  float drop_p;
-  unsigned long long seed;
-  const long long* seed_dev;
-};
+enum { EPI_STORE = 0, EPI_MAXOUT3 = 1, EPI_ATOMIC_F32 = 2 };
 
 struct GemmParams {
   int M, N, K;              // K = reduction length per shift (MODE_KK) or total (MODE_MNMN)
@@ -54,7 +31,6 @@ struct GemmParams {
   const __nv_bfloat16* add_src;     // STORE: optional out += row_scale[row] * add_src[row, n]
   const float* row_scale;
   int ld_add;
-  LnFuse ln;                        // EPI_MAXOUT3_LN only
 };
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,

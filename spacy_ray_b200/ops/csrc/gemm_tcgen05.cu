@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include "gemm_launch.h"
 #include "gemm_tcgen05.cuh"
-#include "ln_rows.cuh"
 
 namespace srb {
 
@@ -28,10 +27,6 @@ using namespace sm100;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kNumThreads = 320;          // TMA warp + MMA warp + 8 epilogue warps
-constexpr int kLnWarps = 4;               // EPI_MAXOUT3_LN: + LayerNorm warps
-constexpr int kNumThreadsLn = kNumThreads + kLnWarps * 32;
-__host__ __device__ constexpr int threads_for(int epi) { return epi == EPI_MAXOUT3_LN ? kNumThreadsLn : kNumThreads; }
-constexpr int kLnUpl = 8;                 // fused LN is compiled for width 256 (32 lanes x 8 units)
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 
@@ -66,7 +61,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // CTAs run a TMA producer (completion bytes are signalled on the leader's barriers), only the
 // leader (cluster rank 0) runs the MMA issuer, both run their own epilogue.
 template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR>
-__global__ void __launch_bounds__(threads_for(EPI), 1)
+__global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   static_assert(!PAIR || CL == 2, "the pair MMA needs a 2-CTA cluster");
   using C = Cfg<BLOCK_N, PAIR>;
@@ -108,7 +103,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr); else tmem_alloc<C::kTmemCols>(tmem_ptr); }
   if (p.bias && warp >= 2) {                     // bias -> smem (fp32) once per CTA
-    for (int i = threadIdx.x - 64; i < p.N; i += threads_for(EPI) - 64) bias_s[i] = bf2f(p.bias[i]);
+    for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised too
@@ -258,7 +253,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ++it;
       }
     }
-  } else if (warp < 10) {
+  } else {
     // ================================ epilogue =========================================
     // 8 warps: warp -> TMEM lane quadrant (warp % 4) and column half ((warp - 2) / 4).  The MMA
     // warp was measured spinning on tmem_empty (4 warps, per-element bias LDGs, one wait per
@@ -311,7 +306,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-      } else if (EPI == EPI_MAXOUT3 || EPI == EPI_MAXOUT3_LN) {
+      } else if (EPI == EPI_MAXOUT3) {
         __nv_bfloat16* out = (__nv_bfloat16*)p.out;
 #pragma unroll 1
         for (int c = 0; c < HN; c += 48) {
@@ -357,57 +352,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       tc_fence_before();
-      if (EPI == EPI_MAXOUT3_LN) __threadfence();        // my part of H is visible GPU-wide before it is counted
       __syncwarp();
       if (lane == 0) {
         if (PAIR && cta_rank != 0) mbar_arrive_cluster(map_to_cta(tmem_empty + acc, 0));   // the leader issues the MMAs
         else mbar_arrive(tmem_empty + acc);
-        if (EPI == EPI_MAXOUT3_LN) atomicAdd(p.ln.done + m0 / BM, 1);
       }
       ++it;
-    }
-  }
-  if (EPI == EPI_MAXOUT3_LN && warp >= 10) {
-    // ================================ LayerNorm warps ==================================
-    // Walk the same tile sequence as this CTA's epilogue.  For tile (m_tile, n_tile): once all
-    // n_tiles tiles of the 128-row block are stored (8 epilogue warps each), normalise the
-    // 128 / n_tiles rows that correspond to n_tile; the four LN warps split those rows.
-    const LnFuse& L = p.ln;
-    const int lw = warp - 10;
-    const int rows_per_tile = BM / n_tiles;                 // host guarantees n_tiles divides 128
-    const int rows_per_warp = rows_per_tile / kLnWarps;
-    uint64_t seed = L.seed;
-    if (L.seed_dev) seed += (uint64_t)*L.seed_dev;
-    const float inv_keep = L.drop_p > 0.f ? 1.0f / (1.0f - L.drop_p) : 1.0f;
-    const uint32_t thr = dropout_thr(L.drop_p);
-    const bool has_ln = L.g != nullptr;
-    float gk[kLnUpl], bk[kLnUpl];
-#pragma unroll
-    for (int j = 0; j < kLnUpl; ++j) {
-      gk[j] = has_ln ? bf2f(L.g[lane * kLnUpl + j]) : 1.f;
-      bk[j] = has_ln ? bf2f(L.beta[lane * kLnUpl + j]) : 0.f;
-    }
-    const int target = 8 * n_tiles;
-    for (int w = first_item; w < total_items; w += item_stride) {
-      const int tile = w / splits;
-      const int mg = tile / n_tiles, nt = tile % n_tiles;
-      if (mg * CL * BM >= M) continue;
-      const int mt = mg * CL + (int)cta_rank;
-      const int* cnt = L.done + mt;
-      int seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(cnt) : "memory");
-        if (seen < target) __nanosleep(100);
-      } while (seen < target);
-      const int r0 = mt * BM + nt * rows_per_tile + lw * rows_per_warp;
-      ln_fwd_rows<kLnUpl, 4>((const __nv_bfloat16*)p.out, L.xres, L.mask, gk, bk, has_ln, L.y, L.xhat, L.rstd, r0,
-                             rows_per_warp, M, lane, L.drop_p, thr, inv_keep, seed);
-      __syncwarp();
-      if (lane == 0) {
-        // the last of the kLnWarps * n_tiles consumers of this row block re-arms its counters
-        const int old = atomicAdd(L.consumed + mt, 1);
-        if (old == kLnWarps * n_tiles - 1) { L.consumed[mt] = 0; L.done[mt] = 0; }
-      }
     }
   }
   tc_fence_before();
@@ -466,7 +416,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   if (clusters <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
-  cfg.blockDim = dim3(threads_for(EPI));
+  cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -481,7 +431,7 @@ int gemm_block_k() { return BK; }
 
 bool gemm_supports_cluster(int block_n, int mode, int epi) {
   if (mode == MODE_KK && (epi == EPI_STORE) && (block_n == 256 || block_n == 192 || block_n == 128)) return true;
-  if (mode == MODE_KK && (epi == EPI_MAXOUT3 || epi == EPI_MAXOUT3_LN) && block_n == 192) return true;
+  if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
   if (mode == MODE_MNMN && epi == EPI_ATOMIC_F32 && (block_n == 256 || block_n == 128)) return true;
   if (mode == MODE_KMN && epi == EPI_STORE && (block_n == 256 || block_n == 128)) return true;
   return false;
@@ -502,7 +452,6 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
   SRB_CASE(128, MODE_KK, EPI_STORE)
   SRB_CASE1(64, MODE_KK, EPI_STORE)
   SRB_CASE(192, MODE_KK, EPI_MAXOUT3)
-  SRB_CASE(192, MODE_KK, EPI_MAXOUT3_LN)
   SRB_CASE1(96, MODE_KK, EPI_MAXOUT3)
   SRB_CASE(256, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE(128, MODE_MNMN, EPI_ATOMIC_F32)

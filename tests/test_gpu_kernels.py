@@ -244,41 +244,6 @@ def test_maxout_block_fwd_bwd(ref, use_tc, window, residual, w):
     _close(dbeta, dbetar, 5e-2, 0.05 * math.sqrt(T), "dbeta")
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 3])
-@pytest.mark.parametrize("window,residual", [(1, True), (0, False)])
-def test_fused_gemm_layernorm_matches_two_kernel_path(cluster, window, residual):
-    """EPI_MAXOUT3_LN (LN warps inside the GEMM kernel, row-block completion counters) must give the
-    two-kernel result bit for bit - also on repeated launches (the counters re-arm themselves)."""
-    from spacy_ray_b200.ops.b200_ops import B200Ops
-
-    torch.manual_seed(21)
-    lens = [int(x) for x in torch.randint(1, 60, (170,))]
-    w_in = 256
-    X, mask = _padded_batch(lens, w_in)
-    Xb = X.bfloat16()
-    nO, nP = 256, 3
-    W = (torch.randn(nO, nP, w_in * (3 if window else 1), device="cuda") * 0.05).bfloat16()
-    b = (torch.randn(nO, nP, device="cuda") * 0.1).bfloat16()
-    G = (torch.rand(nO, device="cuda") + 0.5).bfloat16()
-    beta = (torch.randn(nO, device="cuda") * 0.1).bfloat16()
-    fused, plain = B200Ops("cuda:0"), B200Ops("cuda:0")
-    fused.gemm_cluster = plain.gemm_cluster = cluster
-    plain.fused_ln = False
-    assert fused.fused_ln
-    Yp, cp = plain.maxout_block(Xb, W, b, G, beta, mask, window=window, residual=residual, dropout=0.1, is_train=True,
-                                seed=5)
-    for _ in range(3):
-        Yf, cf = fused.maxout_block(Xb, W, b, G, beta, mask, window=window, residual=residual, dropout=0.1,
-                                    is_train=True, seed=5)
-        torch.cuda.synchronize()
-        assert torch.equal(cf["which"], cp["which"])
-        assert torch.equal(Yf, Yp)
-        assert torch.equal(cf["xhat"], cp["xhat"])
-        assert torch.equal(cf["rstd"], cp["rstd"])
-    cnt = next(iter(fused._ln_cnt.values()))
-    assert int(cnt.abs().sum()) == 0                       # every counter back to zero
-
-
 def test_softmax_xent(ops, ref):
     torch.manual_seed(6)
     X = torch.randn(500, 64, device="cuda").bfloat16()

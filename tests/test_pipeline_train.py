@@ -134,3 +134,54 @@ vocab_size = 300
     assert not torch.equal(before, node.get_param("W"))       # gradients reached the shared layer
     assert float(losses["tagger"]) > 0 and float(losses["ner"]) > 0
     assert nlp.evaluate(exs[:10])["tag_acc"] is not None
+
+
+def test_shared_tok2vec_deferred_backprop_matches_immediate():
+    """Tok2VecComponent.update(defer_backprop=True) + finish_backprop() (what engine.Trainer uses to
+    run listener heads on concurrent streams) must produce the same gradients as the default
+    'backward fires with the last listener' protocol."""
+    from pathlib import Path
+
+    import torch
+
+    from spacy_ray_b200.config import Config, resolve_dot_names
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.training.initialize import init_nlp
+
+    text = (Path(__file__).resolve().parent.parent / "configs" / "multitask_w512.cfg").read_text()
+    text = text.replace("width = 512", "width = 32").replace("depth = 8", "depth = 1")
+    text = text.replace("hidden_width = 128", "hidden_width = 32").replace("n_docs = 20000", "n_docs = 24")
+    text = text.replace("max_len = 40", "max_len = 9")
+    cfg = Config().from_str(text, interpolate=False)
+
+    def grads(defer: bool):
+        fix_random_seed(0)
+        nlp = init_nlp(cfg)
+        corpus = resolve_dot_names(cfg.interpolate(), ["corpora.train"])[0]
+        examples = list(corpus(nlp))[:16]
+        batch = nlp.make_batch([eg.predicted for eg in examples])
+        t2v = nlp.get_pipe("tok2vec")
+        gen = torch.Generator().manual_seed(1)
+        for name in ("tagger", "parser", "ner"):        # output layers start at zero: no gradient would reach tok2vec
+            for node in nlp.get_pipe(name).model.walk():
+                for pname in node.param_names:
+                    w = node.get_param(pname)
+                    node.set_param(pname, w + 0.1 * torch.randn(w.shape, generator=gen).to(w.dtype))
+        t2v.update(examples, batch=batch, drop=0.0, sgd=False, losses={}, defer_backprop=defer)
+        for name in ("tagger", "parser", "ner"):
+            nlp.get_pipe(name).update(examples, batch=batch, drop=0.0, sgd=False, losses={})
+        if defer:
+            t2v.finish_backprop()
+        out = {}
+        for node in t2v.model.walk():
+            for pname in node.param_names:
+                g = node.get_grad(pname) if node.has_grad(pname) else None
+                if g is not None:
+                    out[(node.name, node.id, pname)] = g.clone()
+        return out
+
+    a, b = grads(False), grads(True)
+    assert a and a.keys() == b.keys()
+    assert any(float(v.abs().sum()) > 0 for v in a.values())
+    for k in a:
+        torch.testing.assert_close(a[k], b[k], rtol=1e-5, atol=1e-6)

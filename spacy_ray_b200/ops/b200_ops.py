@@ -115,12 +115,13 @@ class B200Ops(TorchOps):
         T, N = dZ.shape
         w = X.shape[1]
         Kt = w * (3 if window else 1)
-        if not (self.use_tc and self.tc_dw and N % 128 == 0 and w % 64 == 0):
+        # N % 64: a 64-row operand fills half of the 128-row M tile, the TMA zero-fills the rest
+        if not (self.use_tc and self.tc_dw and N % 64 == 0 and w % 64 == 0):
             return None
         bn = 256 if w % 256 == 0 else (128 if w % 128 == 0 else 64)
         if out is None:
             out = torch.zeros((N, Kt), dtype=torch.float32, device=dZ.device)
-        tiles = (N // 128) * (Kt // bn)
+        tiles = ((N + 127) // 128) * (Kt // bn)
         splits = max(1, min(148 // max(tiles, 1), (T + 63) // 64))
         self.tc_gemm(dZ, X, out, mode=MODE_MNMN, epi=EPI_ATOMIC_F32, block_n=bn, M=N, N=Kt, K=T, splits=splits,
                      win_w=(w if window else 0))
@@ -320,7 +321,7 @@ class B200Ops(TorchOps):
     def linear_backward(self, dY, X, W, need_dX: bool = True, need_db: bool = True):
         dY = dY.to(torch.bfloat16).contiguous() if dY.dtype != torch.bfloat16 else dY.contiguous()
         X = X.contiguous()
-        dW = self._dw_tc(dY, X, 0) if dY.shape[1] % 128 == 0 else None
+        dW = self._dw_tc(dY, X, 0)
         if dW is None:
             dW = _mm_f32(dY.t(), X)
         db = self.colsum(dY) if need_db else None
@@ -431,12 +432,18 @@ class B200Ops(TorchOps):
         d = rec["d_scores"]                   # (S, nA_pad) bf16, padded columns are zero
         hid = rec["hid"]
         dev = d.device
-        dWu = _mm_f32(d.t(), hid)[:nA]
+        # d has a 128-multiple pitch (zero columns past nA), so both products run on the tcgen05 kernels
+        dWu = self._dw_tc(d, hid, 0)
+        if dWu is None:
+            dWu = _mm_f32(d.t(), hid)
+        dWu = dWu[:nA]
         dbu = self.colsum(d)[:nA]
         Wu = params["Wu"]
         Wu_pad = Wu if Wu.shape[0] == d.shape[1] else torch.cat(
             [Wu, torch.zeros((d.shape[1] - Wu.shape[0], Wu.shape[1]), dtype=Wu.dtype, device=dev)], 0)
-        d_hid = (d @ Wu_pad).contiguous()
+        d_hid = self._dx_tc(d, Wu_pad)
+        if d_hid is None:
+            d_hid = (d @ Wu_pad).contiguous()
         dYf = torch.zeros((n_rows, nF * nO * nP), dtype=torch.float32, device=dev)
         dpad = torch.zeros((nF, nO * nP), dtype=torch.float32, device=dev)
         db = torch.zeros((nO * nP,), dtype=torch.float32, device=dev)

@@ -199,7 +199,8 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   Tensor feats = at::empty({train ? T : 0, 3}, o.dtype(at::kInt));
   Tensor which = at::empty({train ? T : 0, nO}, o.dtype(at::kByte));
   Tensor hid = at::zeros({train ? T : 0, nO}, o);            // rows past the real token count stay zero
-  Tensor d_scores = at::zeros({train ? T : 0, nA_pad}, o);   // (fixed-capacity batches under CUDA graphs)
+  const int64_t ldd = (nA_pad + 127) / 128 * 128;             // GEMM-friendly pitch (dWu / d_hid run on tcgen05)
+  Tensor d_scores = at::zeros({train ? T : 0, ldd}, o);      // (fixed-capacity batches under CUDA graphs)
   Tensor actions = at::empty({T}, o.dtype(at::kInt));
   Tensor loss = at::zeros({}, o.dtype(at::kFloat));
   srb::BiluoArgs a{};
@@ -210,7 +211,7 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   a.inv_active = inv_active.data_ptr<float>();
   a.feats = feats.data_ptr<int32_t>(); a.which = which.data_ptr<uint8_t>(); a.hid = hid.data_ptr();
   a.d_scores = d_scores.data_ptr(); a.actions = actions.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
-  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad;
+  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad; a.ld_scores = (int)ldd;
   a.n_labels = (int)n_labels; a.train = train ? 1 : 0;
   srb::launch_biluo_steps(a, cur_stream());
   return {feats, which, hid, d_scores, actions, loss};
@@ -232,7 +233,8 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   Tensor feats = at::full({S, 8}, -1, o.dtype(at::kInt));
   Tensor which = at::zeros({S, nO}, o.dtype(at::kByte));
   Tensor hid = at::zeros({S, nO}, o);
-  Tensor d_scores = at::zeros({S, nA_pad}, o);
+  const int64_t ldd = (nA_pad + 127) / 128 * 128;
+  Tensor d_scores = at::zeros({S, ldd}, o);
   Tensor history = at::full({n_steps_cap}, -1, o.dtype(at::kInt));
   Tensor heads = at::empty({n_tokens}, o.dtype(at::kInt));
   Tensor labels = at::empty({n_tokens}, o.dtype(at::kInt));
@@ -250,7 +252,7 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   a.heads_out = heads.data_ptr<int32_t>(); a.labels_out = labels.data_ptr<int32_t>();
   a.n_steps = n_steps.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
   a.scale = (float)scale;
-  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad;
+  a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad; a.ld_scores = (int)ldd;
   a.train = train ? 1 : 0;
   TORCH_CHECK(srb::launch_arc_eager_steps(a, cur_stream()), "arc_eager_steps: unsupported hidden width / pieces / #actions");
   return {feats, which, hid, d_scores, history, heads, labels, n_steps, loss};

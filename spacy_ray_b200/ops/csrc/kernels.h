@@ -91,7 +91,8 @@ struct BiluoArgs {
   int32_t* feats;              // (T, 3) rows
   uint8_t* which;              // (T, nO)
   void* hid;                   // bf16 (T, nO)
-  void* d_scores;              // bf16 (T, nA_pad)
+  void* d_scores;              // bf16 (T, ld_scores); columns >= nA stay zero
+  int ld_scores;               // row pitch of d_scores (multiple of 128: feeds the tcgen05 GEMMs directly)
   int32_t* actions;            // (T)
   float* loss;                 // scalar accumulator
   int B, nO, nP, nA, nA_pad, n_labels, train;
@@ -117,7 +118,8 @@ struct ArcArgs {
   int32_t* feats;              // (S, 8)
   uint8_t* which;              // (S, nO)
   void* hid;                   // bf16 (S, nO)
-  void* d_scores;              // bf16 (S, nA_pad)
+  void* d_scores;              // bf16 (S, ld_scores); columns >= nA stay zero
+  int ld_scores;
   int32_t* history;            // (S) chosen action per step (optional)
   int32_t* heads_out;          // (T) predicted head (doc-relative, root = self)
   int32_t* labels_out;         // (T) predicted label or -1

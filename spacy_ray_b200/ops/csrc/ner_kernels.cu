@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
           float dv = 0.f;
           if (ga >= 0 && ok[j]) dv = (e[j] * inv - (a == ga ? 1.f : 0.f)) * scale;
           loss_acc += dv * dv;
-          ((__nv_bfloat16*)A.d_scores)[tok * A.nA_pad + a] = f2bf(dv);
+          ((__nv_bfloat16*)A.d_scores)[tok * A.ld_scores + a] = f2bf(dv);
         }
       }
       if (lane < 3) {

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
           float dv = 0.f;
           if (ok[j] && gsum > 0.f) dv = (e[j] * inv - eg[j] * ginv) * A.scale;
           loss_acc += dv * dv;
-          ((__nv_bfloat16*)A.d_scores)[rec * A.nA_pad + a] = f2bf(dv);
+          ((__nv_bfloat16*)A.d_scores)[rec * A.ld_scores + a] = f2bf(dv);
         }
       }
       if (lane < 8) {

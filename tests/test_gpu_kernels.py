@@ -188,11 +188,11 @@ def test_colsum_kernel(ops, T, C):
 
 @pytest.mark.parametrize("window", [0, 1])
 @pytest.mark.parametrize("cluster", [1, 2, 3])
-def test_tc_dw_mn_major_split_k(ops, ref, window, cluster):
+@pytest.mark.parametrize("w,N", [(128, 384), (64, 64), (256, 128), (64, 192)])
+def test_tc_dw_mn_major_split_k(ops, ref, window, cluster, w, N):
     ops = type(ops)("cuda:0")
     ops.gemm_cluster = cluster
     torch.manual_seed(4)
-    w, N = 128, 384
     X, mask = _padded_batch(tuple(range(2, 60)), w)
     Xb = X.bfloat16()
     Tp = X.shape[0]

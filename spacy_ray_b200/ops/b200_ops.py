@@ -71,7 +71,6 @@ class B200Ops(TorchOps):
         # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
         # replays draw fresh masks although the per-call seeds were baked in at capture time
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._wt_cache: Dict[int, Tuple[int, torch.Tensor]] = {}
         # weight-gradient GEMMs that accumulate straight into the flat gradient bucket run on a side
         # stream: nothing in the backward pass reads them, and their CTAs fill the SMs the dX GEMM
         # leaves idle in its last, partial wave (201 M-tiles on 148 SMs = 1.36 waves).  The

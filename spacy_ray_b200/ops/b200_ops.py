@@ -337,6 +337,22 @@ class B200Ops(TorchOps):
 
     def softmax_xent(self, X, W, b, labels):
         X = X.contiguous()
+        nC = W.shape[0]
+        if X.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and X.shape[1] % 16 == 0 and nC <= 128:
+            # K6 in one kernel: logits GEMM + softmax + CE gradient + loss + argmax
+            out = self.k.linear_softmax_xent(X, W.contiguous(), b.to(torch.bfloat16).contiguous(), labels.contiguous())
+            if out:
+                dp, guesses, loss = out                        # dp: (T, 128k) bf16, zero past nC
+                self.launches += 1
+                dW = self._dw_tc(dp, X, 0)
+                dW = dW[:nC] if dW is not None else _mm_f32(dp[:, :nC].t(), X)
+                db = self.colsum(dp)[:nC]
+                Wp = W if nC == dp.shape[1] else torch.cat(
+                    [W, torch.zeros((dp.shape[1] - nC, W.shape[1]), dtype=W.dtype, device=W.device)], 0)
+                dX = self._dx_tc(dp, Wp)
+                if dX is None:
+                    dX = dp[:, :nC] @ W
+                return loss, dp[:, :nC], guesses, dX, dW, db
         logits = (X @ W.t()).to(torch.float32) + b.to(torch.float32)
         d, guesses, loss = self.k.softmax_xent(logits.contiguous(), labels.contiguous())
         self.launches += 1

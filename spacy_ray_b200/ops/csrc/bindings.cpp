@@ -165,6 +165,25 @@ std::vector<Tensor> softmax_xent(const Tensor& logits, const Tensor& labels) {
   return {d, guesses, loss};
 }
 
+// Tagger head in one kernel.  Returns {d (Tp, ldd) bf16 with ldd = 128-multiple and zeros past nC, guesses, loss};
+// an empty list when the shape is outside the kernel's range (caller falls back to GEMM + softmax_xent).
+std::vector<Tensor> linear_softmax_xent(const Tensor& X, const Tensor& W, const Tensor& b, const Tensor& labels) {
+  SRB_CHECK_CUDA(X); SRB_CHECK_BF16(X); SRB_CHECK_CUDA(W); SRB_CHECK_BF16(W); SRB_CHECK_CUDA(b); SRB_CHECK_BF16(b);
+  SRB_CHECK_CUDA(labels);
+  TORCH_CHECK(labels.scalar_type() == at::kLong && X.dim() == 2 && W.dim() == 2 && W.size(1) == X.size(1));
+  c10::cuda::CUDAGuard guard(X.device());
+  const int Tp = (int)X.size(0), w = (int)X.size(1), nC = (int)W.size(0);
+  const int64_t ldd = ((nC + 7) / 8 * 8 + 127) / 128 * 128;
+  Tensor d = at::zeros({Tp, ldd}, X.options());
+  Tensor guesses = at::empty({Tp}, X.options().dtype(at::kLong));
+  Tensor loss = at::zeros({}, X.options().dtype(at::kFloat));
+  const bool ok = srb::try_launch_linear_softmax_xent(X.data_ptr(), W.data_ptr(), b.data_ptr(), labels.data_ptr<int64_t>(),
+                                                      d.data_ptr(), guesses.data_ptr<int64_t>(), loss.data_ptr<float>(),
+                                                      Tp, w, nC, (int)ldd, cur_stream());
+  if (!ok) return {};
+  return {d, guesses, loss};
+}
+
 void adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, c10::optional<Tensor> w_out, const Tensor& blk_key,
                 const Tensor& blk_off, const Tensor& key_off, const Tensor& key_len, Tensor norms, const Tensor& hyper,
                 const Tensor& step) {
@@ -279,6 +298,7 @@ TORCH_LIBRARY(srb, m) {
   m.def("seq2col(Tensor X) -> Tensor");
   m.def("col2seq_residual(Tensor dXw, Tensor? dY, Tensor mask) -> Tensor");
   m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");
+  m.def("linear_softmax_xent(Tensor X, Tensor W, Tensor b, Tensor labels) -> Tensor[]");
   m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
   m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train) -> Tensor[]");
   m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train) -> Tensor[]");
@@ -297,6 +317,7 @@ TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("seq2col", seq2col);
   m.impl("col2seq_residual", col2seq_residual);
   m.impl("softmax_xent", softmax_xent);
+  m.impl("linear_softmax_xent", linear_softmax_xent);
   m.impl("adam_shard", adam_shard);
   m.impl("biluo_steps", biluo_steps);
   m.impl("arc_eager_steps", arc_eager_steps);

@@ -50,6 +50,10 @@ bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float*
 void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool perm_is_i32, const float* mask, HashEmbedTables t,
                                   const void* dY, int R, cudaStream_t s);
 
+// K6 fused: logits GEMM + softmax + CE gradient (pitch ldd, zero-initialised by the caller) + loss + argmax
+bool try_launch_linear_softmax_xent(const void* X, const void* W, const void* b, const int64_t* labels, void* d_out,
+                                    int64_t* guesses, float* loss, int Tp, int w, int nC, int ldd, cudaStream_t s);
+
 // out[c] += sum_t X[t, c]  (bf16 in, fp32 accumulate); false = shape not supported.
 bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, cudaStream_t s);
 

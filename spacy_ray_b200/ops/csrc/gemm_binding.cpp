@@ -7,6 +7,8 @@
 #include <torch/types.h>
 
 #include "gemm.h"
+#include <cstdlib>
+
 #include "gemm_launch.h"
 
 namespace srb {
@@ -39,16 +41,28 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
               b_row_off.size() == a_row_shift.size() && b_col_off.size() == a_row_shift.size());
   c10::cuda::CUDAGuard guard(A.device());
   if ((cluster != 2 && cluster != 3) || !gemm_supports_cluster((int)block_n, (int)mode, (int)epi)) cluster = 1;
+  // window GEMM (shifts -1/0/+1 of the same A columns): load A once per k-block with a one-row halo
+  bool halo = false;
+  if (n_shifts == 3 && splits <= 1 && gemm_supports_halo((int)block_n, (int)mode, (int)epi, (int)cluster) &&
+      std::getenv("SRB_GEMM_HALO") == nullptr) {
+    bool seen[3] = {false, false, false};
+    halo = a_col_off[0] == a_col_off[1] && a_col_off[1] == a_col_off[2];
+    for (int s = 0; s < 3 && halo; ++s) {
+      const int64_t r = a_row_shift[s] + 1;
+      if (r < 0 || r > 2 || seen[r]) halo = false; else seen[r] = true;
+    }
+  }
+  const uint32_t a_rows = halo ? (uint32_t)kHaloRows : 128u;
   CUtensorMap ta, tb;
   int r1, r2;
   if (mode == MODE_KK) {
-    r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);
+    r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, a_rows);
     // with a 2-CTA cluster each CTA loads (and multicasts) half of the B rows of a tile
     r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64,
                            (uint32_t)(cluster > 1 ? block_n / 2 : block_n));
   } else if (mode == MODE_KMN) {
     TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major B needs block_n % 64 == 0");
-    r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, 128);
+    r1 = make_tmap_2d_bf16(&ta, A.data_ptr(), (uint64_t)A.size(1), (uint64_t)A.size(0), (uint64_t)A.stride(0) * 2, 64, a_rows);
     r2 = make_tmap_2d_bf16(&tb, B.data_ptr(), (uint64_t)B.size(1), (uint64_t)B.size(0), (uint64_t)B.stride(0) * 2, 64, 64);
   } else {
     TORCH_CHECK(block_n % 64 == 0, "tc_gemm: MN-major mode needs block_n % 64 == 0");
@@ -64,6 +78,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
     p.b_row_off[s] = (int)b_row_off[s]; p.b_col_off[s] = (int)b_col_off[s];
   }
   p.splits = (int)splits; p.win_w = (int)win_w;
+  p.halo = halo ? 1 : 0;
   p.m_dev = m_dev.has_value() && m_dev->defined() ? m_dev->data_ptr<int>() : nullptr;
   p.out = out.data_ptr();
   p.ldo = (int)out.stride(0);

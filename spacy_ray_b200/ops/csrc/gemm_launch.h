@@ -21,6 +21,7 @@ struct GemmParams {
   int a_col_off[3];         // added to the A K coordinate
   int b_row_off[3];         // added to the B row coordinate (N for MODE_KK, K for MODE_KMN)
   int b_col_off[3];         // added to the B column coordinate (K for MODE_KK, N for MODE_KMN)
+  int halo;                 // window GEMMs: A tile loaded ONCE per k-block with a one-row halo (see kernel)
   int splits;               // split-K factor (EPI_ATOMIC_F32)
   int win_w;                // MODE_MNMN: >0 = B is the window-expanded view of a (T, win_w) array
   const int* m_dev;         // optional device-side row count (<= M) for fixed-shape CUDA graphs
@@ -41,6 +42,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
                         int cluster, int num_sms, cudaStream_t s);
 bool gemm_supports_cluster(int block_n, int mode, int epi);
+// window GEMM with shifts {-1,0,+1}: true if a halo variant (A loaded once per k-block) is compiled
+bool gemm_supports_halo(int block_n, int mode, int epi, int cluster);
+constexpr int kHaloRows = 130;   // A tensor map box rows for the halo variants
 int gemm_block_k();
 
 }  // namespace srb

@@ -32,10 +32,18 @@ constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 
 // PAIR (cta_group::2): a CTA stores only its half of the B tile, so a stage is smaller and the
 // ring is deeper - more bytes in flight per SM for the same shared memory.
-template <int BLOCK_N, bool PAIR = false>
+// HALO (window GEMMs, shifts -1/0/+1): the A tile is loaded ONCE per k-block with one extra row
+// above and below (130 rows x 128 B) and the three shifted operands are read out of it through
+// descriptors that start 0, 1 or 2 rows into the tile (base_offset = row phase).  That removes two
+// of the three A loads of these L2->SM-bound kernels; a stage then carries the B tiles of all
+// three shifts.
+template <int BLOCK_N, bool PAIR = false, bool HALO = false>
 struct Cfg {
-  static constexpr int kStageA = BM * BK * 2;            // 16 KB
-  static constexpr int kStageB = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BK * 2;
+  static constexpr int kTileB = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BK * 2;
+  static constexpr int kBoxA = (HALO ? kHaloRows : BM) * BK * 2;             // bytes the A load delivers
+  static constexpr int kStageA = HALO ? 17 * 1024 : BM * BK * 2;             // 1024-aligned
+  static constexpr int kStageB = (HALO ? 3 : 1) * kTileB;
+  static constexpr int kTxBytes = kBoxA + kStageB;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStagesRaw = kSmemBudget / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -60,11 +68,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // stored AND fetched, which is what the L2 -> smem-bound single-CTA kernels were missing.  Both
 // CTAs run a TMA producer (completion bytes are signalled on the leader's barriers), only the
 // leader (cluster rank 0) runs the MMA issuer, both run their own epilogue.
-template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR>
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR, bool HALO = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   static_assert(!PAIR || CL == 2, "the pair MMA needs a 2-CTA cluster");
-  using C = Cfg<BLOCK_N, PAIR>;
+  static_assert(!HALO || (MODE != MODE_MNMN && (PAIR || CL == 1)), "halo: K-major A, single CTA or pair MMA");
+  using C = Cfg<BLOCK_N, PAIR, HALO>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
@@ -81,7 +90,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = p.N / BLOCK_N;
   const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
-  const int total_kb = (MODE != MODE_MNMN ? p.n_shifts : 1) * kpb;
+  const int total_kb = (MODE != MODE_MNMN && !HALO ? p.n_shifts : 1) * kpb;
   const int splits = p.splits > 0 ? p.splits : 1;
   const int m_groups = (m_tiles + CL - 1) / CL;              // a cluster takes CL vertically adjacent M tiles
   const int total_items = m_groups * n_tiles * splits;
@@ -124,6 +133,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* a_dst = sA + stage * C::kStageA;
           unsigned char* b_dst = sB + stage * C::kStageB;
+          if (HALO) {
+            // one A load (130 rows starting at m0 - 1; rows outside the array are zero-filled) and the
+            // B tiles of the three shifts
+            const uint32_t fb = PAIR ? map_to_cta(full_bar + stage, 0) : 0u;
+            if (!PAIR || cta_rank == 0) mbar_arrive_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * C::kTxBytes);
+            if (PAIR) tma_load_2d_2sm(a_dst, &tmA, fb, p.a_col_off[0] + kb * BK, m0 - 1);
+            else tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[0] + kb * BK, m0 - 1);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              unsigned char* bs = b_dst + s * C::kTileB;
+              if (MODE == MODE_KK) {
+                const int c = p.b_col_off[s] + kb * BK, r = n0 + p.b_row_off[s] + (PAIR ? (int)cta_rank * (BLOCK_N / 2) : 0);
+                if (PAIR) tma_load_2d_2sm(bs, &tmB, fb, c, r);
+                else tma_load_2d(bs, &tmB, full_bar + stage, c, r);
+              } else {                               // MODE_KMN: 64-column atoms of W as stored
+                constexpr int kAtoms = BLOCK_N / 64 / (PAIR ? 2 : 1);
+                const int krow = p.b_row_off[s] + kb * BK, c0 = p.b_col_off[s] + n0;
+#pragma unroll
+                for (int jj = 0; jj < kAtoms; ++jj) {
+                  const int j = (PAIR ? (int)cta_rank * kAtoms : 0) + jj;
+                  if (PAIR) tma_load_2d_2sm(bs + jj * (BK * 128), &tmB, fb, c0 + j * 64, krow);
+                  else tma_load_2d(bs + jj * (BK * 128), &tmB, full_bar + stage, c0 + j * 64, krow);
+                }
+              }
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (PAIR) {
             // both CTAs' bytes are counted on the LEADER's full barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * C::kStage);
@@ -227,6 +264,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * C::kStageA);
           const uint32_t b_addr = smem_u32(sB + stage * C::kStageB);
+          if (HALO) {
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const uint32_t r = (uint32_t)(p.a_row_shift[s] + 1);           // 0, 1 or 2 rows into the halo tile
+              const uint32_t bs = b_addr + s * C::kTileB;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t adesc = make_smem_desc(a_addr + r * 128 + k * 32, 0, 1024, r);
+                const uint64_t bdesc = MODE == MODE_KK ? make_smem_desc(bs + k * 32, 0, 1024)
+                                                       : make_smem_desc(bs + k * 16 * 128, BK * 128, 1024);
+                const uint32_t accum = (kb > kb0 || s > 0 || k > 0) ? 1u : 0u;
+                if (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accum);
+                else umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t adesc, bdesc;
@@ -242,6 +295,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           }
           if (PAIR) umma_commit_pair(empty_bar + stage, kMask);
           else if (CL == 1) umma_commit(empty_bar + stage);
@@ -398,12 +452,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR = false>
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR = false, bool HALO = false>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int num_sms, cudaStream_t s) {
-  using C = Cfg<BLOCK_N, PAIR>;
+  using C = Cfg<BLOCK_N, PAIR, HALO>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -424,7 +478,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR>, a, b, p);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO>, a, b, p);
 }
 
 int gemm_block_k() { return BK; }
@@ -437,8 +491,27 @@ bool gemm_supports_cluster(int block_n, int mode, int epi) {
   return false;
 }
 
+bool gemm_supports_halo(int block_n, int mode, int epi, int cluster) {
+  if (cluster != 1 && cluster != 3) return false;
+  if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
+  if (mode == MODE_KMN && epi == EPI_STORE && (block_n == 256 || block_n == 128)) return true;
+  return false;
+}
+
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
                         int cluster, int num_sms, cudaStream_t s) {
+  if (p.halo) {
+#define SRB_HALO(BN, MD, EP)                                                                       \
+  if (block_n == BN && mode == MD && epi == EP) {                                                  \
+    if (cluster == 3) return launch_one<BN, MD, EP, 2, true, true>(a, b, p, num_sms, s);           \
+    return launch_one<BN, MD, EP, 1, false, true>(a, b, p, num_sms, s);                            \
+  }
+    SRB_HALO(192, MODE_KK, EPI_MAXOUT3)
+    SRB_HALO(256, MODE_KMN, EPI_STORE)
+    SRB_HALO(128, MODE_KMN, EPI_STORE)
+#undef SRB_HALO
+    return cudaErrorInvalidValue;
+  }
 #define SRB_CASE(BN, MD, EP)                                                              \
   if (block_n == BN && mode == MD && epi == EP) {                                         \
     if (cluster == 3) return launch_one<BN, MD, EP, 2, true>(a, b, p, num_sms, s);        \

@@ -222,8 +222,13 @@ __device__ __forceinline__ void tmem_ld_wait_regs(float* v) {
 
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// `base_offset` (bits [49,52)): for a matrix that does not start on the 1024-byte swizzle
+// repeat - here a tile read from row r of a larger 128 B-pitch shared-memory tile - it is the
+// phase ((start_addr >> 7) & 7) the hardware needs to apply the 128 B swizzle correctly.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);             // [0,14)   start address >> 4
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // [16,30)  leading byte offset >> 4
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // [32,46)  stride byte offset >> 4

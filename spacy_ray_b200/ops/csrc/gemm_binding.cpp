@@ -44,7 +44,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   // window GEMM (shifts -1/0/+1 of the same A columns): load A once per k-block with a one-row halo
   bool halo = false;
   if (n_shifts == 3 && splits <= 1 && gemm_supports_halo((int)block_n, (int)mode, (int)epi, (int)cluster) &&
-      std::getenv("SRB_GEMM_HALO") == nullptr) {
+      !(std::getenv("SRB_GEMM_HALO") && std::getenv("SRB_GEMM_HALO")[0] == '0')) {
     bool seen[3] = {false, false, false};
     halo = a_col_off[0] == a_col_off[1] && a_col_off[1] == a_col_off[2];
     for (int s = 0; s < 3 && halo; ++s) {

@@ -34,7 +34,9 @@ constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 // ring is deeper - more bytes in flight per SM for the same shared memory.
 // HALO (window GEMMs, shifts -1/0/+1): the A tile is loaded ONCE per k-block with one extra row
 // above and below (130 rows x 128 B) and the three shifted operands are read out of it through
-// descriptors that start 0, 1 or 2 rows into the tile (base_offset = row phase).  That removes two
+// descriptors that start 0, 1 or 2 rows (128 B each) into the tile.  The 128 B swizzle is a function
+// of the absolute shared-memory address bits, so a row-shifted start address needs no further
+// correction (measured: base_offset must stay 0; setting it to the row phase gives wrong data).  That removes two
 // of the three A loads of these L2->SM-bound kernels; a stage then carries the B tiles of all
 // three shifts.
 template <int BLOCK_N, bool PAIR = false, bool HALO = false>
@@ -271,7 +273,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint32_t bs = b_addr + s * C::kTileB;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t adesc = make_smem_desc(a_addr + r * 128 + k * 32, 0, 1024, r);
+                const uint64_t adesc = make_smem_desc(a_addr + r * 128 + k * 32, 0, 1024);
                 const uint64_t bdesc = MODE == MODE_KK ? make_smem_desc(bs + k * 32, 0, 1024)
                                                        : make_smem_desc(bs + k * 16 * 128, BK * 128, 1024);
                 const uint32_t accum = (kb > kb0 || s > 0 || k > 0) ? 1u : 0u;

@@ -222,9 +222,9 @@ __device__ __forceinline__ void tmem_ld_wait_regs(float* v) {
 
 // ---- descriptors ------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
-// `base_offset` (bits [49,52)): for a matrix that does not start on the 1024-byte swizzle
-// repeat - here a tile read from row r of a larger 128 B-pitch shared-memory tile - it is the
-// phase ((start_addr >> 7) & 7) the hardware needs to apply the 128 B swizzle correctly.
+// `base_offset` (bits [49,52)) is left 0 everywhere: on sm_100a the 128 B swizzle is applied on the
+// absolute address, so a descriptor may start at any 128 B row of a 1024 B-aligned tile (the halo
+// GEMM variants rely on this; verified numerically).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t base_offset = 0) {
   uint64_t d = 0;

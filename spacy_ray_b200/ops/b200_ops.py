@@ -67,6 +67,7 @@ class B200Ops(TorchOps):
         # 3 = 2-CTA clusters issuing tcgen05.mma.cta_group::2 (M = 256, each CTA holds half of B);
         # 2 = 2-CTA clusters with single-CTA MMAs sharing B by TMA multicast; 1 = no clusters
         self.gemm_cluster = int(os.environ.get("SRB_GEMM_CLUSTER", "3"))
+        self.dx_block_n = int(os.environ.get("SRB_DX_BN", "128"))
         self.launches = 0            # our kernels launched (bench.py reports this)
         # device-side dropout stream position: the captured training step bumps it, so CUDA-graph
         # replays draw fresh masks although the per-call seeds were baked in at capture time
@@ -283,6 +284,10 @@ class B200Ops(TorchOps):
                 dW = dW_dst
         # ---- dX ----------------------------------------------------------
         bn = self._pick_block_n(w_in)
+        if window and bn and w_in % self.dx_block_n == 0:
+            # halo window GEMM: 128-wide N tiles give a 4-stage ring and 2.7 waves instead of 3 stages /
+            # 1.36 waves (measured 34.4 vs 41.8 us at the flagship shape)
+            bn = self.dx_block_n
         if self._tc_ok(N, w_in) and bn:
             # B = the weights as stored, (N, nI) = (K, N) row-major -> MN-major UMMA operand: no
             # per-step transpose of W (it changes every step, so a cached W^T is useless)

@@ -176,3 +176,35 @@ def test_engine_serves_multi_head_pipelines_like_the_generic_path(shared):
         for head in ("tagger", "parser", "ner"):
             assert abs(g[head] - f[head]) <= 0.08 * abs(g[head]) + 0.02, (head, generic, fast)
     assert fast[-1]["tagger"] < fast[0]["tagger"]
+
+
+def test_train_step_reads_each_loss_one_step_late():
+    """Trainer.train_step(lag=1) must report exactly the losses a blocking run (lag=0) reports, shifted by
+    one call; flush_loss() returns the last one."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.engine import Trainer
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.worker import Worker
+
+    text = multi_cfg(["ner"], width=64, depth=2, n_docs=200, max_len=16, hidden=64)
+
+    def run(lag):
+        fix_random_seed(0)
+        w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0, mode="sync",
+                   comm="auto")
+        w.set_proxy(None)
+        exs = list(w.train_corpus(w.nlp))
+        tr = Trainer(w.nlp, w.proxy, exs, docs_per_batch=32, dropout=0.0, prefetch=False)
+        out = [tr.train_step(np.arange(i * 8, i * 8 + 32), lag=lag) for i in range(6)]
+        last = tr.flush_loss()
+        tr.close()
+        return out, last
+
+    blocking, last0 = run(0)
+    lagged, last1 = run(1)
+    assert last0 is None or last0 == pytest.approx(blocking[-1])
+    assert lagged[0] == pytest.approx(blocking[0], rel=1e-3)            # first call has nothing older to report
+    for i in range(1, 6):
+        assert lagged[i] == pytest.approx(blocking[i - 1], rel=1e-3), (i, lagged, blocking)
+    assert last1 == pytest.approx(blocking[-1], rel=1e-3)

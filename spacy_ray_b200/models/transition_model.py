@@ -18,8 +18,8 @@ SURVEY.md K7); the PyTorch reference below is the spec it is tested against.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
 
 import torch
 

@@ -12,7 +12,7 @@ single fused tcgen05 GEMM kernel instead of thinc's ~8 launches.
 from __future__ import annotations
 
 import itertools
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 import torch
 

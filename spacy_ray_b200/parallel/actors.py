@@ -34,7 +34,7 @@ import queue
 import threading
 import time
 import traceback
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, List, Optional
 
 _CTX = mp.get_context("spawn")
 _POOL_SIZE = 40

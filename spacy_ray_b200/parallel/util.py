@@ -11,7 +11,7 @@ to the last rank, trailing ranks empty if there are fewer groups than ranks.
 from __future__ import annotations
 
 import time
-from typing import Any, Dict, Iterable, List, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 KeyT = Tuple[int, str]
 

@@ -23,7 +23,7 @@ import socket
 import sys
 import time
 from pathlib import Path
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Optional, Sequence
 
 from .config import Config, ConfigValidationError, load_config, parse_config_overrides
 from .utils.logging import logger

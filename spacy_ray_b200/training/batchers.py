@@ -4,7 +4,7 @@ config (``/root/reference/spacy_ray/worker.py:170-175``); the default is
 from __future__ import annotations
 
 import itertools
-from typing import Any, Callable, Iterable, Iterator, List, Optional, Sequence, Union
+from typing import Any, Callable, Iterable, Iterator, List, Optional, Union
 
 from ..config import registry
 

@@ -2,7 +2,6 @@
 equivalent; the reference calls it in every worker, ``worker.py:91``)."""
 from __future__ import annotations
 
-from typing import Any, Dict, Optional
 
 from ..config import Config, registry, resolve_dot_names
 from ..nn.layers import fix_random_seed

@@ -344,6 +344,11 @@ class Worker:
             return
         if set(self.T["frozen_components"]) or set(self.T["annotating_components"]):
             return
+        if int(self.T["accumulate_gradient"]) > 1:
+            # the captured step ends with the exchange + optimizer; micro-batch accumulation needs the
+            # generic path (one proxy.step() per full batch)
+            logger.info("rank %d: generic training path (accumulate_gradient > 1)", self.rank)
+            return
         try:
             from .engine import Trainer
 

@@ -402,7 +402,11 @@ class Trainer:
         g = self._graphs.get(rb)
         if g is None:
             g = self._capture(rb)
+        if hasattr(comm, "_sync_hyper"):
+            comm._sync_hyper()                 # learning-rate schedules: the kernel reads the device copy
         g.replay()
+        if hasattr(comm, "host_bookkeeping"):
+            comm.host_bookkeeping()
         n_ops, n_comm = self._launches_per_replay[rb]
         self.ops.launches += n_ops
         if hasattr(comm, "launches"):

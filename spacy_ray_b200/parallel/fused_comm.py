@@ -164,12 +164,19 @@ class FusedSymmComm:
             float(self.timeout_s), True,
         )
         self.launches += 1
+        if not torch.cuda.is_current_stream_capturing():
+            self.host_bookkeeping()
+
+    def host_bookkeeping(self) -> None:
+        """Host-side mirror of one executed step (update counters used by checkpoints / bias
+        correction on resume, periodic error-flag check).  ``fused_step`` calls it when it runs
+        eagerly; ``engine.Trainer`` calls it after every CUDA-graph replay of a captured step."""
         opt = self.optimizer
-        if opt is not None and hasattr(opt, "nr_update"):
-            for k in t["keys"]:
+        if opt is not None and hasattr(opt, "nr_update") and self.tables is not None:
+            for k in self.tables["keys"]:
                 opt.nr_update[k] = opt.nr_update.get(k, 0) + 1
         self._steps_since_check += 1
-        if self._steps_since_check >= 64 and not torch.cuda.is_current_stream_capturing():
+        if self._steps_since_check >= 64:
             self.check()
 
     def check(self) -> None:

@@ -208,3 +208,36 @@ def test_train_step_reads_each_loss_one_step_late():
     for i in range(1, 6):
         assert lagged[i] == pytest.approx(blocking[i - 1], rel=3e-2), (i, lagged, blocking)
     assert last1 == pytest.approx(blocking[-1], rel=3e-2)
+
+
+def test_learning_rate_changes_reach_the_captured_step():
+    """The fused exchange kernel reads its hyper-parameters from a device tensor; a schedule that
+    changes the learning rate between steps must take effect on CUDA-graph replays too."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.engine import Trainer
+    from spacy_ray_b200.worker import Worker
+
+    text = multi_cfg(["ner"], width=64, depth=2, n_docs=200, max_len=16, hidden=64)
+    w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0, mode="sync", comm="auto")
+    w.set_proxy(None)
+    exs = list(w.train_corpus(w.nlp))
+    tr = Trainer(w.nlp, w.proxy, exs, docs_per_batch=32, dropout=0.0, prefetch=False)
+    ids = np.arange(32)
+    for _ in range(4):                                   # eager first step, capture, replays
+        tr.train_step(ids, lag=0)
+    assert len(tr._graphs) >= 1
+    before = w.proxy.param_flat.clone()
+    tr.train_step(ids, lag=0)
+    torch.cuda.synchronize()
+    assert not torch.equal(before, w.proxy.param_flat)   # still learning
+    w.optimizer.learn_rate = 0.0
+    w.optimizer.L2 = 0.0
+    frozen = w.proxy.param_flat.clone()
+    for _ in range(3):
+        tr.train_step(ids, lag=0)
+    torch.cuda.synchronize()
+    assert torch.equal(frozen, w.proxy.param_flat)       # lr = 0 reached the replayed kernel
+    nr = list(w.optimizer.nr_update.values())
+    assert nr and min(nr) >= 8                           # host-side update counters follow the replays
+    tr.close()

@@ -9,6 +9,19 @@ baseline arm used to quantify what the fusion buys.
 
 There is no silent fallback: constructing ``B200Ops`` without the built
 extension raises (``python -m spacy_ray_b200.build`` builds it in-tree).
+
+What this replaces: the reference itself ships no kernels; under
+``spacy_ray/worker.py:91`` (``init_nlp``) and ``worker.py:254-262`` (``require_gpu``) it runs
+thinc's ``CupyOps`` - NVRTC scalar kernels + cuBLAS fp32 - one launch per op.  Op map:
+K1 ``multi_hash_embed*`` -> ``hash_embed_fwd_kernel`` / ``hash_embed_bwd_sorted_kernel``;
+K2-K5 ``maxout_block*`` -> tcgen05 ``gemm_kernel`` (window, bias, maxout epilogue; dX from the weights
+as stored; split-K dW) + ``maxout_ln_{fwd,bwd}_vec_kernel``; K6 ``softmax_xent`` ->
+``linear_softmax_xent_kernel``; K7 ``transition_steps`` -> ``biluo_steps_kernel`` /
+``arc_eager_steps_kernel``; K8 lives in the fused exchange kernel (``parallel/fused_comm.py``).
+
+Environment switches (all default to the fast path): ``SRB_USE_TC``, ``SRB_TC_DW``,
+``SRB_GEMM_CLUSTER`` (1 / 2 multicast / 3 pair MMA), ``SRB_GEMM_HALO``, ``SRB_DX_BN``,
+``SRB_SIDE_DW``, ``SRB_SORTED_EMBED``.
 """
 from __future__ import annotations
 

@@ -37,3 +37,22 @@ def test_missing_config_is_a_clean_error(tmp_path):
     r = subprocess.run([sys.executable, "-m", "spacy_ray_b200", "ray", "train", str(tmp_path / "nope.cfg")],
                        cwd=ROOT, capture_output=True, text=True, timeout=120)
     assert r.returncode == 1 and "Config" in r.stderr
+
+
+@pytest.mark.slow
+def test_cli_trains_ner_from_jsonl_files(tmp_path):
+    """The reference's example workload shape (bin/get-data.sh -> NER from JSONL): make-data.py writes the
+    files, `spacy.Corpus.v1` reads them through ${paths.*} overrides, checkpoints land in -o."""
+    data = tmp_path / "data"
+    r = subprocess.run([sys.executable, str(ROOT / "bin" / "make-data.py"), str(data), "--n-train", "80", "--n-dev", "20"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = tmp_path / "out"
+    r = subprocess.run(
+        [sys.executable, "-m", "spacy_ray_b200", "ray", "train", str(ROOT / "configs" / "ner_jsonl.cfg"), "-w", "1",
+         "-o", str(out), "--paths.train", str(data / "train.jsonl"), "--paths.dev", str(data / "dev.jsonl"),
+         "--training.max_steps", "4", "--training.eval_frequency", "2"],
+        cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "LOSS NER" in r.stdout and "ENTS_F" in r.stdout
+    assert (out / "model-last" / "ner" / "model").exists()

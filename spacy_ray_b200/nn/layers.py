@@ -156,7 +156,8 @@ def _run_block(
 
 # ---- MultiHashEmbed --------------------------------------------------------
 DEFAULT_ATTRS = ("NORM", "PREFIX", "SUFFIX", "SHAPE")
-ATTR_COLUMNS = {"NORM": 0, "PREFIX": 1, "SUFFIX": 2, "SHAPE": 3, "ORTH": 4, "LOWER": 0}
+# columns of Doc.to_array() / the native featuriser; LOWER aliases NORM (both are the lower-cased form here)
+ATTR_COLUMNS = {"NORM": 0, "PREFIX": 1, "SUFFIX": 2, "SHAPE": 3, "LOWER": 0}
 
 
 def MultiHashEmbed(
@@ -172,6 +173,9 @@ def MultiHashEmbed(
         raise NotImplementedError("static vectors are not supported (no vectors table in this build)")
     if len(attrs) != len(rows):
         raise ValueError("MultiHashEmbed: attrs and rows must have the same length")
+    unknown = [a for a in attrs if a not in ATTR_COLUMNS]
+    if unknown:
+        raise ValueError(f"MultiHashEmbed: unsupported attrs {unknown}; this build featurises {sorted(ATTR_COLUMNS)}")
     seed = 7
     embeds = []
     for attr, nV in zip(attrs, rows):

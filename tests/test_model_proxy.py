@@ -79,3 +79,13 @@ def test_to_from_bytes_roundtrip():
     for na, nb in zip(a.walk(), b.walk()):
         for p in na.param_names:
             assert torch.equal(na.get_param(p), nb.get_param(p))
+
+
+def test_multi_hash_embed_rejects_attrs_the_featuriser_does_not_produce():
+    import pytest
+
+    from spacy_ray_b200.nn.layers import MultiHashEmbed
+
+    MultiHashEmbed(32, attrs=["LOWER", "SHAPE"], rows=[100, 50])
+    with pytest.raises(ValueError, match="unsupported attrs"):
+        MultiHashEmbed(32, attrs=["NORM", "ORTH"], rows=[100, 50])

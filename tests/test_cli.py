@@ -56,3 +56,20 @@ def test_cli_trains_ner_from_jsonl_files(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "LOSS NER" in r.stdout and "ENTS_F" in r.stdout
     assert (out / "model-last" / "ner" / "model").exists()
+
+
+@pytest.mark.slow
+def test_stock_spacy_generated_config_runs_unchanged(tmp_path):
+    """A config as `spacy init config` writes it (tokenizer block, [initialize], augmenter = null, listener +
+    shared tok2vec, batch_by_words with a compounding size, spacy.ConsoleLogger.v1) must train as is."""
+    data = tmp_path / "data"
+    r = subprocess.run([sys.executable, str(ROOT / "bin" / "make-data.py"), str(data), "--n-train", "60", "--n-dev", "15"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run(
+        [sys.executable, "-m", "spacy_ray_b200", "ray", "train", str(ROOT / "configs" / "spacy_default_ner.cfg"), "-w", "2",
+         "--paths.train", str(data / "train.jsonl"), "--paths.dev", str(data / "dev.jsonl"),
+         "--training.max_steps", "4", "--training.eval_frequency", "2"],
+        cwd=ROOT, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "LOSS TOK2VEC" in r.stdout and "LOSS NER" in r.stdout and "ENTS_F" in r.stdout

@@ -240,13 +240,17 @@ class Trainer:
         self.dropout = float(dropout)
         self.B = int(docs_per_batch)
         self.store = ExampleStore(examples, self.heads)
-        why = self.unsupported_reason(nlp, self.store.max_len)
+        # the arc-eager kernel keeps a document's state in shared memory sized for 128 tokens: longer
+        # documents stay in the store but batches containing one are handed back to the generic path
+        self.max_doc_len = 128 if any(k == "parser" for _n, _c, k in self.heads) else None
+        cap_len = self.store.max_len if self.max_doc_len is None else min(self.store.max_len, self.max_doc_len)
+        why = self.unsupported_reason(nlp, cap_len)
         if why is not None:
             raise ValueError(f"pipeline not supported by the device-resident engine: {why}")
         self._doc_index = {id(eg.reference): i for i, eg in enumerate(examples)}
         self.bucket_rows = int(bucket_rows)
-        rows_cap = _align(self.B * self.store.max_len + self.B + 1, self.bucket_rows)
-        self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(self.store.max_len, 64),
+        rows_cap = _align(self.B * cap_len + self.B + 1, self.bucket_rows)
+        self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(cap_len, 64),
                            slots=tuple(self.store.slots), bucket=self.bucket_rows,
                            n_attr=int(self.store.attrs.shape[1]))
         self.host_grouping = os.environ.get("SRB_HOST_GROUP", "1") != "0"
@@ -316,6 +320,9 @@ class Trainer:
 
     def prepare(self, ids: np.ndarray) -> None:
         """Queue the collation of a future batch (returns immediately)."""
+        if self.max_doc_len is not None and len(ids) and int(self.store.lens[ids].max()) > self.max_doc_len:
+            raise ValueError(f"batch contains a document longer than {self.max_doc_len} tokens; "
+                             "use nlp.update (generic path) for it")
         stage = self.stages[self._stage_i]
         self._stage_i = (self._stage_i + 1) % len(self.stages)
         if self._prefetch:
@@ -512,6 +519,8 @@ class Trainer:
                 return None
             out[i] = j
         if self.rows_for(out) > self.lay.rows:
+            return None
+        if self.max_doc_len is not None and int(self.store.lens[out].max(initial=0)) > self.max_doc_len:
             return None
         return out
 

@@ -351,6 +351,8 @@ class Trainer:
         Returns the per-head losses as one small device vector (``loss_names`` order)."""
         tb = self._batch_views(rows)
         gold = self.dv.gold
+        if hasattr(self.proxy, "begin_step"):
+            self.proxy.begin_step(overlap=True)             # buckets are exchanged under the backward pass
         self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
         shared = [c for _n, c, k in self.heads if k == "tok2vec"]
         n_heads = sum(1 for _n, _c, k in self.heads if k != "tok2vec")
@@ -427,6 +429,8 @@ class Trainer:
         comm = self.proxy.comm
         if hasattr(comm, "_sync_hyper"):
             comm._sync_hyper()
+        if hasattr(comm, "reset_gates"):
+            comm.reset_gates()                 # the first consumer of every bucket carries its gate in the graph
         torch.cuda.synchronize(self.device)
         l0, c0 = self.ops.launches, getattr(comm, "launches", 0)
         g = torch.cuda.CUDAGraph()

@@ -92,6 +92,24 @@ class B200Ops(TorchOps):
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
+        # C2: consumer-side gates.  ``FusedSymmComm`` installs itself here; kernels that read
+        # parameters ask it which buckets of freshly exchanged weights they are the first to touch
+        # (``_gate``: descriptor for an in-kernel gate; ``_gate_now``: stand-alone one-warp wait in
+        # front of consumers that have no in-kernel gate).
+        self.gate_provider: Any = None
+
+    def _gate(self, *tensors) -> list:
+        gp = self.gate_provider
+        return gp.gate_for(tensors) if gp is not None else []
+
+    def _gate_now(self, *tensors) -> None:
+        g = self._gate(*tensors)
+        if g:
+            self.k.gate_wait(self.gate_provider.epoch, g)
+            self.launches += 1
+
+    def side_stream_if_pending(self) -> Optional["torch.cuda.Stream"]:
+        return self._side if self._side_pending else None
 
     # ------------------------------------------------------------------ GEMM helpers
     def _tc_ok(self, *dims: int) -> bool:
@@ -99,10 +117,10 @@ class B200Ops(TorchOps):
 
     def tc_gemm(self, A, B, out, *, mode, epi, block_n, M, N, K, a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,),
                 b_col_off=(0,), splits=1, win_w=0, bias=None, which=None, add_src=None, row_scale=None, m_dev=None,
-                max_ctas=0, cluster=None) -> None:
+                max_ctas=0, cluster=None, gate=None) -> None:
         self.k.tc_gemm(A, B, out, mode, epi, block_n, M, N, K, list(a_row_shift), list(a_col_off), list(b_row_off),
                        list(b_col_off), splits, win_w, bias, which, add_src, row_scale, m_dev, max_ctas,
-                       self.gemm_cluster if cluster is None else cluster)
+                       self.gemm_cluster if cluster is None else cluster, gate or [])
         self.launches += 1
 
     @staticmethod
@@ -120,7 +138,7 @@ class B200Ops(TorchOps):
             return None
         out = torch.empty((M, N), dtype=torch.bfloat16, device=X.device)
         self.tc_gemm(X.contiguous(), W.contiguous(), out, mode=MODE_KK, epi=EPI_STORE, block_n=bn, M=M, N=N, K=K,
-                     bias=b)
+                     bias=b, gate=self._gate(W, b))
         return out
 
     def _dw_tc(self, dZ: torch.Tensor, X: torch.Tensor, window: int, out: Optional[torch.Tensor] = None):
@@ -143,7 +161,8 @@ class B200Ops(TorchOps):
     # ------------------------------------------------------------------ K1
     def multi_hash_embed(self, attrs, mask, tables, seeds, columns):
         self.launches += 1
-        return self.k.hash_embed_fwd(attrs, _mask1d(mask), list(tables), list(seeds), list(columns))
+        return self.k.hash_embed_fwd(attrs, _mask1d(mask), list(tables), list(seeds), list(columns),
+                                     self._gate(*tables))
 
     def multi_hash_embed_backward(self, dY, attrs, mask, n_rows, seeds, columns, out=None, perm=None):
         nO = dY.shape[1] // len(n_rows)
@@ -195,11 +214,12 @@ class B200Ops(TorchOps):
             else:
                 shifts = {}
             self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
-                         bias=b.reshape(-1), which=which, **shifts)
+                         bias=b.reshape(-1), which=which, gate=self._gate(W, b, G, beta), **shifts)
             Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed,
                                                        self.seed_dev)
             self.launches += 1
         else:
+            self._gate_now(W, b, G, beta)
             Xw = self.k.seq2col(X) if window else X
             Z = Xw @ W2.t()
             Y, which, xhat, rstd = self.k.maxout_ln_fwd(Z, b.reshape(-1), G, beta, X if residual else None, m1,
@@ -332,6 +352,7 @@ class B200Ops(TorchOps):
         out = self._linear_tc(X, W, b)
         if out is not None:
             return out
+        self._gate_now(W, b)
         Y = X @ W.t()
         return Y + b if b is not None else Y
 
@@ -354,6 +375,7 @@ class B200Ops(TorchOps):
         return torch.softmax(logits.to(torch.float32), dim=-1)
 
     def softmax_xent(self, X, W, b, labels):
+        self._gate_now(W, b)
         X = X.contiguous()
         nC = W.shape[0]
         if X.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and X.shape[1] % 16 == 0 and nC <= 128:
@@ -383,6 +405,7 @@ class B200Ops(TorchOps):
     def transition_steps(self, system, Yf, params, batch, gold, is_train):
         from ..models.transitions import ArcEagerSystem, BiluoSystem
 
+        self._gate_now(params["pad"], params["b"], params["Wu"], params["bu"])
         if isinstance(system, ArcEagerSystem):
             return self._arc_eager_steps(system, Yf, params, batch, gold, is_train)
         if not isinstance(system, BiluoSystem):
@@ -486,6 +509,7 @@ class B200Ops(TorchOps):
 
     # ------------------------------------------------------------------ misc
     def gemm(self, A, B, trans1=False, trans2=False):
+        self._gate_now(A, B)
         a = A.t() if trans1 else A
         b = B.t() if trans2 else B
         return a.to(torch.bfloat16) @ b.to(torch.bfloat16)

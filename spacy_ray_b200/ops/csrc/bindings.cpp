@@ -37,7 +37,7 @@ srb::HashEmbedTables make_tables(const std::vector<Tensor>& tables, const std::v
 }
 
 Tensor hash_embed_fwd(const Tensor& attrs, const Tensor& mask, std::vector<Tensor> tables, std::vector<int64_t> seeds,
-                      std::vector<int64_t> columns) {
+                      std::vector<int64_t> columns, std::vector<int64_t> gate) {
   SRB_CHECK_CUDA(attrs); SRB_CHECK_CUDA(mask);
   TORCH_CHECK(attrs.scalar_type() == at::kLong && mask.scalar_type() == at::kFloat);
   c10::cuda::CUDAGuard guard(attrs.device());
@@ -45,7 +45,8 @@ Tensor hash_embed_fwd(const Tensor& attrs, const Tensor& mask, std::vector<Tenso
   for (size_t a = 0; a < tables.size(); ++a) { SRB_CHECK_CUDA(tables[a]); SRB_CHECK_BF16(tables[a]); t.table[a] = tables[a].data_ptr(); }
   const int Tp = (int)attrs.size(0);
   Tensor out = at::empty({Tp, (int64_t)t.n_tables * t.width}, attrs.options().dtype(at::kBFloat16));
-  srb::launch_hash_embed_fwd(attrs.data_ptr<int64_t>(), mask.data_ptr<float>(), t, out.data_ptr(), Tp, cur_stream());
+  srb::launch_hash_embed_fwd(attrs.data_ptr<int64_t>(), mask.data_ptr<float>(), t, out.data_ptr(), Tp,
+                             srb::make_gate_args(gate.data(), gate.size()), cur_stream());
   return out;
 }
 
@@ -289,7 +290,7 @@ void transition_scatter(const Tensor& d_hid, const Tensor& which, const Tensor& 
 }  // namespace
 
 TORCH_LIBRARY(srb, m) {
-  m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns) -> Tensor");
+  m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns, int[] gate) -> Tensor");
   m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
   m.def("hash_embed_bwd_sorted(Tensor dY, Tensor keys, Tensor perm, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
   m.def("colsum_acc(Tensor X, Tensor(a!) out) -> ()");

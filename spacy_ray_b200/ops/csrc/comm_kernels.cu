@@ -1,46 +1,38 @@
-// C1 + K8 + C2 in ONE kernel: reduce-scatter of the flat gradient bucket over NVLink
-// peer memory, fused with the sharded Adam step (per-tensor clipping, fp32 master) and
-// the all-gather push of the refreshed bf16 weights into every peer's weight buffer.
+// C1 + K8 + C2: the gradient push / parameter pull of the reference as peer-memory kernels.
 //
-// This replaces the reference's per-key Ray RPCs (gradient push proxies.py:104,
-// parameter push proxies.py:75): same bytes, zero host involvement, no NCCL call.
+// The reference ships every gradient tensor to its owner and every updated tensor back to
+// every peer as separate Ray RPCs (gradient push proxies.py:102-104, optimizer on the owner
+// proxies.py:126-128, parameter push proxies.py:71-75).  Here the flat gradient bucket is cut
+// into a few BUCKETS in the order the backward pass completes them, and for every bucket one
+// launch of `fused_bucket_kernel` runs - on a side stream, concurrently with the rest of the
+// backward pass - the whole owner-side pipeline over NVLink peer memory, no NCCL, no host:
 //
-//   phase 0  flag exchange: "my gradients for this epoch are complete"
-//   phase 1  for my shard: g = sum_p peer_grad_p[shard]  (P2P ld.relaxed.sys v4, or one
-//            multimem.ld_reduce through the NVSwitch when a multicast mapping exists)
-//            -> written in place + per-key sum of squares
-//   grid barrier
-//   phase 2  per-key clip, Adam on fp32 master/m1/m2, bf16 weights stored straight into
-//            all W ranks' weight buffers (P2P st v4 / multimem.st), own grads zeroed
-//   phase 3  flag exchange "read done" -> zero the rest of my gradient buffer;
-//            flag exchange "weights of epoch e published" -> (optionally) wait for all.
+//   phase 0  "my gradients of bucket b, epoch e, are complete" -> every rank's signal page;
+//            owners wait for all ranks' flags
+//   phase 1  for my keys of the bucket: g = sum_p peer_grad_p  (one multimem.ld_reduce through the
+//            NVSwitch, or P2P ld.relaxed.sys from every peer), every rank's copy of that extent is
+//            ZEROED in the same pass (multimem.st / P2P st) - the buffers are accumulators and the
+//            next backward pass must find them clear -, g -> local scratch, per-key sum of squares
+//   grid barrier (co-resident CTAs, sense-reversing)
+//   phase 2  per-key clip, Adam / RAdam / SGD on the fp32 master (+ moments, + parameter averages),
+//            bf16 weights stored straight into ALL ranks' weight buffers (multimem.st / P2P st)
+//   grid barrier -> "published (b, me) = e" into every rank's signal page.
+//
+// Nothing waits for the publication here: the first consumer of a bucket's weights in the next
+// forward pass does (gate.cuh; gemm_tcgen05.cu's TMA producer warp, hash_embed_fwd_kernel).
+// The same flag also orders the remote zeroing against the next step's gradient writes: a rank
+// only writes gradients of bucket b after its forward pass consumed bucket b's weights, i.e. after
+// it has seen every owner's published flag, which the owner releases after its zero stores.
 //
 // Every spin has a wall-clock timeout (%globaltimer); on timeout the kernel records an
 // error code and exits instead of hanging the GPU (a dead peer must
 // produce an error, not a hang).
 #include "comm_launch.h"
 #include "common.cuh"
+#include "gate.cuh"
 
 namespace srb {
 
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -48,6 +40,10 @@ __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
                : "l"(p)
                : "memory");
   return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
 }
 __device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* mc) {
   float4 v;
@@ -57,63 +53,80 @@ __device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* mc) {
                : "memory");
   return v;
 }
+__device__ __forceinline__ void multimem_st_v4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void multimem_st_v2_b32(void* mc, uint32_t a, uint32_t b) {
   asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(a)),
                "f"(__uint_as_float(b))
                : "memory");
 }
-
-// Spin until *flag >= target (system scope).  Returns false on timeout.
-__device__ __forceinline__ bool wait_flag_sys(const uint32_t* flag, uint32_t target, uint64_t timeout_ns) {
-  const uint64_t t0 = globaltimer_ns();
-  while ((int32_t)(ld_acquire_sys(flag) - target) < 0) {
-    if (globaltimer_ns() - t0 > timeout_ns) return false;
-    __nanosleep(64);
-  }
-  return true;
+// A zero vector that the compiler cannot hoist above the load that produced `v`: the store that
+// clears a gradient word must not be issued before the (switch-side) read of that word returned.
+__device__ __forceinline__ float4 zero_after(const float4& v) {
+  uint32_t z;
+  asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_uint(v.x)));
+  const float f = __uint_as_float(z);
+  return make_float4(f, f, f, f);
 }
 
-// Device-scope barrier across the (co-resident) CTAs of this kernel.
-__device__ __forceinline__ bool grid_barrier(uint32_t* counter, uint32_t target, uint64_t timeout_ns) {
+// Sense-reversing barrier across the (co-resident) CTAs of one launch.  state[0] = arrivals,
+// state[1] = generation.  Returns false on timeout.
+__device__ __forceinline__ bool grid_barrier(uint32_t* state, uint64_t timeout_ns) {
   __syncthreads();
   bool ok = true;
   if (threadIdx.x == 0) {
+    const uint32_t gen = ld_acquire_gpu(state + 1);
     __threadfence();
-    atomicAdd(counter, 1u);
-    const uint64_t t0 = globaltimer_ns();
-    while ((int32_t)(ld_acquire_gpu(counter) - target) < 0) {
-      if (globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+    if (atomicAdd(state, 1u) == gridDim.x - 1) {
+      state[0] = 0u;
+      __threadfence();
+      st_release_gpu(state + 1, gen + 1u);
+    } else {
+      const uint64_t t0 = globaltimer_ns();
+      while (ld_acquire_gpu(state + 1) == gen) {
+        if (globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+      }
     }
   }
   __syncthreads();
   return ok;
 }
 
-__global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs a) {
-  const int W = a.world, rank = a.rank;
-  const uint32_t epoch = *a.epoch + 1;                     // flag value for this invocation
+__global__ void __launch_bounds__(256, 2) fused_bucket_kernel(FusedCommArgs a) {
+  const int W = a.world, rank = a.rank, bkt = a.bucket;
+  const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
   const uint64_t tmo = a.timeout_ns;
+  const int n_items = a.blk_end - a.blk_begin;
   __shared__ int s_fail;
   __shared__ float s_part[8];
   if (threadIdx.x == 0) s_fail = 0;
   __syncthreads();
 
-  // ---------------- phase 0: gradients of every rank are complete -----------------------
-  if (blockIdx.x == 0 && threadIdx.x < W) {
-    __threadfence_system();
-    st_release_sys(a.signal[threadIdx.x] + kSlotGrad * kMaxWorld + rank, epoch);
+  // ---------------- phase 0: every rank's gradients of this bucket are complete --------------
+  if (W > 1) {
+    if (blockIdx.x == 0 && threadIdx.x < W) {
+      __threadfence_system();
+      st_release_sys(a.signal[threadIdx.x] + flag_grad_idx(bkt, rank), epoch);
+    }
+    if (n_items > 0 && threadIdx.x < W) {
+      if (!wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, threadIdx.x), epoch, tmo)) s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 1); return; }
   }
-  if (threadIdx.x < W) {
-    if (!wait_flag_sys(a.signal[rank] + kSlotGrad * kMaxWorld + threadIdx.x, epoch, tmo)) s_fail = 1;
-  }
-  __syncthreads();
-  if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 1); return; }
 
   const int64_t s0 = a.shard_start;
   float* my_grad = a.grad[rank];
+  const float lr = a.hyper[0], b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], clip = a.hyper[4], l2 = a.hyper[5];
+  const bool wd = a.hyper[6] != 0.f;
   const float gs = a.hyper[7];
-  // ---------------- phase 1: reduce my shard, per-key sum of squares ---------------------
-  for (int b = blockIdx.x; b < a.n_blocks; b += gridDim.x) {
+  const bool l2_in_grad = (l2 != 0.f) && !wd;
+  const bool keep_red = (W > 1) || gs != 1.f || l2_in_grad;       // otherwise phase 2 re-reads the gradient itself
+  // ---------------- phase 1: reduce my keys, clear every copy, per-key sum of squares --------
+  for (int b = a.blk_begin + blockIdx.x; b < a.blk_end; b += gridDim.x) {
     const int k = a.blk_key[b];
     const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
     const int64_t end = a.key_off[k] + a.key_len[k];
@@ -126,25 +139,38 @@ __global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs 
       const int64_t t0 = base + threadIdx.x * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) { ok[j] = (t0 + j * 1024) < end; s[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      if (a.grad_mc) {
+      if (W == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = *(const float4*)(my_grad + s0 + t0 + j * 1024);
+      } else if (a.grad_mc) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = multimem_ld_reduce_v4(a.grad_mc + s0 + t0 + j * 1024);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ok[j]) multimem_st_v4(a.grad_mc + s0 + t0 + j * 1024, zero_after(s[j]));
       } else {
 #pragma unroll 2
         for (int p = 0; p < W; ++p) {
-          const float* src = a.grad[(rank + p) % W] + s0 + t0;      // stagger peers across ranks
+          float* src = a.grad[(rank + p) % W] + s0 + t0;            // stagger peers across ranks
           float4 v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) if (ok[j]) v[j] = ld_relaxed_sys_v4(src + j * 1024);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (ok[j]) { s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w; }
+          for (int j = 0; j < 4; ++j) if (ok[j]) {
+            s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w;
+            st_relaxed_sys_v4(src + j * 1024, zero_after(v[j]));
+          }
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (ok[j]) {
+          const int64_t idx = t0 + j * 1024;
           s[j].x *= gs; s[j].y *= gs; s[j].z *= gs; s[j].w *= gs;
-          *(float4*)(my_grad + s0 + t0 + j * 1024) = s[j];
+          if (l2_in_grad) {                       // thinc: L2 joins the gradient BEFORE the clip norm
+            const float4 w4 = *(const float4*)(a.master + idx);
+            s[j].x += l2 * w4.x; s[j].y += l2 * w4.y; s[j].z += l2 * w4.z; s[j].w += l2 * w4.w;
+          }
+          if (keep_red) *(float4*)(a.red + idx) = s[j];
           acc += s[j].x * s[j].x + s[j].y * s[j].y + s[j].z * s[j].z + s[j].w * s[j].w;
         }
       }
@@ -160,19 +186,27 @@ __global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs 
     }
     __syncthreads();
   }
-  // everyone has finished READING peers' gradient buffers -> they may be zeroed
-  const uint32_t bar_base = (epoch - 1) * 3u * gridDim.x;
-  if (!grid_barrier(a.bar_counter, bar_base + gridDim.x, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
-  if (blockIdx.x == 0 && threadIdx.x < W)
-    st_release_sys(a.signal[threadIdx.x] + kSlotRead * kMaxWorld + rank, epoch);
+  uint32_t* bar = a.bar + 2 * bkt;
+  if (n_items > 0) {
+    if (!grid_barrier(bar, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
+  }
 
-  // ---------------- phase 2: clip + Adam + publish bf16 weights to all ranks -------------
-  const float lr = a.hyper[0], b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], clip = a.hyper[4], l2 = a.hyper[5];
-  const bool wd = a.hyper[6] != 0.f;
-  const float t = (float)(*a.step + 1);
-  const float fix1 = 1.f - powf(b1, t), fix2 = 1.f - powf(b2, t);
-  const float lr_t = lr * sqrtf(fix2) / fix1;
-  for (int b = blockIdx.x; b < a.n_blocks; b += gridDim.x) {
+  // ---------------- phase 2: clip + optimizer + publish bf16 weights to all ranks ------------
+  const float t = (float)(*(const volatile int32_t*)a.step + 1);
+  const float b1t = powf(b1, t), b2t = powf(b2, t);
+  const float fix1 = 1.f - b1t, fix2 = 1.f - b2t;
+  float lr_t = lr * sqrtf(fix2) / fix1;                    // Adam: bias correction folded into the rate
+  bool rect = true;
+  if (a.opt_mode == kOptRAdam) {
+    const float sma_max = 2.f / (1.f - b2) - 1.f;
+    const float sma = sma_max - 2.f * t * b2t / fix2;
+    rect = sma >= 5.f;
+    lr_t = rect ? lr * sqrtf(fix2 * (sma - 4.f) / (sma_max - 4.f) * (sma - 2.f) / sma * sma_max / (sma_max - 2.f)) / fix1
+                : lr / fix1;
+  }
+  // thinc's update_averages: decay = min((1 + t) / (10 + t), 0.9999); ema -= (1 - decay) * (ema - w)
+  const float avg_mix = 1.f - fminf((1.f + t) / (10.f + t), 0.9999f);
+  for (int b = a.blk_begin + blockIdx.x; b < a.blk_end; b += gridDim.x) {
     const int k = a.blk_key[b];
     const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
     const int64_t end = a.key_off[k] + a.key_len[k];
@@ -184,17 +218,21 @@ __global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs 
     {
       // loads for all 4 vectors of this thread first (16 independent 16-byte loads in flight)
       const int64_t t0 = base + threadIdx.x * 4;
-      float4 g4[4], w4[4], a4[4], b4[4];
+      const float* gsrc = keep_red ? a.red : (my_grad + s0);
+      float4 g4[4], w4[4], a4[4], b4[4], e4[4];
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t idx = t0 + j * 1024;
         ok[j] = idx < end;
         if (ok[j]) {
-          g4[j] = *(const float4*)(my_grad + s0 + idx);
+          g4[j] = *(const float4*)(gsrc + idx);
           w4[j] = *(const float4*)(a.master + idx);
-          a4[j] = *(const float4*)(a.m1 + idx);
-          b4[j] = *(const float4*)(a.m2 + idx);
+          if (a.opt_mode != kOptSGD) {
+            a4[j] = *(const float4*)(a.m1 + idx);
+            b4[j] = *(const float4*)(a.m2 + idx);
+          }
+          if (a.avg) e4[j] = *(const float4*)(a.avg + idx);
         }
       }
 #pragma unroll
@@ -205,18 +243,29 @@ __global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs 
         float av[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w}, bv[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float x = gv[e];
-          if (l2 != 0.f && !wd) x += l2 * wv[e];
-          x *= scale;
-          av[e] = b1 * av[e] + (1.f - b1) * x;
-          bv[e] = b2 * bv[e] + (1.f - b2) * x * x;
-          wv[e] -= lr_t * av[e] / (sqrtf(bv[e]) + eps);
+          const float x = gv[e] * scale;
+          if (a.opt_mode == kOptSGD) {
+            wv[e] -= lr * x;
+          } else {
+            av[e] = b1 * av[e] + (1.f - b1) * x;
+            bv[e] = b2 * bv[e] + (1.f - b2) * x * x;
+            if (rect) wv[e] -= lr_t * av[e] / (sqrtf(bv[e]) + eps);
+            else wv[e] -= lr_t * av[e];
+          }
           if (wd && l2 != 0.f) wv[e] *= (1.f - lr * l2);
         }
         *(float4*)(a.master + idx) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        *(float4*)(a.m1 + idx) = make_float4(av[0], av[1], av[2], av[3]);
-        *(float4*)(a.m2 + idx) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-        *(float4*)(my_grad + s0 + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.opt_mode != kOptSGD) {
+          *(float4*)(a.m1 + idx) = make_float4(av[0], av[1], av[2], av[3]);
+          *(float4*)(a.m2 + idx) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        }
+        if (a.avg) {
+          float ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ev[e] -= avg_mix * (ev[e] - wv[e]);
+          *(float4*)(a.avg + idx) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+        }
+        if (W == 1) *(float4*)(my_grad + s0 + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
         __nv_bfloat162 lo = __floats2bfloat162_rn(wv[0], wv[1]);
         __nv_bfloat162 hi = __floats2bfloat162_rn(wv[2], wv[3]);
         const uint32_t ulo = *(uint32_t*)&lo, uhi = *(uint32_t*)&hi;
@@ -232,41 +281,51 @@ __global__ void __launch_bounds__(256, 2) fused_rs_adam_ag_kernel(FusedCommArgs 
       }
     }
   }
-  __threadfence_system();
-  if (!grid_barrier(a.bar_counter, bar_base + 2u * gridDim.x, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 3); return; }
-  if (blockIdx.x == 0 && threadIdx.x < W)
-    st_release_sys(a.signal[threadIdx.x] + kSlotParam * kMaxWorld + rank, epoch);
-
-  // ---------------- phase 3: zero the peers' shards of my gradient buffer ----------------
-  if (threadIdx.x < W) {
-    if (!wait_flag_sys(a.signal[rank] + kSlotRead * kMaxWorld + threadIdx.x, epoch, tmo)) s_fail = 1;
+  if (n_items > 0) {
+    __threadfence_system();
+    if (!grid_barrier(bar, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 3); return; }
   }
-  __syncthreads();
-  if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 4); return; }
-  {
-    const int64_t total4 = a.total_elems / 4;
-    const int64_t lo4 = s0 / 4, hi4 = (s0 + a.shard_cap) / 4;
-    float4* g4 = (float4*)my_grad;
-    for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256)
-      if (i < lo4 || i >= hi4) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // padding of my own shard beyond the owned keys is never written, stays zero
-  }
-  for (int k = blockIdx.x * 256 + threadIdx.x; k < a.n_keys; k += gridDim.x * 256) a.norms_sq[k] = 0.f;
-  // ---------------- all weights of this epoch have landed here ---------------------------
-  if (a.wait_params) {
-    if (threadIdx.x < W) {
-      if (!wait_flag_sys(a.signal[rank] + kSlotParam * kMaxWorld + threadIdx.x, epoch, tmo)) s_fail = 1;
+  // ---------------- published: the first consumer of these weights on each rank waits for this
+  if (blockIdx.x == 0) {
+    if (W > 1 && threadIdx.x < W) {
+      __threadfence_system();
+      st_release_sys(a.signal[threadIdx.x] + flag_pub_idx(bkt, rank), epoch);
     }
-    __syncthreads();
-    if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 5); return; }
+    for (int k = a.key_begin + (int)threadIdx.x; k < a.key_end; k += blockDim.x) a.norms_sq[k] = 0.f;
+    if (a.last && threadIdx.x == 0) {
+      *a.step = *(const volatile int32_t*)a.step + 1;
+      __threadfence();
+      *(volatile uint32_t*)a.epoch = epoch;
+    }
   }
-  if (!grid_barrier(a.bar_counter, bar_base + 3u * gridDim.x, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 6); return; }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *a.epoch = epoch; *a.step = *a.step + 1; }
 }
 
-cudaError_t launch_fused_rs_adam_ag(const FusedCommArgs& a, int grid, cudaStream_t s) {
-  fused_rs_adam_ag_kernel<<<grid, 256, 0, s>>>(a);
+cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s) {
+  fused_bucket_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();
+}
+
+// Stand-alone gate for consumers that have no in-kernel gate (library GEMM fallbacks, host reads).
+__global__ void gate_wait_kernel(GateArgs g) { gate_wait_warp(g); }
+cudaError_t launch_gate_wait(const GateArgs& g, cudaStream_t s) {
+  gate_wait_kernel<<<1, 32, 0, s>>>(g);
+  return cudaGetLastError();
+}
+
+// Device-scope barrier on a monotonic counter (stand-alone collectives below).
+__device__ __forceinline__ bool grid_barrier_counter(uint32_t* counter, uint32_t target, uint64_t timeout_ns) {
+  __syncthreads();
+  bool ok = true;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_gpu(counter) - target) < 0) {
+      if (globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+    }
+  }
+  __syncthreads();
+  return ok;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -312,7 +371,7 @@ __global__ void __launch_bounds__(256, 2) p2p_reduce_scatter_kernel(P2PCollArgs 
     for (int j = 0; j < 4; ++j) if (ok[j]) *(float4*)((float*)a.out + (i0 + j * stride) * 4) = acc[j];
   }
   const uint32_t bar_base = (epoch - 1) * gridDim.x;
-  if (!grid_barrier(a.bar_counter, bar_base + gridDim.x, a.timeout_ns)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
+  if (!grid_barrier_counter(a.bar_counter, bar_base + gridDim.x, a.timeout_ns)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
   // peers may only overwrite their buffers once everyone has read: exchange read-done flags
   if (blockIdx.x == 0 && threadIdx.x < W)
     st_release_sys(a.signal[threadIdx.x] + kSlotRead * kMaxWorld + rank, epoch);
@@ -345,7 +404,7 @@ __global__ void __launch_bounds__(256, 1) p2p_all_gather_kernel(P2PCollArgs a) {
   }
   __threadfence_system();
   const uint32_t bar_base = (epoch - 1) * gridDim.x;
-  if (!grid_barrier(a.bar_counter, bar_base + gridDim.x, a.timeout_ns)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
+  if (!grid_barrier_counter(a.bar_counter, bar_base + gridDim.x, a.timeout_ns)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
   if (blockIdx.x == 0) {
     if (threadIdx.x < W) st_release_sys(a.signal[threadIdx.x] + kSlotParam * kMaxWorld + rank, epoch);
     if (threadIdx.x < W && !wait_flag_sys(a.signal[rank] + kSlotParam * kMaxWorld + threadIdx.x, epoch, a.timeout_ns)) s_fail = 1;

@@ -1,6 +1,7 @@
 // Fused non-GEMM kernels of the tok2vec / tagger hot path.
 // Each one replaces a chain of thinc/cupy launches with a single pass over HBM.
 #include "common.cuh"
+#include "gate.cuh"
 #include "kernels.h"
 
 namespace srb {
@@ -10,10 +11,17 @@ namespace srb {
 // =====================================================================================
 __global__ void __launch_bounds__(256) hash_embed_fwd_kernel(const int64_t* __restrict__ attrs,
                                                              const float* __restrict__ mask, HashEmbedTables t,
-                                                             __nv_bfloat16* __restrict__ out, int Tp) {
+                                                             __nv_bfloat16* __restrict__ out, int Tp,
+                                                             GateArgs gate) {
   const int row = blockIdx.x;
   const int C = t.n_tables * t.width;
   const bool live = mask[row] != 0.0f;
+  if (gate.flags != nullptr) {
+    // C2: the embedding tables are the first weights the forward pass reads and the last the exchange
+    // publishes; wait for their owners' "published" flags here instead of at the end of the last step
+    if (threadIdx.x < 32) gate_wait_warp(gate);
+    __syncthreads();
+  }
   for (int v = threadIdx.x; v < C / 8; v += blockDim.x) {
     const int col = v * 8;
     const int a = col / t.width;
@@ -42,11 +50,11 @@ __global__ void __launch_bounds__(256) hash_embed_fwd_kernel(const int64_t* __re
 }
 
 void launch_hash_embed_fwd(const int64_t* attrs, const float* mask, HashEmbedTables t, void* out, int Tp,
-                           cudaStream_t s) {
+                           const GateArgs& gate, cudaStream_t s) {
   if (Tp <= 0) return;
   int C = t.n_tables * t.width;
   int threads = C / 8 < 256 ? ((C / 8 + 31) / 32) * 32 : 256;
-  hash_embed_fwd_kernel<<<Tp, threads, 0, s>>>(attrs, mask, t, (__nv_bfloat16*)out, Tp);
+  hash_embed_fwd_kernel<<<Tp, threads, 0, s>>>(attrs, mask, t, (__nv_bfloat16*)out, Tp, gate);
 }
 
 // K1 backward: scatter-add into the fp32 table gradients.

@@ -28,7 +28,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
              std::vector<int64_t> b_row_off, std::vector<int64_t> b_col_off, int64_t splits, int64_t win_w,
              const c10::optional<Tensor>& bias, const c10::optional<Tensor>& which,
              const c10::optional<Tensor>& add_src, const c10::optional<Tensor>& row_scale,
-             const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster) {
+             const c10::optional<Tensor>& m_dev, int64_t max_ctas, int64_t cluster, std::vector<int64_t> gate) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && out.is_cuda());
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && B.scalar_type() == at::kBFloat16, "tc_gemm: bf16 operands");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "tc_gemm: row-major 2D operands");
@@ -95,6 +95,7 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   p.add_src = add_src.has_value() && add_src->defined() ? (const __nv_bfloat16*)add_src->data_ptr() : nullptr;
   p.ld_add = p.add_src ? (int)add_src->stride(0) : 0;
   p.row_scale = row_scale.has_value() && row_scale->defined() ? row_scale->data_ptr<float>() : nullptr;
+  p.gate = make_gate_args(gate.data(), gate.size());
   int sms = num_sms_for(A.get_device());
   if (max_ctas > 0 && max_ctas < sms) sms = (int)max_ctas;
   cudaError_t e = launch_gemm(ta, tb, p, (int)block_n, (int)mode, (int)epi, (int)cluster, sms,
@@ -109,7 +110,8 @@ void register_gemm_ops(torch::Library& m) {
   m.def(
       "tc_gemm(Tensor A, Tensor B, Tensor(a!) out, int mode, int epi, int block_n, int M, int N, int K, "
       "int[] a_row_shift, int[] a_col_off, int[] b_row_off, int[] b_col_off, int splits, int win_w, "
-      "Tensor? bias, Tensor? which, Tensor? add_src, Tensor? row_scale, Tensor? m_dev, int max_ctas, int cluster) -> ()");
+      "Tensor? bias, Tensor? which, Tensor? add_src, Tensor? row_scale, Tensor? m_dev, int max_ctas, int cluster, "
+      "int[] gate) -> ()");
 }
 void register_gemm_impls(torch::Library& m) { m.impl("tc_gemm", tc_gemm); }
 

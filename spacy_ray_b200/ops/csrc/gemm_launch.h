@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "comm_launch.h"
+
 namespace srb {
 
 // MODE_KK:   A (M,K) and B (N,K) both K-major ("NT")           - forward / plain linear
@@ -32,6 +34,9 @@ struct GemmParams {
   const __nv_bfloat16* add_src;     // STORE: optional out += row_scale[row] * add_src[row, n]
   const float* row_scale;
   int ld_add;
+  // C2: optional consumer-side gate on the "published" flags of the buckets that hold B (the weights)
+  // and the bias: the TMA producer warp waits for them right before its first load (gate.cuh)
+  GateArgs gate;
 };
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,

@@ -17,6 +17,7 @@
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).
 #include "common.cuh"
+#include "gate.cuh"
 #include "gemm_launch.h"
 #include "gemm_tcgen05.cuh"
 
@@ -101,9 +102,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int item_stride = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    // C2: the all-gather's consumer side.  The owners of this layer's weights pushed them into my
+    // weight buffer from inside their exchange kernels; wait for their "published" flags here, while
+    // warp 1 initialises barriers and allocates TMEM, instead of at the end of the previous step.
+    gate_wait_warp(p.gate);
   }
   if (warp == 1 && lane == 0) {
     // PAIR: one MMA issuer (the leader) frees a stage in both CTAs; its tmem_empty barrier
@@ -113,13 +120,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr); else tmem_alloc<C::kTmemCols>(tmem_ptr); }
-  if (p.bias && warp >= 2) {                     // bias -> smem (fp32) once per CTA
+  if (p.bias && warp >= 2 && p.gate.flags == nullptr) {      // bias -> smem (fp32) once per CTA
     for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (p.gate.flags != nullptr) {
+    // gated launch: the bias is part of the freshly published bucket, read it only now (after the
+    // gate + barrier above), then sync the epilogue warps among themselves
+    if (warp == 0) fence_proxy_async_global();               // peers' generic-proxy stores -> my TMA loads
+    if (p.bias && warp >= 2) {
+      for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kNumThreads - 64) : "memory");
+    }
+  }
 
   if (warp == 0) {
     // ================================ TMA producer =====================================

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "comm_launch.h"
+
 namespace srb {
 
 struct HashEmbedTables {
@@ -21,7 +23,7 @@ struct HashEmbedTables {
 // K1: fused hashing + 4-row gather-sum for all tables, written straight into the
 // concat layout. out: bf16 (Tp, n_tables*width).
 void launch_hash_embed_fwd(const int64_t* attrs, const float* mask, HashEmbedTables t, void* out, int Tp,
-                           cudaStream_t s);
+                           const GateArgs& gate, cudaStream_t s);
 // K1 backward: dE_a[rows] += mask * dY[:, a-block]  (fp32 atomics).
 void launch_hash_embed_bwd(const int64_t* attrs, const float* mask, HashEmbedTables t, const void* dY, int Tp,
                            cudaStream_t s);

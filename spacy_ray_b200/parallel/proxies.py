@@ -144,6 +144,20 @@ class PeerProxy:
                 self._grads[key] = None
                 self._grad_counts[key] = 0
 
+    def load_param(self, id: int, name: str, value: torch.Tensor, version: int) -> None:
+        """Resume: adopt ``value`` for ``key`` on THIS rank whether or not it owns the key, at an
+        explicit ``version``.  Every rank loads the same checkpoint with the same version, so the
+        replicas agree and the owners' version gates (``check_version``) accept the peers' first
+        gradients - ``set_param`` alone ignores non-owned keys that already exist (reference
+        ``proxies.py:62-69``), which left resumed peers on their random initialisation."""
+        key = make_key(id, name)
+        with self._lock:
+            self._params[key] = self._to_local(value, self._params.get(key))
+            self._versions[key] = int(version)
+            self._grads[key] = None
+            self._grad_counts[key] = 0
+            self._next_params.pop(key, None)
+
     def get_param(self, id: int, name: str) -> torch.Tensor:
         key = make_key(id, name)
         with self._lock:

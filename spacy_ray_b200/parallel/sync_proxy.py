@@ -28,7 +28,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from ..ops import get_current_ops
-from .util import KeyT, divide_params, divide_params_balanced, make_key
+from .util import DIVIDERS, KeyT, make_key
 
 ALIGN = 128  # elements; keeps every key 256 B (bf16) / 512 B (fp32) aligned for TMA + vector loads
 
@@ -66,8 +66,11 @@ class FlatLayout:
     @classmethod
     def build(cls, components: Sequence[Tuple[str, Any]], world_size: int, *, balance: str = "nodes") -> "FlatLayout":
         """``components``: ``[(name, model)]``.  ``balance``: ``"nodes"`` = the
-        reference partition, ``"bytes"`` = byte-balanced contiguous partition."""
-        divide = divide_params if balance == "nodes" else divide_params_balanced
+        reference partition, ``"bytes"`` = byte-balanced contiguous partition, ``"lpt"`` = greedy
+        largest-first assignment (what the fused exchange uses by default)."""
+        if balance not in DIVIDERS:
+            raise ValueError(f"Unknown shard balance {balance!r} (expected one of {sorted(DIVIDERS)})")
+        divide = DIVIDERS[balance]
         per_rank: List[List[KeyT]] = [[] for _ in range(world_size)]
         shapes: Dict[KeyT, Tuple[int, ...]] = {}
         seen = set()
@@ -216,6 +219,10 @@ class ShardedSyncProxy:
         self.n_grads_discarded = 0
         self.other_workers: list = []
         self._grad_counts: Dict[KeyT, int] = {}
+        self._grad_order: List[KeyT] = []           # gradient-completion order of the first step(s)
+        self._order_taken = not hasattr(self.comm, "set_order")
+        self._hook = getattr(self.comm, "key_ready", None)
+        self._in_step = False
 
     # ---- ParamServer-facing ------------------------------------------------
     def set_param(self, id: int, name: str, value: torch.Tensor) -> None:
@@ -238,6 +245,10 @@ class ShardedSyncProxy:
         if value.data_ptr() != view.data_ptr():          # kernels may have written in place
             view.add_(value.reshape(view.shape))
         self._grad_counts[key] = self._grad_counts.get(key, 0) + 1
+        if not self._order_taken:
+            self._grad_order.append(key)
+        if self._hook is not None:
+            self._hook(key, self)                        # a completed bucket starts its exchange right away
 
     def set_grad(self, id: int, name: str, value: torch.Tensor) -> None:
         key = make_key(id, name)
@@ -267,8 +278,39 @@ class ShardedSyncProxy:
         return 1.0 if self.n_grads_used else None
 
     # ---- the step --------------------------------------------------------------
+    def begin_step(self, overlap: bool = True) -> None:
+        """Optional: announce the start of a step's backward pass.  With ``overlap`` (and a comm
+        backend that supports it) each gradient bucket is exchanged as soon as its last ``inc_grad``
+        arrives, concurrently with the rest of the backward pass; ``step()`` then only launches
+        what is left and joins.  Without the call, ``step()`` exchanges everything at the end."""
+        begin = getattr(self.comm, "begin_step", None)
+        if begin is not None:
+            begin(self, overlap)
+        self._in_step = True
+
+    def take_grad_order(self) -> List[KeyT]:
+        """The order in which this step's gradients were completed (first occurrence per key)."""
+        self._order_taken = True
+        seen, out = set(), []
+        for k in self._grad_order:
+            if k not in seen:
+                seen.add(k)
+                out.append(k)
+        self._grad_order = []
+        return out
+
+    def quiesce(self) -> None:
+        """Make the current stream wait until every peer's weights of the last exchange have landed
+        (consumers normally do this themselves, kernel by kernel: ``ops/csrc/gate.cuh``)."""
+        q = getattr(self.comm, "quiesce", None)
+        if q is not None:
+            q()
+
     def step(self) -> None:
         """Gradient exchange + sharded optimizer + weight publication."""
+        if not self._in_step:
+            self.begin_step(overlap=False)
+        self._in_step = False
         join = getattr(get_current_ops(), "join_side", None)
         if join is not None:
             join()            # gradient GEMMs the backend ran on a side stream write into grad_flat

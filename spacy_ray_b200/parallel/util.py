@@ -83,6 +83,35 @@ def divide_params_balanced(model, num_workers: int) -> List[List[KeyT]]:
     return shares
 
 
+def divide_params_lpt(model, num_workers: int) -> List[List[KeyT]]:
+    """Longest-processing-time assignment of node groups to ranks: groups sorted by size,
+    each handed to the currently lightest rank (ties -> lowest rank; deterministic, so every
+    rank derives the same map).  Not contiguous in walk order, but the flat layout is
+    owner-major anyway; the heaviest rank ends up at max(largest tensor, ~mean)."""
+    groups = _key_groups(model)
+    by_key = {}
+    for node in model.walk():
+        for name in node.param_names:
+            if node.has_param(name):
+                by_key[make_key(node.id, name)] = int(node.get_param(name).numel())
+    sized = [(sum(by_key.get(k, 0) for k in g), i, g) for i, g in enumerate(groups)]
+    sized.sort(key=lambda t: (-t[0], t[1]))
+    load = [0] * num_workers
+    picked: List[List[int]] = [[] for _ in range(num_workers)]
+    for size, i, _g in sized:
+        r = min(range(num_workers), key=lambda j: (load[j], j))
+        load[r] += size
+        picked[r].append(i)
+    shares: List[List[KeyT]] = [[] for _ in range(num_workers)]
+    for r in range(num_workers):
+        for i in sorted(picked[r]):                # keep walk order inside a rank
+            shares[r].extend(groups[i])
+    return shares
+
+
+DIVIDERS = {"nodes": divide_params, "bytes": divide_params_balanced, "lpt": divide_params_lpt}
+
+
 def set_params_proxy(model, proxy) -> None:
     """Install ``proxy`` on every node of ``model``: existing parameter values
     are handed to ``proxy.set_param`` first, then the node's ``ParamServer``

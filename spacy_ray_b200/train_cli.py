@@ -7,7 +7,7 @@ including dotted config overrides from leftover args (``:44``) and loading the
 config un-interpolated (``:46``).  Unlike the reference, ``--output`` is wired
 (``:41`` is a TODO there).  Extra flags select the data plane:
 ``--mode sync|async``, ``--comm auto|dist|fused``, ``--quorum K``,
-``--shard-balance nodes|bytes``, ``--resume PATH``.
+``--shard-balance auto|nodes|bytes|lpt``, ``--resume PATH``.
 
 ``ray_train(config, *, ray_address, num_workers, use_gpu, code_path)`` keeps the
 reference's Python signature (``:56-63``) and control flow (create workers ->
@@ -80,7 +80,7 @@ def _add_train_args(p: argparse.ArgumentParser) -> None:
                    help="sync = flat-bucket reduce-scatter/Adam/all-gather per step; async = reference peer-proxy protocol")
     p.add_argument("--comm", choices=["auto", "dist", "fused", "local"], default="auto")
     p.add_argument("--quorum", type=int, default=None, help="async mode: gradients per update (reference default 2)")
-    p.add_argument("--shard-balance", choices=["nodes", "bytes"], default="nodes")
+    p.add_argument("--shard-balance", choices=["auto", "nodes", "bytes", "lpt"], default="auto")
     p.add_argument("--resume", dest="resume_path", type=Path, default=None, help="Checkpoint dir to resume from")
     p.add_argument("--no-shard-data", dest="shard_data", action="store_false",
                    help="Give every rank the full corpus (reference behaviour)")
@@ -137,7 +137,7 @@ def ray_train(
     mode: str = "sync",
     comm: str = "auto",
     quorum: Optional[int] = None,
-    shard_balance: str = "nodes",
+    shard_balance: str = "auto",
     resume_path: Optional[Path] = None,
     shard_data: bool = True,
     inject_fault: Optional[str] = None,

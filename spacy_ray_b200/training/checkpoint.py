@@ -34,7 +34,9 @@ def structural_keys(nlp) -> Dict[KeyT, Tuple[str, int, str]]:
 
 
 def save_optimizer_shard(path: Path, nlp, optimizer, owned_keys: Iterable[KeyT], *, rank: int, world_size: int,
-                         extra: Optional[Dict[str, Any]] = None) -> Path:
+                         extra: Optional[Dict[str, Any]] = None, master: Optional[Dict[KeyT, torch.Tensor]] = None) -> Path:
+    """``master``: fp32 master weights of the owned keys when the model weights are kept in lower
+    precision (bf16) - without them a resumed run would restart from bf16-rounded weights."""
     path = Path(path) / "optim"
     path.mkdir(parents=True, exist_ok=True)
     skeys = structural_keys(nlp)
@@ -43,51 +45,83 @@ def save_optimizer_shard(path: Path, nlp, optimizer, owned_keys: Iterable[KeyT],
     def conv(d):
         return None if d is None else {skeys[k]: v for k, v in d.items() if k in skeys}
 
+    own = set(owned_keys)
+    mstate = dict(state.get("master") or {})
+    if master:
+        mstate.update({k: v.detach().to("cpu", torch.float32) for k, v in master.items() if k in own})
     blob = {
         "rank": rank, "world_size": world_size,
         "mom1": conv(state["mom1"]), "mom2": conv(state["mom2"]), "nr_update": conv(state["nr_update"]),
-        "averages": conv(state["averages"]), "step": state["step"], "hyper": state["hyper"],
+        "averages": conv(state["averages"]), "master": conv(mstate), "step": state["step"], "hyper": state["hyper"],
         "extra": extra or {},
     }
     out = path / f"rank{rank}-of{world_size}.pt"
-    torch.save(blob, out)
+    tmp = path / f".rank{rank}-of{world_size}.pt.tmp"
+    torch.save(blob, tmp)
+    tmp.replace(out)                      # atomic: a crash mid-save never leaves a truncated shard
+    if rank == 0:                         # shards of an earlier run with a different world size are stale
+        for f in path.glob("rank*-of*.pt"):
+            try:
+                if int(f.stem.split("-of")[1]) != world_size:
+                    f.unlink()
+            except (ValueError, OSError):
+                pass
     return out
 
 
 def load_optimizer_shards(path: Path, nlp, optimizer, owned_keys: Iterable[KeyT], *, rank: int, world_size: int,
                           allow_reshard: bool = True) -> Dict[str, Any]:
-    """Load the optimizer state for ``owned_keys``.  With the same world size only
-    this rank's file is read; otherwise (``allow_reshard``) all shards are scanned
-    and the keys this rank now owns are picked out."""
+    """Load the optimizer state for ``owned_keys``.  This rank's own file is read first; if it does
+    not cover every owned key (different world size, or the same world size with a different
+    ``shard_balance``) and ``allow_reshard``, the remaining shards of the newest complete set are
+    scanned too.  Returns ``{"extra": ..., "master": {key: fp32 tensor}, "nr_update": int}``."""
     path = Path(path) / "optim"
     files = sorted(path.glob("rank*-of*.pt"))
     if not files:
         raise FileNotFoundError(f"No optimizer shards under {path}")
-    saved_ws = int(files[0].stem.split("-of")[1])
+    by_ws: Dict[int, list] = {}
+    for f in files:
+        try:
+            by_ws.setdefault(int(f.stem.split("-of")[1]), []).append(f)
+        except ValueError:
+            continue
+    complete = {ws: fs for ws, fs in by_ws.items() if len(fs) == ws}
+    if world_size in complete:
+        saved_ws = world_size
+    elif complete:
+        saved_ws = max(complete, key=lambda ws: max(f.stat().st_mtime for f in complete[ws]))
+    else:
+        saved_ws = max(by_ws, key=lambda ws: len(by_ws[ws]))
     if saved_ws != world_size and not allow_reshard:
         raise ValueError(f"Checkpoint was written with world_size={saved_ws}, now {world_size}")
-    wanted = [path / f"rank{rank}-of{world_size}.pt"] if saved_ws == world_size else files
+    group = by_ws[saved_ws]
+    mine = path / f"rank{rank}-of{world_size}.pt"
+    wanted = ([mine] if (saved_ws == world_size and mine in group) else []) + [f for f in group if f != mine]
     by_struct = {v: k for k, v in structural_keys(nlp).items()}
     owned = set(owned_keys)
-    state = {"mom1": {}, "mom2": {}, "nr_update": {}, "averages": None, "step": 0}
+    state: Dict[str, Any] = {"mom1": {}, "mom2": {}, "nr_update": {}, "averages": None, "master": {}, "step": 0}
     extra: Dict[str, Any] = {}
-    for f in wanted:
+    for i, f in enumerate(wanted):
+        if i > 0 and (not allow_reshard or owned <= set(state["nr_update"])):
+            break                          # own file covered everything (the common case)
         blob = torch.load(f, map_location="cpu", weights_only=False)
         state["step"] = max(state["step"], int(blob.get("step", 0)))
         extra = blob.get("extra", {}) or extra
-        for field in ("mom1", "mom2", "nr_update"):
-            for skey, v in (blob[field] or {}).items():
+        for fld in ("mom1", "mom2", "nr_update", "master"):
+            for skey, v in (blob.get(fld) or {}).items():
                 key = by_struct.get(tuple(skey))
-                if key is not None and key in owned:
-                    state[field][key] = v
+                if key is not None and key in owned and key not in state[fld]:
+                    state[fld][key] = v
         if blob.get("averages"):
             state["averages"] = state["averages"] or {}
             for skey, v in blob["averages"].items():
                 key = by_struct.get(tuple(skey))
                 if key is not None and key in owned:
-                    state["averages"][key] = v
+                    state["averages"].setdefault(key, v)
+    master = state.pop("master")
     optimizer.load_state_dict(state)
-    return extra
+    nr = max(state["nr_update"].values()) if state["nr_update"] else 0
+    return {"extra": extra, "master": master, "nr_update": int(nr)}
 
 
 def save_pipeline(nlp, path: Path, *, training_cfg: Optional[Dict[str, Any]] = None, info: Optional[Dict[str, Any]] = None,

@@ -60,9 +60,9 @@ def create_train_batches(
 ) -> Iterator[Tuple[int, List[Example]]]:
     """Yields ``(epoch, batch)``.  ``max_epochs == 0`` = forever, ``-1`` = stream
     the corpus without loading/shuffling.  With ``shard`` each data-parallel rank
-    sees a disjoint 1/world_size slice of every epoch's (identically shuffled)
-    example list - the reference gives every rank the *same* data
-    (SURVEY.md 2.3 "Data sharding: No (gap)")."""
+    sees a disjoint 1/world_size of every epoch's (identically shuffled) batches, and all
+    ranks get the same number of batches (the ragged tail of an epoch is dropped) - the
+    reference gives every rank the *same* data (SURVEY.md 2.3 "Data sharding: No (gap)")."""
     epoch = 0
     if max_epochs >= 0:
         examples = list(corpus(nlp))
@@ -76,9 +76,20 @@ def create_train_batches(
         else:
             data = corpus(nlp)
         if shard and world_size > 1:
-            data = (eg for i, eg in enumerate(data) if i % world_size == rank)
-        for batch in batcher(data):
-            yield epoch, batch
+            # Batch the (identically shuffled) GLOBAL stream and deal whole batches round-robin; a
+            # round is only handed out once it is complete.  Every rank therefore runs exactly the
+            # same number of steps per epoch - each step contains a collective, so a rank with one
+            # batch more than its peers would wait for them forever (sync mode) - and still sees a
+            # disjoint 1/world_size of the data at the configured batch size.
+            group: List[List[Example]] = []
+            for batch in batcher(data):
+                group.append(batch)
+                if len(group) == world_size:
+                    yield epoch, group[rank]
+                    group = []
+        else:
+            for batch in batcher(data):
+                yield epoch, batch
         epoch += 1
 
 

@@ -86,7 +86,7 @@ class Optimizer:
             w32 = self.master.get(key)
             if w32 is None or w32.shape != weights.shape:
                 w32 = self.master[key] = weights.to(torch.float32).clone()
-        if self.use_adam:
+        if self.use_adam and not self.use_radam:
             if key not in self.mom1:
                 self.mom1[key] = torch.zeros_like(w32)
                 self.mom2[key] = torch.zeros_like(w32)
@@ -102,23 +102,36 @@ class Optimizer:
                 g = g + self.L2 * w32
             if self.grad_clip:
                 norm = torch.linalg.vector_norm(g)
-                if float(norm) >= self.grad_clip:
-                    g = g * (self.grad_clip / float(norm))
-            w32.add_(g, alpha=-self.learn_rate * lr_scale)
+                scale = torch.where(norm >= self.grad_clip, self.grad_clip / norm.clamp_min(1e-30),
+                                    torch.ones_like(norm))      # no host sync
+                g = g * scale
+            lr = self.learn_rate * lr_scale
+            if self.use_adam:                     # RAdam (thinc ``Optimizer._radam``)
+                if key not in self.mom1:
+                    self.mom1[key] = torch.zeros_like(w32)
+                    self.mom2[key] = torch.zeros_like(w32)
+                m1, m2 = self.mom1[key], self.mom2[key]
+                m2.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+                m1.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+                step_size, rect = radam_step_size(nr, self.b1, self.b2)
+                if rect:
+                    w32.addcdiv_(m1, m2.sqrt().add_(self.eps), value=-lr * step_size)
+                else:
+                    w32.add_(m1, alpha=-lr * step_size)
+            else:
+                w32.add_(g, alpha=-lr)
             if self.L2 != 0.0 and self.L2_is_weight_decay:
                 w32.mul_(1.0 - self.learn_rate * self.L2)
             gradient.zero_()
         if w32 is not weights:
             weights.copy_(w32)
         if self.averages is not None:
+            # thinc ``update_averages``: the running average starts at zero
             avg = self.averages.get(key)
             if avg is None:
-                self.averages[key] = w32.clone()
-            else:
-                t = min(nr, 1 + nr / 10.0)   # thinc-style: fast start, then ~EMA
-                decay = (1.0 + t) / (10.0 + t)
-                decay = min(decay, 0.9999)
-                avg.mul_(decay).add_(w32, alpha=1.0 - decay)
+                avg = self.averages[key] = torch.zeros_like(w32)
+            decay = min((1.0 + nr) / (10.0 + nr), 0.9999)
+            avg.sub_(avg - w32, alpha=1.0 - decay)
         return weights, gradient
 
     # ---- state -----------------------------------------------------------
@@ -129,19 +142,53 @@ class Optimizer:
             "mom2": {k: v.detach().to("cpu") for k, v in self.mom2.items() if sel(k)},
             "nr_update": {k: v for k, v in self.nr_update.items() if sel(k)},
             "averages": None if self.averages is None else {k: v.detach().to("cpu") for k, v in self.averages.items() if sel(k)},
+            "master": {k: v.detach().to("cpu") for k, v in self.master.items() if sel(k)},
             "step": self.step,
             "hyper": {"learn_rate": self.learn_rate, "L2": self.L2, "b1": self.b1, "b2": self.b2,
                       "eps": self.eps, "grad_clip": self.grad_clip},
         }
 
     def load_state_dict(self, state: Dict[str, Any], device=None) -> None:
+        """Entries that already exist with the same shape are COPIED INTO (they may be views of a
+        fused kernel's flat moment buffers - ``FusedSymmComm.bind`` - and rebinding the dict entry
+        would silently detach the kernel from the restored state)."""
         dev = device or (self.ops.device if self.ops is not None else get_current_ops().device)
-        self.mom1.update({k: v.to(dev) for k, v in state["mom1"].items()})
-        self.mom2.update({k: v.to(dev) for k, v in state["mom2"].items()})
+
+        def merge(dst: Dict[KeyT, torch.Tensor], src: Dict[KeyT, torch.Tensor]) -> None:
+            for k, v in src.items():
+                cur = dst.get(k)
+                if cur is not None and tuple(cur.shape) == tuple(v.shape):
+                    cur.copy_(v.to(device=cur.device, dtype=cur.dtype))
+                else:
+                    dst[k] = v.to(dev)
+
+        merge(self.mom1, state["mom1"])
+        merge(self.mom2, state["mom2"])
         self.nr_update.update(state["nr_update"])
         if state.get("averages") is not None:
-            self.averages = {k: v.to(dev) for k, v in state["averages"].items()}
-        self.step = int(state.get("step", 0))
+            if self.averages is None:
+                self.averages = {}
+            merge(self.averages, state["averages"])
+        if state.get("master"):
+            merge(self.master, state["master"])
+        target = int(state.get("step", 0))
+        while self.step < target:                 # fast-forward learning-rate (and other) schedules
+            self.step_schedules()
+
+
+def radam_step_size(t: int, beta1: float, beta2: float):
+    """Rectified-Adam step multiplier at update ``t`` -> (step_size, rectified?).  When the variance
+    of the adaptive rate is not tractable yet (N_sma < 5) the update degenerates to bias-corrected
+    momentum SGD, exactly like thinc's ``_radam`` (``degenerated_to_sgd``)."""
+    import math
+
+    beta2_t = beta2 ** t
+    sma_max = 2.0 / (1.0 - beta2) - 1.0
+    sma = sma_max - 2.0 * t * beta2_t / (1.0 - beta2_t)
+    if sma >= 5.0:
+        return (math.sqrt((1.0 - beta2_t) * (sma - 4.0) / (sma_max - 4.0) * (sma - 2.0) / sma * sma_max / (sma_max - 2.0))
+                / (1.0 - beta1 ** t)), True
+    return 1.0 / (1.0 - beta1 ** t), False
 
 
 @registry.optimizers("Adam.v1")
@@ -164,7 +211,6 @@ def Adam(
 def RAdam(learn_rate: Schedule = 0.001, *, L2: Schedule = 0.0, beta1: Schedule = 0.9, beta2: Schedule = 0.999,
           eps: Schedule = 1e-8, grad_clip: Schedule = 1.0, L2_is_weight_decay: bool = True,
           use_averages: bool = True) -> Optimizer:
-    # Rectification only changes the first few hundred steps; treated as Adam here.
     return Optimizer(learn_rate, L2=L2, beta1=beta1, beta2=beta2, eps=eps, grad_clip=grad_clip,
                      L2_is_weight_decay=L2_is_weight_decay, use_averages=use_averages, use_radam=True)
 

@@ -43,7 +43,7 @@ from .nn.layers import offset_dropout_stream
 from .ops import get_current_ops, require_cpu, require_gpu, set_current_ops
 from .parallel.proxies import PeerProxy, RayPeerProxy  # noqa: F401
 from .parallel.sync_proxy import FlatLayout, LocalComm, ShardedSyncProxy, TorchDistComm
-from .parallel.util import KeyT, divide_params, divide_params_balanced, set_params_proxy
+from .parallel.util import DIVIDERS, KeyT, set_params_proxy
 from .training.checkpoint import load_optimizer_shards, save_optimizer_shard, save_pipeline
 from .training.initialize import init_nlp
 from .training.loop import (
@@ -74,7 +74,7 @@ class Worker:
         output_path: Optional[Path] = None,
         resume_path: Optional[Path] = None,
         shard_data: bool = True,
-        shard_balance: str = "nodes",
+        shard_balance: str = "auto",
         dist_init: Optional[Dict[str, Any]] = None,
         fused_ops: bool = True,
         inject_fault: Optional[str] = None,
@@ -159,9 +159,25 @@ class Worker:
     def get_quorum(self) -> int:
         return self.num_workers * int(self.T["accumulate_gradient"])
 
+    def _balance(self) -> str:
+        """``auto``: the reference partition (node counts, leftovers to the last rank) everywhere except
+        under the fused exchange, whose step time is set by the heaviest shard -> size-balanced."""
+        if self.shard_balance != "auto":
+            return self.shard_balance
+        return "lpt" if self._resolved_comm() == "fused" else "nodes"
+
+    def _resolved_comm(self) -> str:
+        if self.mode != "sync":
+            return "actors"
+        if self.comm_name != "auto":
+            return self.comm_name
+        ops = get_current_ops()
+        if ops.device.type == "cuda" and getattr(ops, "fused", False):
+            return "fused"                    # bucketed RS+Adam+AG kernels (also the 1-GPU multi-tensor optimizer)
+        return "local" if self.num_workers == 1 else "dist"
+
     def _divide(self, model):
-        fn = divide_params if self.shard_balance == "nodes" else divide_params_balanced
-        return fn(model, self.num_workers)
+        return DIVIDERS[self._balance()](model, self.num_workers)
 
     def get_owned_keys(self) -> List[KeyT]:
         owned: List[KeyT] = []
@@ -214,13 +230,8 @@ class Worker:
                 all_peers=list(peers), self_index=self.rank,
             )
         elif self.mode == "sync":
-            layout = FlatLayout.build(models, self.num_workers, balance=self.shard_balance)
-            comm_name = self.comm_name
-            if comm_name == "auto":
-                if ops.device.type == "cuda" and getattr(ops, "fused", False):
-                    comm_name = "fused"           # one-kernel RS+Adam+AG (also the 1-GPU multi-tensor Adam)
-                else:
-                    comm_name = "local" if self.num_workers == 1 else "dist"
+            comm_name = self._resolved_comm()
+            layout = FlatLayout.build(models, self.num_workers, balance=self._balance())
             buffers = None
             if comm_name == "local":
                 comm: Any = LocalComm(self.rank, self.num_workers)
@@ -232,8 +243,10 @@ class Worker:
                     self._ensure_dist()
                 from .parallel.fused_comm import FusedSymmComm
 
-                comm = FusedSymmComm(self.rank, self.num_workers, layout, ops.device, optimizer=self.optimizer)
+                comm = FusedSymmComm(self.rank, self.num_workers, layout, ops.device, optimizer=self.optimizer,
+                                     ops=ops)
                 buffers = comm.buffers
+                ops.gate_provider = comm          # consumer-side gates on freshly exchanged weights (C2)
             else:
                 raise ValueError(f"Unknown comm backend {comm_name!r}")
             param_dtype = getattr(ops, "param_dtype", ops.dtype)
@@ -257,17 +270,36 @@ class Worker:
         path = self.resume_path
         assert path is not None
         self.nlp.from_disk(path)
+        force = getattr(self.proxy, "load_param", None)      # async proxy: overwrite non-owned keys too
         for _n, c in self.nlp.pipeline:          # push loaded weights through the proxy
             if hasattr(c, "model"):
                 for node in c.model.walk():
                     for pname in node.param_names:
                         if node.has_param(pname):
-                            self.proxy.set_param(node.id, pname, node._params._params[(node.id, pname)])
+                            value = node._params._params[(node.id, pname)]
+                            if force is not None:
+                                force(node.id, pname, value, version=2)
+                            else:
+                                self.proxy.set_param(node.id, pname, value)
         try:
-            load_optimizer_shards(path, self.nlp, self.optimizer, self.get_owned_keys(),
-                                  rank=self.rank, world_size=self.num_workers)
+            loaded = load_optimizer_shards(path, self.nlp, self.optimizer, self.get_owned_keys(),
+                                           rank=self.rank, world_size=self.num_workers)
         except FileNotFoundError:
             logger.warning("resume: no optimizer shards found under %s; starting with fresh moments", path)
+            loaded = None
+        proxy = self.proxy
+        if loaded is not None and isinstance(proxy, ShardedSyncProxy):
+            # fp32 master weights of the owned shard (the checkpointed model holds bf16-rounded values)
+            for key, value in (loaded.get("master") or {}).items():
+                view = proxy._master_views.get(key)
+                if view is not None:
+                    view.copy_(value.to(device=view.device, dtype=torch.float32).reshape(view.shape))
+            proxy.version = int((loaded.get("extra") or {}).get("version") or 0)
+            restore = getattr(proxy.comm, "load_optimizer_state", None)
+            if restore is not None:
+                restore(loaded["nr_update"])           # device-side update counter (bias correction)
+        if isinstance(proxy, ShardedSyncProxy) and self.num_workers > 1:
+            proxy.sync_from_owner()
 
     def train(self, peers=None, evaluator: Any = None) -> None:
         """Build the step generator and start it on a thread (so that, as an
@@ -426,6 +458,8 @@ class Worker:
             raise RuntimeError(f"rank {self.rank} failed:\n{self._error}")
 
     def evaluate(self):
+        if self.proxy is not None and hasattr(self.proxy, "quiesce"):
+            self.proxy.quiesce()
         if not self._has_evaluation_callback:
             self._evaluation_callback = create_evaluation_callback(
                 self.nlp, self.dev_corpus, self.T["score_weights"] or self.nlp.config["training"].get("score_weights"),
@@ -437,12 +471,19 @@ class Worker:
         """Rank 0 writes the pipeline directory; every rank writes the optimizer
         state of the keys it owns (``optim/rank{r}-of{n}.pt``)."""
         output_path = Path(output_path)
+        if self.proxy is not None and hasattr(self.proxy, "quiesce"):
+            self.proxy.quiesce()                 # every peer's weights of the last exchange have landed
         if self.rank == 0:
             save_pipeline(self.nlp, output_path, training_cfg=self.T, info=info, before_to_disk=self.before_to_disk)
         if self.optimizer is not None and self.proxy is not None:
+            master = None
+            if isinstance(self.proxy, ShardedSyncProxy) and self.proxy.param_dtype != torch.float32:
+                master = dict(self.proxy._master_views)
             save_optimizer_shard(output_path, self.nlp, self.optimizer, self.get_owned_keys(),
                                  rank=self.rank, world_size=self.num_workers,
-                                 extra={"version": getattr(self.proxy, "version", None)})
+                                 extra={"version": getattr(self.proxy, "version", None),
+                                        "shard_balance": self._balance()},
+                                 master=master)
 
     def _resolve_gpu(self, use_gpu: int, fused_ops: bool = True) -> int:
         if use_gpu is not None and use_gpu >= 0:

@@ -26,99 +26,15 @@ import torch
 import torch.distributed as dist
 
 
-def fake_layout(world: int, seed: int = 0):
-    from spacy_ray_b200.parallel.sync_proxy import ALIGN, FlatLayout, _round_up
-
-    g = torch.Generator().manual_seed(seed)
-    sizes = [5000 * 256, 1000 * 256, 2500 * 256, 2500 * 256, 768 * 1024, 768, 256, 256]
-    for _ in range(8):
-        sizes += [768 * 768, 768, 256, 256]
-    sizes += [64 * 256, 64, 3 * 64 * 2 * 64, 128, 384, 73 * 64, 73]
-    keys = [(i + 1, "p") for i in range(len(sizes))]
-    per_rank = [[] for _ in range(world)]
-    n = max(1, len(keys) // world)
-    for i, k in enumerate(keys):
-        per_rank[min(i // n, world - 1)].append(k)
-    owner, offset, numel, shape, order = {}, {}, {}, {}, []
-    shard_len = []
-    for r in range(world):
-        pos = 0
-        for k in per_rank[r]:
-            sz = sizes[k[0] - 1]
-            order.append(k); owner[k] = r; numel[k] = sz; shape[k] = (sz,); offset[k] = pos
-            pos += _round_up(sz, ALIGN)
-        shard_len.append(pos)
-    cap = _round_up(max(shard_len), ALIGN)
-    starts = [r * cap for r in range(world)]
-    for k in order:
-        offset[k] += starts[owner[k]]
-    return FlatLayout(order, owner, offset, numel, shape, starts, shard_len, cap, world)
-
-
 def run_check(rank, world, dev, steps=4):
-    from spacy_ray_b200.ops.torch_ops import TorchOps
-    from spacy_ray_b200.parallel.fused_comm import FusedSymmComm
-    from spacy_ray_b200.parallel.sync_proxy import ShardedSyncProxy
-    from spacy_ray_b200.training.optimizer import Optimizer
+    """The correctness check lives with the tests (``tests/mgpu_worker.py``, also run by
+    ``pytest -m multigpu``): bucketed fused exchange vs NCCL reduce-scatter + per-key reference
+    optimizer + all-gather on the flagship key-size distribution."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import mgpu_worker
 
-    layout = fake_layout(world)
-    opt = Optimizer(0.01, L2=0.01, grad_clip=1.0)
-    comm = FusedSymmComm(rank, world, layout, dev, optimizer=opt, timeout_s=10.0)
-    proxy = ShardedSyncProxy(layout, opt, rank=rank, world_size=world, device=dev, comm=comm,
-                             param_dtype=torch.bfloat16, buffers=comm.buffers)
-    comm.bind(proxy)
-    # identical initial weights everywhere
-    g0 = torch.Generator(device="cpu").manual_seed(123)
-    init = (torch.randn(layout.total, generator=g0) * 0.1)
-    for k in layout.keys:       # padding stays zero
-        o, n = layout.offset[k], layout.numel[k]
-        proxy.param_flat[o:o + n] = init[o:o + n].to(dev).bfloat16()
-    s0 = layout.shard_start[rank]
-    for k in layout.owned_keys(rank):
-        o, n = layout.offset[k], layout.numel[k]
-        proxy.master[o - s0:o - s0 + n] = proxy.param_flat[o:o + n].float()
-    # reference state (library path)
-    ref_ops = TorchOps(str(dev))
-    ref_master = proxy.master.clone()
-    ref_m1 = torch.zeros_like(ref_master)
-    ref_m2 = torch.zeros_like(ref_master)
-    ref_param = proxy.param_flat.clone()
-    torch.cuda.synchronize()
-    dist.barrier()
-    worst = 0.0
-    for step in range(steps):
-        gg = torch.Generator(device="cpu").manual_seed(1000 * step + rank)
-        grad = torch.zeros(layout.total)
-        for k in layout.keys:
-            o, n = layout.offset[k], layout.numel[k]
-            grad[o:o + n] = torch.randn(n, generator=gg) * (0.01 if n > 1000 else 1.0)
-        grad = grad.to(dev)
-        proxy.grad_flat.copy_(grad)
-        # ---- reference: NCCL reduce-scatter + per-key Adam + all-gather
-        shard = torch.empty(layout.shard_cap, device=dev)
-        dist.reduce_scatter_tensor(shard, grad.clone())
-        for k in layout.owned_keys(rank):
-            o, n = layout.offset[k] - s0, layout.numel[k]
-            ref_ops.adam_step(ref_master[o:o + n], shard[o:o + n], ref_m1[o:o + n], ref_m2[o:o + n], lr=0.01,
-                              beta1=0.9, beta2=0.999, eps=1e-8, nr_update=step + 1, grad_clip=1.0, l2=0.01,
-                              l2_is_weight_decay=True)
-        mine = ref_master.bfloat16()
-        dist.all_gather_into_tensor(ref_param, mine)
-        # ---- ours: one kernel
-        proxy.step()
-        torch.cuda.synchronize()
-        comm.check()
-        err = (proxy.param_flat.float() - ref_param.float()).abs().max().item()
-        merr = (proxy.master - ref_master).abs().max().item()
-        worst = max(worst, err, merr)
-        assert float(proxy.grad_flat.abs().sum()) == 0.0, "gradient buffer not zeroed"
-        # all ranks hold identical weights
-        chk = proxy.param_flat.float().sum().reshape(1).double()
-        allc = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(allc, chk)
-        assert all(float(c) == float(allc[0]) for c in allc), "ranks disagree on weights"
-    return {"check": "ok", "steps": steps, "max_abs_err_vs_nccl_path": worst, "world": world,
-            "nvls": bool(comm.grad_mc), "params": int(sum(layout.numel.values()))}
+    args = argparse.Namespace(steps=steps, scale=1, buckets=6, opt="adam", balance="lpt", pipe="ner")
+    return mgpu_worker.case_exchange(rank, world, dev, args)
 
 
 def time_op(fn, iters, warm=3):

@@ -18,7 +18,7 @@ void fused_comm_bucket(std::vector<int64_t> grad_ptrs, std::vector<int64_t> para
                        const Tensor& key_off, const Tensor& key_len, const Tensor& hyper, Tensor step, Tensor epoch,
                        Tensor bar, Tensor error, int64_t shard_start, int64_t blk_begin, int64_t blk_end,
                        int64_t key_begin, int64_t key_end, int64_t bucket, bool last, int64_t rank, int64_t grid,
-                       int64_t opt_mode, double timeout_s) {
+                       int64_t opt_mode, double timeout_s, int64_t test_delay_us) {
   const int W = (int)grad_ptrs.size();
   TORCH_CHECK(W >= 1 && W <= kMaxWorld && (int)param_ptrs.size() == W && (int)signal_ptrs.size() == W);
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && red.scalar_type() == at::kFloat);
@@ -50,6 +50,7 @@ void fused_comm_bucket(std::vector<int64_t> grad_ptrs, std::vector<int64_t> para
   a.blk_begin = (int)blk_begin; a.blk_end = (int)blk_end; a.key_begin = (int)key_begin; a.key_end = (int)key_end;
   a.bucket = (int)bucket; a.last = last ? 1 : 0;
   a.world = W; a.rank = (int)rank; a.opt_mode = (int)opt_mode;
+  a.test_delay_ns = (uint64_t)test_delay_us * 1000ull;
   cudaError_t e = launch_fused_bucket(a, (int)grid, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(e == cudaSuccess, "fused_comm_bucket launch failed: ", cudaGetErrorString(e));
 }
@@ -94,7 +95,8 @@ void register_comm_ops(torch::Library& m) {
       "Tensor(r!) red, Tensor(a!) master, Tensor(b!) m1, Tensor(c!) m2, Tensor(i!)? avg, Tensor(d!) norms, "
       "Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor hyper, Tensor(e!) step, "
       "Tensor(f!) epoch, Tensor(g!) bar, Tensor(h!) error, int shard_start, int blk_begin, int blk_end, "
-      "int key_begin, int key_end, int bucket, bool last, int rank, int grid, int opt_mode, float timeout_s) -> ()");
+      "int key_begin, int key_end, int bucket, bool last, int rank, int grid, int opt_mode, float timeout_s, "
+      "int test_delay_us) -> ()");
   m.def("gate_wait(Tensor epoch, int[] gate) -> ()");
   m.def(
       "p2p_collective(int kind, int[] buf_ptrs, int[] signal_ptrs, int mc, Tensor(a!) local, Tensor(b!) epoch, "

@@ -191,6 +191,13 @@ __global__ void __launch_bounds__(256, 2) fused_bucket_kernel(FusedCommArgs a) {
     if (!grid_barrier(bar, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
   }
 
+  if (a.test_delay_ns) {          // test hook: a slow owner (the consumers' gates must hold them back)
+    if (threadIdx.x == 0) {
+      const uint64_t t0 = globaltimer_ns();
+      while (globaltimer_ns() - t0 < a.test_delay_ns) __nanosleep(1000);
+    }
+    __syncthreads();
+  }
   // ---------------- phase 2: clip + optimizer + publish bf16 weights to all ranks ------------
   const float t = (float)(*(const volatile int32_t*)a.step + 1);
   const float b1t = powf(b1, t), b2t = powf(b2, t);

@@ -78,6 +78,7 @@ struct FusedCommArgs {
   int last;                      // 1 = this launch ends the step (advances epoch / update counter)
   int world, rank;
   int opt_mode;                  // kOptAdam / kOptRAdam / kOptSGD
+  uint64_t test_delay_ns;        // tests only: hold the weight publication back by this long (late publisher)
 };
 
 struct P2PCollArgs {

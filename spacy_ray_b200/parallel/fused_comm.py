@@ -184,7 +184,8 @@ class FusedSymmComm:
         self.launches = 0
         self.n_buckets_target = int(n_buckets or os.environ.get("SRB_COMM_BUCKETS", 6))
         self.overlap = os.environ.get("SRB_COMM_OVERLAP", "1") != "0"
-        self.terminal_wait = os.environ.get("SRB_GATE_ALWAYS", "0") == "1"    # debugging: PR-1 behaviour
+        self.terminal_wait = os.environ.get("SRB_GATE_ALWAYS", "0") == "1"    # debugging: round-1 behaviour
+        self.test_delay_us = 0               # tests: make this rank a late publisher (see tests/mgpu_worker.py)
         total = layout.total
         # NVLS (multimem.ld_reduce / multimem.st through the NVSwitch) whenever a multicast mapping
         # exists; SRB_NVLS=0 forces the plain peer-pointer variant.
@@ -373,6 +374,7 @@ class FusedSymmComm:
                 self.hyper, self.step_t, self.epoch, self.bar, self.error,
                 int(L.shard_start[self.rank]), int(bb), int(be), int(kb), int(ke), int(b),
                 bool(b == self.plan.n - 1), self.rank, self._grid_for(b), int(self.opt_mode), float(self.timeout_s),
+                int(self.test_delay_us),
             )
         self.launches += 1
 

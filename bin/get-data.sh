@@ -12,4 +12,7 @@ if [ $# -ge 2 ] && command -v wget >/dev/null; then
 else
   python "$(dirname "$0")/make-data.py" "$out" --n-train ${TRAIN_DOCS:-20000} --n-dev ${DEV_DOCS:-2000}
 fi
-echo "wrote $out/train.jsonl and $out/dev.jsonl (use with [corpora.*] @readers = \"spacy.Corpus.v1\")"
+# the reference converts with `spacy convert`; same step, same output names (DocBin .spacy files)
+python -m spacy_ray_b200 convert "$out/train.jsonl" "$out/train.spacy"
+python -m spacy_ray_b200 convert "$out/dev.jsonl" "$out/dev.spacy"
+echo "wrote $out/{train,dev}.jsonl and $out/{train,dev}.spacy (use with [corpora.*] @readers = \"spacy.Corpus.v1\")"

@@ -95,7 +95,7 @@ __device__ __forceinline__ bool grid_barrier(uint32_t* state, uint64_t timeout_n
   return ok;
 }
 
-__global__ void __launch_bounds__(256, 2) fused_bucket_kernel(FusedCommArgs a) {
+__global__ void __launch_bounds__(256, 3) fused_bucket_kernel(FusedCommArgs a) {
   const int W = a.world, rank = a.rank, bkt = a.bucket;
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
   const uint64_t tmo = a.timeout_ns;
@@ -222,14 +222,18 @@ __global__ void __launch_bounds__(256, 2) fused_bucket_kernel(FusedCommArgs a) {
       const float norm = sqrtf(a.norms_sq[k]);
       if (norm >= clip) scale = clip / fmaxf(norm, 1e-30f);
     }
-    {
-      // loads for all 4 vectors of this thread first (16 independent 16-byte loads in flight)
-      const int64_t t0 = base + threadIdx.x * 4;
-      const float* gsrc = keep_red ? a.red : (my_grad + s0);
-      float4 g4[4], w4[4], a4[4], b4[4], e4[4];
-      bool ok[4];
+    // two passes of two vectors each: 2 x 5 independent 16-byte loads in flight per thread, and few
+    // enough live registers (<= 85) that a CTA of this kernel fits on an SM NEXT TO a CTA of the
+    // tcgen05 GEMM kernels (320 threads x 128 registers) - that co-residency is what lets the
+    // exchange of a finished bucket run under the rest of the backward pass
+    const float* gsrc = keep_red ? a.red : (my_grad + s0);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int64_t t0 = base + threadIdx.x * 4 + half * 2048;
+      float4 g4[2], w4[2], a4[2], b4[2], e4[2];
+      bool ok[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         const int64_t idx = t0 + j * 1024;
         ok[j] = idx < end;
         if (ok[j]) {
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) fused_bucket_kernel(FusedCommArgs a) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         if (!ok[j]) continue;
         const int64_t idx = t0 + j * 1024;
         float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w}, wv[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};

@@ -293,7 +293,7 @@ class FusedSymmComm:
 
     def _comm_stream(self) -> "torch.cuda.Stream":
         if self._stream is None:
-            self._stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SRB_COMM_PRIO", "-1")))
         return self._stream
 
     # ------------------------------------------------------------------ plan
@@ -316,8 +316,11 @@ class FusedSymmComm:
         n = be - bb
         if self._grid_override:
             return max(1, min(int(self._grid_override), max(n, 1)))
-        # persistent, co-resident grid (the kernel has device-wide barriers): at most 2 CTAs per SM
-        return max(1, min(2 * self._sms, n))
+        # persistent, co-resident grid (the kernel has device-wide barriers).  Buckets that run under
+        # the backward pass share each SM with a CTA of the tcgen05 GEMM kernels (registers allow one
+        # CTA of this kernel next to one of those); the last bucket has the device to itself.
+        per_sm = 2 if b == self.plan.n - 1 else 1
+        return max(1, min(per_sm * self._sms, n))
 
     # ------------------------------------------------------------------ the step
     def begin_step(self, proxy, overlap: bool) -> None:

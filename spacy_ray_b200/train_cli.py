@@ -63,6 +63,10 @@ def build_parser() -> argparse.ArgumentParser:
     _add_train_args(train)
     plain = sub.add_parser("train", help="Single-process training (no workers).")
     _add_train_args(plain)
+    conv = sub.add_parser("convert", help="Convert a JSONL corpus to a DocBin (.spacy) file, like `spacy convert`.")
+    conv.add_argument("input_path", type=Path)
+    conv.add_argument("output_path", type=Path, help="output file (.spacy) or directory")
+    conv.add_argument("--limit", "-n", type=int, default=0)
     return parser
 
 
@@ -94,6 +98,15 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     if args.group is None or (args.group == "ray" and args.command is None):
         parser.print_help()
         return 1
+    if args.group == "convert":
+        from .training.docbin import convert_jsonl
+
+        out = args.output_path
+        if out.suffix != ".spacy":
+            out = out / (args.input_path.stem + ".spacy")
+        n = convert_jsonl(args.input_path, out, limit=args.limit)
+        print(f"✔ Generated output file ({n} documents): {out}")
+        return 0
     try:
         ray_train_cli(args, extra)
     except ConfigValidationError as e:

@@ -1,11 +1,12 @@
 """Corpus readers.
 
-``spacy.Corpus.v1`` upstream reads binary ``.spacy`` DocBins; there is no spaCy
-here, so the same registry name reads JSON-lines instead (one doc per line:
-``{"words", "tags", "ents", "heads", "deps"}`` or Prodigy-style
-``{"text", "spans"}`` - the format the reference's ``bin/get-data.sh`` fetches).
-An empty/None path yields nothing, which is what the reference's only test
-relies on (``spacy_ray/tests/test_worker.py:26-29``).
+``spacy.Corpus.v1`` reads what upstream reads - binary ``.spacy`` DocBin files
+(``training/docbin.py`` implements the container without spaCy; the reference's
+``bin/get-data.sh:6-13`` produces them with ``spacy convert``) - and, in the same
+directory walk, JSON-lines files (one doc per line: ``{"words", "tags", "ents",
+"heads", "deps"}`` or Prodigy-style ``{"text", "spans"}``, the raw format that script
+downloads).  An empty/None path yields nothing, which is what the reference's only
+test relies on (``spacy_ray/tests/test_worker.py:26-29``).
 
 ``spacy_ray_b200.SyntheticCorpus.v1`` generates a seeded, *learnable* synthetic
 corpus (there is no network for real data): Zipfian vocabulary, per-type tags,
@@ -35,7 +36,7 @@ class JsonlCorpus:
         if self.path is None or str(self.path) in ("", "."):
             return []
         if self.path.is_dir():
-            return sorted(p for p in self.path.rglob("*") if p.suffix in (".jsonl", ".json"))
+            return sorted(p for p in self.path.rglob("*") if p.suffix in (".jsonl", ".json", ".spacy"))
         if not self.path.exists():
             raise FileNotFoundError(f"Corpus path not found: {self.path}")
         return [self.path]
@@ -44,6 +45,18 @@ class JsonlCorpus:
         if self._cache is None:
             docs: List[Doc] = []
             for f in self._files():
+                if self.limit and len(docs) >= self.limit:
+                    break
+                if f.suffix == ".spacy":
+                    from .docbin import DocBin
+
+                    for d in DocBin().from_disk(f).get_docs():
+                        if len(d) == 0 or (self.max_length and len(d) > self.max_length):
+                            continue
+                        docs.append(d)
+                        if self.limit and len(docs) >= self.limit:
+                            break
+                    continue
                 with f.open("r", encoding="utf8") as fh:
                     for line in fh:
                         line = line.strip()

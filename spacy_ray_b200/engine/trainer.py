@@ -213,6 +213,8 @@ class Trainer:
         for name, comp, kind in heads:
             if kind is None:
                 return f"component {name!r} ({comp.__class__.__name__}) has no device-side update"
+            if any(node.name == "staticvectors" for node in comp.model.walk()):
+                return f"{name}: static vectors (row lookup is host-side; generic path)"
             if kind in ("ner", "parser"):
                 lower = comp.model.get_ref("lower").get_param("W")
                 _nF, nO, nP, _nI = lower.shape
@@ -253,6 +255,8 @@ class Trainer:
         self.lay = _Layout(rows=rows_cap, docs=self.B, lmax=_align(cap_len, 64),
                            slots=tuple(self.store.slots), bucket=self.bucket_rows,
                            n_attr=int(self.store.attrs.shape[1]))
+        if hasattr(self.ops, "max_rows_hint"):
+            self.ops.max_rows_hint = max(int(self.ops.max_rows_hint), int(rows_cap))
         self.host_grouping = os.environ.get("SRB_HOST_GROUP", "1") != "0"
         self.head_streams = os.environ.get("SRB_HEAD_STREAMS", "1") != "0"
         self._head_streams: List[torch.cuda.Stream] = []

@@ -39,7 +39,11 @@ def build_tagger_model(tok2vec: Model, nO: Optional[int] = None, normalize: bool
         Returns ``(loss, guesses)``."""
         X, bp_t2v = tok2vec(batch, True)
         W, b = output.get_param("W"), output.get_param("b")
-        loss, _d, guesses, dX, dW, db = model.ops.softmax_xent(X, W, b, labels)
+        if getattr(model.ops, "fused", False):      # gradients accumulate straight into the flat bucket
+            go = {"W": output.grad_buffer("W"), "b": output.grad_buffer("b")}
+            loss, _d, guesses, dX, dW, db = model.ops.softmax_xent(X, W, b, labels, grad_out=go)
+        else:
+            loss, _d, guesses, dX, dW, db = model.ops.softmax_xent(X, W, b, labels)
         output.inc_grad("W", dW)
         output.inc_grad("b", db)
         bp_t2v(dX)

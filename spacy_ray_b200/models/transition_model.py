@@ -126,12 +126,21 @@ def build_transition_model(
         if not is_train or rec["n_steps"] == 0:
             return out
         # ---- batched backward over all recorded steps --------------------
-        g = transition_backward(ops, rec, params, batch.n_rows)
+        fused = getattr(ops, "fused", False)
+        go = None
+        if fused:         # kernels accumulate straight into the flat gradient bucket
+            go = {"Wu": upper.grad_buffer("W"), "bu": upper.grad_buffer("b"), "b": lower.grad_buffer("b"),
+                  "pad": lower.grad_buffer("pad")}
+        g = transition_backward(ops, rec, params, batch.n_rows, grad_out=go)
         upper.inc_grad("W", g["dWu"])
         upper.inc_grad("b", g["dbu"])
         lower.inc_grad("b", g["db"].reshape(nO_, nP_))
         lower.inc_grad("pad", g["dpad"].reshape(1, nF_, nO_, nP_))
-        dH, dWl2, _ = ops.linear_backward(g["dYf"], H, Wl2, need_db=False)      # the precompute layer has no bias
+        if fused:
+            dH, dWl2, _ = ops.linear_backward(g["dYf"], H, Wl2, need_db=False,
+                                              grad_out={"W": lower.grad_buffer("W")})
+        else:
+            dH, dWl2, _ = ops.linear_backward(g["dYf"], H, Wl2, need_db=False)  # the precompute layer has no bias
         lower.inc_grad("W", dWl2.reshape(nF_, nO_, nP_, nI_))
         bp_t2v(bp_lin(dH))
         return out
@@ -302,14 +311,14 @@ def _arc_steps_reference(system: ArcEagerSystem, Yf, params, batch, gold, is_tra
     return rec
 
 
-def transition_backward(ops, rec, params, n_rows: int) -> Dict[str, torch.Tensor]:
+def transition_backward(ops, rec, params, n_rows: int, grad_out=None) -> Dict[str, torch.Tensor]:
     """Gradients of everything downstream of ``Yf`` from the step records.
 
     dWu = d^T hid; dbu = sum d; d_hid = d Wu; dPre = route d_hid to the winning
     piece; db = sum dPre; dYf[ids[f], f] += dPre (or dpad[f] if ids[f] < 0)."""
     fused = getattr(ops, "transition_backward", None)
     if fused is not None:
-        out = fused(rec, params, n_rows)
+        out = fused(rec, params, n_rows, grad_out=grad_out) if grad_out is not None else fused(rec, params, n_rows)
         if out is not None:
             return out
     nF, nO, nP = params["nF"], params["nO"], params["nP"]

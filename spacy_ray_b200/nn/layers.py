@@ -169,8 +169,6 @@ def MultiHashEmbed(
 ) -> Model:
     """TokenBatch -> (Tp, width): 4-way hashed embeddings per attribute,
     concatenated, mixed by Maxout + LayerNorm (+ dropout)."""
-    if include_static_vectors:
-        raise NotImplementedError("static vectors are not supported (no vectors table in this build)")
     if len(attrs) != len(rows):
         raise ValueError("MultiHashEmbed: attrs and rows must have the same length")
     unknown = [a for a in attrs if a not in ATTR_COLUMNS]
@@ -181,7 +179,12 @@ def MultiHashEmbed(
     for attr, nV in zip(attrs, rows):
         seed += 1
         embeds.append(HashEmbed(width, int(nV), seed=seed, column=ATTR_COLUMNS[attr]))
-    mix = Maxout(nO=width, nI=width * len(embeds), nP=maxout_pieces)
+    static = None
+    if include_static_vectors:
+        from .staticvectors import StaticVectors
+
+        static = StaticVectors(width)           # vectors[rows] @ W^T, joins the concat as one more block
+    mix = Maxout(nO=width, nI=width * (len(embeds) + (1 if static is not None else 0)), nP=maxout_pieces)
     norm = LayerNorm(width)
 
     def init(model: Model, X=None, Y=None):
@@ -194,10 +197,18 @@ def MultiHashEmbed(
         seeds = [e.attrs["seed"] for e in embeds]
         cols = [e.attrs["column"] for e in embeds]
         concat = ops.multi_hash_embed(batch.attrs, batch.mask, tables, seeds, cols)
+        bp_static = None
+        if static is not None:
+            sv, bp_static = static(batch, is_train)
+            concat = torch.cat([concat, sv.to(concat.dtype) * batch.mask.to(concat.dtype)], dim=1)
         Y, bp_mix = _run_block(model, mix, norm, concat, batch.mask, window=0, residual=False, is_train=is_train)
 
         def backprop(dY):
             d_concat = bp_mix(dY)
+            if bp_static is not None:
+                w_hash = width * len(embeds)
+                bp_static(d_concat[:, w_hash:].contiguous())
+                d_concat = d_concat[:, :w_hash].contiguous()
             bufs = [e.grad_buffer("E") for e in embeds] if getattr(ops, "fused", False) else None
             if bufs is not None and any(b is None for b in bufs):
                 bufs = None
@@ -213,7 +224,8 @@ def MultiHashEmbed(
 
     return Model(
         "multihashembed", forward, init=init, dims={"nO": width},
-        layers=[*embeds, mix, norm], attrs={"dropout_rate": 0.0, "attrs": list(attrs)},
+        layers=[*embeds, *([static] if static is not None else []), mix, norm],
+        attrs={"dropout_rate": 0.0, "attrs": list(attrs)},
         refs={"mix": mix, "norm": norm},
     )
 
@@ -290,15 +302,13 @@ def HashEmbedCNN(
     width: int, depth: int, embed_size: int = 2000, window_size: int = 1, maxout_pieces: int = 3,
     subword_features: bool = True, pretrained_vectors: Any = None,
 ) -> Model:
-    if pretrained_vectors:
-        raise NotImplementedError("pretrained vectors are not supported")
     if subword_features:
         attrs = ["NORM", "PREFIX", "SUFFIX", "SHAPE"]
         rows = [embed_size, embed_size // 2, embed_size // 2, embed_size // 2]
     else:
         attrs, rows = ["NORM"], [embed_size]
     return Tok2Vec(
-        MultiHashEmbed(width, attrs, rows),
+        MultiHashEmbed(width, attrs, rows, include_static_vectors=bool(pretrained_vectors)),
         MaxoutWindowEncoder(width, window_size, maxout_pieces, depth),
     )
 
@@ -358,7 +368,12 @@ def Linear(nO: Optional[int] = None, nI: Optional[int] = None, *, init_zero: boo
         Y = model.ops.linear(X, W, b)
 
         def backprop(dY):
-            dX, dW, db = model.ops.linear_backward(dY, X, W)
+            if getattr(model.ops, "fused", False):
+                # kernels accumulate straight into the flat gradient bucket (inc_grad recognises the buffer)
+                go = {"W": model.grad_buffer("W"), "b": model.grad_buffer("b")}
+                dX, dW, db = model.ops.linear_backward(dY, X, W, grad_out=go)
+            else:
+                dX, dW, db = model.ops.linear_backward(dY, X, W)
             model.inc_grad("W", dW)
             model.inc_grad("b", db)
             return dX

@@ -92,6 +92,8 @@ class B200Ops(TorchOps):
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self.max_rows_hint = 0               # engine.Trainer: largest row count any captured step will use
         # C2: consumer-side gates.  ``FusedSymmComm`` installs itself here; kernels that read
         # parameters ask it which buckets of freshly exchanged weights they are the first to touch
         # (``_gate``: descriptor for an in-kernel gate; ``_gate_now``: stand-alone one-warp wait in
@@ -141,8 +143,11 @@ class B200Ops(TorchOps):
                      bias=b, gate=self._gate(W, b))
         return out
 
-    def _dw_tc(self, dZ: torch.Tensor, X: torch.Tensor, window: int, out: Optional[torch.Tensor] = None):
-        """dW[n, k] (+)= sum_t dZ[t, n] * Xw[t, k] on the tcgen05 MN-major/split-K kernel."""
+    def _dw_tc(self, dZ: torch.Tensor, X: torch.Tensor, window: int, out: Optional[torch.Tensor] = None,
+               n_valid: Optional[int] = None):
+        """dW[n, k] (+)= sum_t dZ[t, n] * Xw[t, k] on the tcgen05 MN-major/split-K kernel.
+        ``n_valid``: only the first ``n_valid`` rows of dW exist (``dZ`` has a padded pitch whose extra
+        columns are zero); ``out`` may then be the (n_valid, k) gradient buffer itself."""
         T, N = dZ.shape
         w = X.shape[1]
         Kt = w * (3 if window else 1)
@@ -150,11 +155,12 @@ class B200Ops(TorchOps):
         if not (self.use_tc and self.tc_dw and N % 64 == 0 and w % 64 == 0):
             return None
         bn = 256 if w % 256 == 0 else (128 if w % 128 == 0 else 64)
+        rows = N if n_valid is None else int(n_valid)
         if out is None:
-            out = torch.zeros((N, Kt), dtype=torch.float32, device=dZ.device)
-        tiles = ((N + 127) // 128) * (Kt // bn)
+            out = torch.zeros((rows, Kt), dtype=torch.float32, device=dZ.device)
+        tiles = ((rows + 127) // 128) * (Kt // bn)
         splits = max(1, min(148 // max(tiles, 1), (T + 63) // 64))
-        self.tc_gemm(dZ, X, out, mode=MODE_MNMN, epi=EPI_ATOMIC_F32, block_n=bn, M=N, N=Kt, K=T, splits=splits,
+        self.tc_gemm(dZ, X, out, mode=MODE_MNMN, epi=EPI_ATOMIC_F32, block_n=bn, M=rows, N=Kt, K=T, splits=splits,
                      win_w=(w if window else 0))
         return out
 
@@ -247,20 +253,24 @@ class B200Ops(TorchOps):
             torch.cuda.current_stream(self.device).wait_stream(self._side)
             self._side_pending = False
 
-    def colsum(self, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """fp32 column sums of a (T, C) bf16 matrix (bias gradients), one kernel."""
+    def colsum(self, X: torch.Tensor, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None) -> torch.Tensor:
+        """fp32 column sums of a (T, C) bf16 matrix (bias gradients), one kernel, ACCUMULATED into
+        ``out`` (which may be the gradient buffer).  ``n_valid``: only the first columns are real."""
         C = X.shape[1]
+        nv = C if n_valid is None else int(n_valid)
         if out is None:
-            out = torch.zeros((C,), dtype=torch.float32, device=X.device)
+            out = torch.zeros((nv,), dtype=torch.float32, device=X.device)
         if X.dtype == torch.bfloat16 and C % 8 == 0 and C <= 2048 and X.stride(1) == 1 and X.stride(0) % 8 == 0:
-            self.k.colsum_acc(X, out)
+            self.k.colsum_acc(X, out, nv)
             self.launches += 1
         else:
-            out.add_(X.to(torch.float32).sum(dim=0))
+            out.add_(X[:, :nv].to(torch.float32).sum(dim=0))
         return out
 
     def _dx_tc(self, dY: torch.Tensor, W: torch.Tensor) -> Optional[torch.Tensor]:
-        """dX = dY @ W on the tensor cores with W (nO, nI) as stored (MODE_KMN)."""
+        """dX = dY @ W on the tensor cores with W (nO, nI) as stored (MODE_KMN).  ``dY`` may have a
+        padded pitch (K = dY.shape[1] >= W.shape[0], extra columns zero): the TMA zero-fills the
+        missing rows of W, so no padded copy of the weights is made."""
         M, K = dY.shape
         N = W.shape[1]
         bn = self._pick_block_n(N)
@@ -356,13 +366,25 @@ class B200Ops(TorchOps):
         Y = X @ W.t()
         return Y + b if b is not None else Y
 
-    def linear_backward(self, dY, X, W, need_dX: bool = True, need_db: bool = True):
+    def linear_backward(self, dY, X, W, need_dX: bool = True, need_db: bool = True,
+                        grad_out: Optional[Dict[str, torch.Tensor]] = None):
+        """``grad_out``: fp32 views of the flat gradient bucket for ``W`` / ``b``; the split-K GEMM and
+        the column-sum kernel accumulate straight into them (no zero-fill + add launches)."""
         dY = dY.to(torch.bfloat16).contiguous() if dY.dtype != torch.bfloat16 else dY.contiguous()
         X = X.contiguous()
-        dW = self._dw_tc(dY, X, 0)
+        go = grad_out or {}
+        gW, gb = go.get("W"), go.get("b")
+        if gW is not None and not (gW.dtype == torch.float32 and gW.is_contiguous()):
+            gW = None
+        if gb is not None and not (gb.dtype == torch.float32 and gb.is_contiguous()):
+            gb = None
+        dW = self._dw_tc(dY, X, 0, out=gW.view(W.shape) if gW is not None else None)
         if dW is None:
             dW = _mm_f32(dY.t(), X)
-        db = self.colsum(dY) if need_db else None
+            if gW is not None:
+                gW.view(W.shape).add_(dW)
+                dW = gW
+        db = self.colsum(dY, out=gb.view(-1) if gb is not None else None) if need_db else None
         dX = None
         if need_dX:
             dX = self._dx_tc(dY, W)
@@ -374,7 +396,7 @@ class B200Ops(TorchOps):
     def softmax(self, logits):
         return torch.softmax(logits.to(torch.float32), dim=-1)
 
-    def softmax_xent(self, X, W, b, labels):
+    def softmax_xent(self, X, W, b, labels, grad_out: Optional[Dict[str, torch.Tensor]] = None):
         self._gate_now(W, b)
         X = X.contiguous()
         nC = W.shape[0]
@@ -384,12 +406,19 @@ class B200Ops(TorchOps):
             if out:
                 dp, guesses, loss = out                        # dp: (T, 128k) bf16, zero past nC
                 self.launches += 1
-                dW = self._dw_tc(dp, X, 0)
-                dW = dW[:nC] if dW is not None else _mm_f32(dp[:, :nC].t(), X)
-                db = self.colsum(dp)[:nC]
-                Wp = W if nC == dp.shape[1] else torch.cat(
-                    [W, torch.zeros((dp.shape[1] - nC, W.shape[1]), dtype=W.dtype, device=W.device)], 0)
-                dX = self._dx_tc(dp, Wp)
+                gW, gb = (grad_out or {}).get("W"), (grad_out or {}).get("b")
+                if gW is not None and not (gW.dtype == torch.float32 and gW.is_contiguous()):
+                    gW = None
+                if gb is not None and not (gb.dtype == torch.float32 and gb.is_contiguous()):
+                    gb = None
+                dW = self._dw_tc(dp, X, 0, out=gW.view(W.shape) if gW is not None else None, n_valid=nC)
+                if dW is None:
+                    dW = _mm_f32(dp[:, :nC].t(), X)
+                    if gW is not None:
+                        gW.view(W.shape).add_(dW)
+                        dW = gW
+                db = self.colsum(dp, out=gb.view(-1) if gb is not None else None, n_valid=nC)
+                dX = self._dx_tc(dp, W)                           # rows >= nC of W: zero-filled by the TMA
                 if dX is None:
                     dX = dp[:, :nC] @ W
                 return loss, dp[:, :nC], guesses, dX, dW, db
@@ -480,7 +509,18 @@ class B200Ops(TorchOps):
                         "nA": system.n_actions})
         return rec
 
-    def transition_backward(self, rec, params, n_rows):
+    def _workspace(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        """Persistent zero-initialised fp32 scratch, (>= rows, cols): allocated once (at the largest row
+        count the engine announced via ``max_rows_hint``) and handed out as a row slice, so captured
+        steps neither allocate nor memset it - its users leave it zeroed."""
+        key = (name, cols)
+        ws = self._ws.get(key)
+        if ws is None or ws.shape[0] < rows:
+            ws = self._ws[key] = torch.zeros((max(rows, int(self.max_rows_hint)), cols), dtype=torch.float32,
+                                             device=self.device)
+        return ws[:rows]
+
+    def transition_backward(self, rec, params, n_rows, grad_out: Optional[Dict[str, torch.Tensor]] = None):
         if rec["d_scores"].dtype != torch.bfloat16:
             return None                       # records from the reference loop: use the reference backward
         nF, nO, nP = params["nF"], params["nO"], params["nP"]
@@ -488,24 +528,28 @@ class B200Ops(TorchOps):
         d = rec["d_scores"]                   # (S, nA_pad) bf16, padded columns are zero
         hid = rec["hid"]
         dev = d.device
-        # d has a 128-multiple pitch (zero columns past nA), so both products run on the tcgen05 kernels
-        dWu = self._dw_tc(d, hid, 0)
+        go = {k: v for k, v in (grad_out or {}).items()
+              if v is not None and v.dtype == torch.float32 and v.is_contiguous()}
+        # d has a 128-multiple pitch (zero columns past nA), so both products run on the tcgen05 kernels;
+        # only the nA real rows / columns are written, straight into the gradient bucket when given
+        gWu = go.get("Wu")
+        dWu = self._dw_tc(d, hid, 0, out=gWu.view(nA, nO) if gWu is not None else None, n_valid=nA)
         if dWu is None:
-            dWu = _mm_f32(d.t(), hid)
-        dWu = dWu[:nA]
-        dbu = self.colsum(d)[:nA]
-        Wu = params["Wu"]
-        Wu_pad = Wu if Wu.shape[0] == d.shape[1] else torch.cat(
-            [Wu, torch.zeros((d.shape[1] - Wu.shape[0], Wu.shape[1]), dtype=Wu.dtype, device=dev)], 0)
-        d_hid = self._dx_tc(d, Wu_pad)
+            dWu = _mm_f32(d[:, :nA].t(), hid)
+            if gWu is not None:
+                gWu.view(nA, nO).add_(dWu)
+                dWu = gWu
+        dbu = self.colsum(d, out=go["bu"].view(-1) if "bu" in go else None, n_valid=nA)
+        d_hid = self._dx_tc(d, params["Wu"])                 # rows >= nA of Wu: zero-filled by the TMA
         if d_hid is None:
-            d_hid = (d @ Wu_pad).contiguous()
-        dYf = torch.zeros((n_rows, nF * nO * nP), dtype=torch.float32, device=dev)
-        dpad = torch.zeros((nF, nO * nP), dtype=torch.float32, device=dev)
-        db = torch.zeros((nO * nP,), dtype=torch.float32, device=dev)
-        self.k.transition_scatter(d_hid, rec["which"], rec["feats"], dYf, dpad, db, nF, nP)
-        self.launches += 1
-        return {"dWu": dWu, "dbu": dbu, "db": db, "dpad": dpad, "dYf": dYf.to(torch.bfloat16)}
+            d_hid = (d[:, :nA] @ params["Wu"]).contiguous()
+        dYf32 = self._workspace("dYf", n_rows, nF * nO * nP)
+        dpad = go["pad"].view(nF, nO * nP) if "pad" in go else torch.zeros((nF, nO * nP), dtype=torch.float32, device=dev)
+        db = go["b"].view(nO * nP) if "b" in go else torch.zeros((nO * nP,), dtype=torch.float32, device=dev)
+        self.k.transition_scatter(d_hid, rec["which"], rec["feats"], dYf32, dpad, db, nF, nP)
+        dYf = self.k.f32_to_bf16_zero(dYf32)                 # bf16 for the GEMMs below; the scratch is clear again
+        self.launches += 2
+        return {"dWu": dWu, "dbu": dbu, "db": db, "dpad": dpad, "dYf": dYf}
 
     # ------------------------------------------------------------------ misc
     def gemm(self, A, B, trans1=False, trans2=False):

@@ -84,14 +84,25 @@ void hash_embed_bwd_sorted(const Tensor& dY, const Tensor& keys, const Tensor& p
 }
 
 // out (C,) fp32 += column sums of X (T, C) bf16
-void colsum_acc(const Tensor& X, Tensor out) {
+void colsum_acc(const Tensor& X, Tensor out, int64_t n_valid) {
   TORCH_CHECK(X.is_cuda(), "X must be a CUDA tensor"); SRB_CHECK_BF16(X); SRB_CHECK_CUDA(out);   // X rows may be strided
+  const int64_t nv = n_valid > 0 ? n_valid : X.size(1);
   TORCH_CHECK(X.dim() == 2 && X.stride(1) == 1 && out.scalar_type() == at::kFloat && out.is_contiguous() &&
-              out.numel() >= X.size(1));
+              nv <= X.size(1) && out.numel() >= nv);
   c10::cuda::CUDAGuard guard(X.device());
   const bool ok = srb::try_launch_colsum_bf16(X.data_ptr(), out.data_ptr<float>(), (int)X.size(0), (int)X.size(1),
-                                              (int)X.stride(0), cur_stream());
+                                              (int)X.stride(0), (int)nv, cur_stream());
   TORCH_CHECK(ok, "colsum_acc: unsupported shape (C must be a multiple of 8, <= 2048)");
+}
+
+// out (bf16, same shape) = src; src = 0 (see launch_f32_to_bf16_zero)
+Tensor f32_to_bf16_zero(Tensor src) {
+  SRB_CHECK_CUDA(src);
+  TORCH_CHECK(src.scalar_type() == at::kFloat && src.numel() % 8 == 0);
+  c10::cuda::CUDAGuard guard(src.device());
+  Tensor out = at::empty(src.sizes(), src.options().dtype(at::kBFloat16));
+  srb::launch_f32_to_bf16_zero(src.data_ptr<float>(), out.data_ptr(), (size_t)src.numel(), cur_stream());
+  return out;
 }
 
 std::vector<Tensor> maxout_ln_fwd(const Tensor& Z, const c10::optional<Tensor>& bias, const c10::optional<Tensor>& G,
@@ -293,7 +304,8 @@ TORCH_LIBRARY(srb, m) {
   m.def("hash_embed_fwd(Tensor attrs, Tensor mask, Tensor[] tables, int[] seeds, int[] columns, int[] gate) -> Tensor");
   m.def("hash_embed_bwd(Tensor dY, Tensor attrs, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
   m.def("hash_embed_bwd_sorted(Tensor dY, Tensor keys, Tensor perm, Tensor mask, Tensor[] grads, int[] seeds, int[] columns) -> ()");
-  m.def("colsum_acc(Tensor X, Tensor(a!) out) -> ()");
+  m.def("colsum_acc(Tensor X, Tensor(a!) out, int n_valid) -> ()");
+  m.def("f32_to_bf16_zero(Tensor(a!) src) -> Tensor");
   m.def("maxout_ln_fwd(Tensor Z, Tensor? bias, Tensor? G, Tensor? beta, Tensor? Xres, Tensor mask, int nO, int nP, float drop_p, int seed, Tensor? seed_dev) -> Tensor[]");
   m.def("maxout_ln_bwd(Tensor dY, Tensor? xhat, Tensor? rstd, Tensor? G, Tensor which, Tensor mask, int nP, float drop_p, int seed, Tensor db, Tensor? dG, Tensor? dbeta, Tensor? seed_dev) -> Tensor");
   m.def("seq2col(Tensor X) -> Tensor");
@@ -313,6 +325,7 @@ TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("hash_embed_bwd", hash_embed_bwd);
   m.impl("hash_embed_bwd_sorted", hash_embed_bwd_sorted);
   m.impl("colsum_acc", colsum_acc);
+  m.impl("f32_to_bf16_zero", f32_to_bf16_zero);
   m.impl("maxout_ln_fwd", maxout_ln_fwd);
   m.impl("maxout_ln_bwd", maxout_ln_bwd);
   m.impl("seq2col", seq2col);

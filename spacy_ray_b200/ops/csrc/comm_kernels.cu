@@ -3,9 +3,10 @@
 // The reference ships every gradient tensor to its owner and every updated tensor back to
 // every peer as separate Ray RPCs (gradient push proxies.py:102-104, optimizer on the owner
 // proxies.py:126-128, parameter push proxies.py:71-75).  Here the flat gradient bucket is cut
-// into a few BUCKETS in the order the backward pass completes them, and for every bucket one
-// launch of `fused_bucket_kernel` runs - on a side stream, concurrently with the rest of the
-// backward pass - the whole owner-side pipeline over NVLink peer memory, no NCCL, no host:
+// into a few BUCKETS in the order the backward pass completes them, and for every bucket the
+// kernel pair `bucket_reduce_kernel` / `bucket_update_kernel` runs - on a side stream, concurrently
+// with the rest of the backward pass - the whole owner-side pipeline over NVLink peer memory,
+// no NCCL, no host:
 //
 //   phase 0  "my gradients of bucket b, epoch e, are complete" -> every rank's signal page;
 //            owners wait for all ranks' flags
@@ -13,10 +14,10 @@
 //            NVSwitch, or P2P ld.relaxed.sys from every peer), every rank's copy of that extent is
 //            ZEROED in the same pass (multimem.st / P2P st) - the buffers are accumulators and the
 //            next backward pass must find them clear -, g -> local scratch, per-key sum of squares
-//   grid barrier (co-resident CTAs, sense-reversing)
+//   (kernel boundary: one CTA per 4096-element work item, so the two phases are two launches)
 //   phase 2  per-key clip, Adam / RAdam / SGD on the fp32 master (+ moments, + parameter averages),
-//            bf16 weights stored straight into ALL ranks' weight buffers (multimem.st / P2P st)
-//   grid barrier -> "published (b, me) = e" into every rank's signal page.
+//            bf16 weights stored straight into ALL ranks' weight buffers (multimem.st / P2P st);
+//            the last CTA to finish releases "published (b, me) = e" into every rank's signal page.
 //
 // Nothing waits for the publication here: the first consumer of a bucket's weights in the next
 // forward pass does (gate.cuh; gemm_tcgen05.cu's TMA producer warp, hash_embed_fwd_kernel).
@@ -72,148 +73,138 @@ __device__ __forceinline__ float4 zero_after(const float4& v) {
   return make_float4(f, f, f, f);
 }
 
-// Sense-reversing barrier across the (co-resident) CTAs of one launch.  state[0] = arrivals,
-// state[1] = generation.  Returns false on timeout.
-__device__ __forceinline__ bool grid_barrier(uint32_t* state, uint64_t timeout_ns) {
-  __syncthreads();
-  bool ok = true;
-  if (threadIdx.x == 0) {
-    const uint32_t gen = ld_acquire_gpu(state + 1);
-    __threadfence();
-    if (atomicAdd(state, 1u) == gridDim.x - 1) {
-      state[0] = 0u;
-      __threadfence();
-      st_release_gpu(state + 1, gen + 1u);
-    } else {
-      const uint64_t t0 = globaltimer_ns();
-      while (ld_acquire_gpu(state + 1) == gen) {
-        if (globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
-      }
-    }
-  }
-  __syncthreads();
-  return ok;
-}
-
-__global__ void __launch_bounds__(256, 3) fused_bucket_kernel(FusedCommArgs a) {
+// One work item (= one 4096-element chunk of one owned key) per CTA, two launches per bucket:
+//   bucket_reduce_kernel  phases 0 + 1 (flags, reduce + clear, per-key sum of squares)
+//   bucket_update_kernel  phase 2 (clip, optimizer, weight stores) + publication by the last CTA
+// The kernel boundary is the "all of this key's partial norms are in" barrier.  No device-wide
+// barrier inside a kernel means no co-residency requirement: the grids can be as large as the
+// bucket, and the CTAs (80 registers x 256 threads) slot in next to the CTAs of whatever the
+// backward pass is running (a tcgen05 GEMM CTA leaves room for exactly one of them per SM).
+__global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) {
   const int W = a.world, rank = a.rank, bkt = a.bucket;
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
-  const uint64_t tmo = a.timeout_ns;
   const int n_items = a.blk_end - a.blk_begin;
   __shared__ int s_fail;
   __shared__ float s_part[8];
   if (threadIdx.x == 0) s_fail = 0;
   __syncthreads();
-
   // ---------------- phase 0: every rank's gradients of this bucket are complete --------------
   if (W > 1) {
     if (blockIdx.x == 0 && threadIdx.x < W) {
       __threadfence_system();
       st_release_sys(a.signal[threadIdx.x] + flag_grad_idx(bkt, rank), epoch);
     }
-    if (n_items > 0 && threadIdx.x < W) {
-      if (!wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, threadIdx.x), epoch, tmo)) s_fail = 1;
+    if (n_items == 0) return;
+    if (threadIdx.x < W) {
+      if (!wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, threadIdx.x), epoch, a.timeout_ns)) s_fail = 1;
     }
     __syncthreads();
     if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 1); return; }
   }
-
+  if (n_items == 0) return;
   const int64_t s0 = a.shard_start;
   float* my_grad = a.grad[rank];
-  const float lr = a.hyper[0], b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], clip = a.hyper[4], l2 = a.hyper[5];
+  const float l2 = a.hyper[5];
   const bool wd = a.hyper[6] != 0.f;
   const float gs = a.hyper[7];
   const bool l2_in_grad = (l2 != 0.f) && !wd;
-  const bool keep_red = (W > 1) || gs != 1.f || l2_in_grad;       // otherwise phase 2 re-reads the gradient itself
+  const bool keep_red = (W > 1) || gs != 1.f || l2_in_grad;       // otherwise the update re-reads the gradient itself
   // ---------------- phase 1: reduce my keys, clear every copy, per-key sum of squares --------
-  for (int b = a.blk_begin + blockIdx.x; b < a.blk_end; b += gridDim.x) {
-    const int k = a.blk_key[b];
-    const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
-    const int64_t end = a.key_off[k] + a.key_len[k];
-    float acc = 0.f;
-    {
-      // 4 independent 16-byte loads per peer are issued before any is consumed (the work item
-      // is exactly 256 threads x 4 vectors), so each thread keeps >= 4 NVLink reads in flight.
-      float4 s[4];
-      bool ok[4];
-      const int64_t t0 = base + threadIdx.x * 4;
+  const int b = a.blk_begin + blockIdx.x;
+  const int k = a.blk_key[b];
+  const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
+  const int64_t end = a.key_off[k] + a.key_len[k];
+  float acc = 0.f;
+  {
+    // 4 independent 16-byte loads per peer are issued before any is consumed (the work item
+    // is exactly 256 threads x 4 vectors), so each thread keeps >= 4 NVLink reads in flight.
+    float4 s[4];
+    bool ok[4];
+    const int64_t t0 = base + threadIdx.x * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { ok[j] = (t0 + j * 1024) < end; s[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      if (W == 1) {
+    for (int j = 0; j < 4; ++j) { ok[j] = (t0 + j * 1024) < end; s[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (W == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = *(const float4*)(my_grad + s0 + t0 + j * 1024);
-      } else if (a.grad_mc) {
+      for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = *(const float4*)(my_grad + s0 + t0 + j * 1024);
+    } else if (a.grad_mc) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = multimem_ld_reduce_v4(a.grad_mc + s0 + t0 + j * 1024);
+      for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = multimem_ld_reduce_v4(a.grad_mc + s0 + t0 + j * 1024);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (ok[j]) multimem_st_v4(a.grad_mc + s0 + t0 + j * 1024, zero_after(s[j]));
-      } else {
+      for (int j = 0; j < 4; ++j) if (ok[j]) multimem_st_v4(a.grad_mc + s0 + t0 + j * 1024, zero_after(s[j]));
+    } else {
 #pragma unroll 2
-        for (int p = 0; p < W; ++p) {
-          float* src = a.grad[(rank + p) % W] + s0 + t0;            // stagger peers across ranks
-          float4 v[4];
+      for (int p = 0; p < W; ++p) {
+        float* src = a.grad[(rank + p) % W] + s0 + t0;            // stagger peers across ranks
+        float4 v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (ok[j]) v[j] = ld_relaxed_sys_v4(src + j * 1024);
+        for (int j = 0; j < 4; ++j) if (ok[j]) v[j] = ld_relaxed_sys_v4(src + j * 1024);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (ok[j]) {
-            s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w;
-            st_relaxed_sys_v4(src + j * 1024, zero_after(v[j]));
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (ok[j]) {
-          const int64_t idx = t0 + j * 1024;
-          s[j].x *= gs; s[j].y *= gs; s[j].z *= gs; s[j].w *= gs;
-          if (l2_in_grad) {                       // thinc: L2 joins the gradient BEFORE the clip norm
-            const float4 w4 = *(const float4*)(a.master + idx);
-            s[j].x += l2 * w4.x; s[j].y += l2 * w4.y; s[j].z += l2 * w4.z; s[j].w += l2 * w4.w;
-          }
-          if (keep_red) *(float4*)(a.red + idx) = s[j];
-          acc += s[j].x * s[j].x + s[j].y * s[j].y + s[j].z * s[j].z + s[j].w * s[j].w;
+        for (int j = 0; j < 4; ++j) if (ok[j]) {
+          s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w;
+          st_relaxed_sys_v4(src + j * 1024, zero_after(v[j]));
         }
       }
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t += s_part[i];
-      atomicAdd(a.norms_sq + k, t);
+    for (int j = 0; j < 4; ++j) {
+      if (ok[j]) {
+        const int64_t idx = t0 + j * 1024;
+        s[j].x *= gs; s[j].y *= gs; s[j].z *= gs; s[j].w *= gs;
+        if (l2_in_grad) {                       // thinc: L2 joins the gradient BEFORE the clip norm
+          const float4 w4 = *(const float4*)(a.master + idx);
+          s[j].x += l2 * w4.x; s[j].y += l2 * w4.y; s[j].z += l2 * w4.z; s[j].w += l2 * w4.w;
+        }
+        if (keep_red) *(float4*)(a.red + idx) = s[j];
+        acc += s[j].x * s[j].x + s[j].y * s[j].y + s[j].z * s[j].z + s[j].w * s[j].w;
+      }
     }
-    __syncthreads();
   }
-  uint32_t* bar = a.bar + 2 * bkt;
-  if (n_items > 0) {
-    if (!grid_barrier(bar, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 2); return; }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_part[i];
+    atomicAdd(a.norms_sq + k, t);
   }
+}
 
-  if (a.test_delay_ns) {          // test hook: a slow owner (the consumers' gates must hold them back)
-    if (threadIdx.x == 0) {
-      const uint64_t t0 = globaltimer_ns();
-      while (globaltimer_ns() - t0 < a.test_delay_ns) __nanosleep(1000);
+__global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) {
+  const int W = a.world, rank = a.rank, bkt = a.bucket;
+  const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;
+  const int n_items = a.blk_end - a.blk_begin;
+  __shared__ int s_last;
+  if (n_items > 0 && *(const volatile int32_t*)a.error == 0) {
+    if (a.test_delay_ns) {          // test hook: a slow owner (the consumers' gates must hold them back)
+      if (threadIdx.x == 0) {
+        const uint64_t t0 = globaltimer_ns();
+        while (globaltimer_ns() - t0 < a.test_delay_ns) __nanosleep(1000);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  // ---------------- phase 2: clip + optimizer + publish bf16 weights to all ranks ------------
-  const float t = (float)(*(const volatile int32_t*)a.step + 1);
-  const float b1t = powf(b1, t), b2t = powf(b2, t);
-  const float fix1 = 1.f - b1t, fix2 = 1.f - b2t;
-  float lr_t = lr * sqrtf(fix2) / fix1;                    // Adam: bias correction folded into the rate
-  bool rect = true;
-  if (a.opt_mode == kOptRAdam) {
-    const float sma_max = 2.f / (1.f - b2) - 1.f;
-    const float sma = sma_max - 2.f * t * b2t / fix2;
-    rect = sma >= 5.f;
-    lr_t = rect ? lr * sqrtf(fix2 * (sma - 4.f) / (sma_max - 4.f) * (sma - 2.f) / sma * sma_max / (sma_max - 2.f)) / fix1
-                : lr / fix1;
-  }
-  // thinc's update_averages: decay = min((1 + t) / (10 + t), 0.9999); ema -= (1 - decay) * (ema - w)
-  const float avg_mix = 1.f - fminf((1.f + t) / (10.f + t), 0.9999f);
-  for (int b = a.blk_begin + blockIdx.x; b < a.blk_end; b += gridDim.x) {
+    const int64_t s0 = a.shard_start;
+    float* my_grad = a.grad[rank];
+    const float lr = a.hyper[0], b1 = a.hyper[1], b2 = a.hyper[2], eps = a.hyper[3], clip = a.hyper[4], l2 = a.hyper[5];
+    const bool wd = a.hyper[6] != 0.f;
+    const float gs = a.hyper[7];
+    const bool keep_red = (W > 1) || gs != 1.f || ((l2 != 0.f) && !wd);
+    // ---------------- phase 2: clip + optimizer + publish bf16 weights to all ranks ----------
+    const float t = (float)(*(const volatile int32_t*)a.step + 1);
+    const float b1t = powf(b1, t), b2t = powf(b2, t);
+    const float fix1 = 1.f - b1t, fix2 = 1.f - b2t;
+    float lr_t = lr * sqrtf(fix2) / fix1;                    // Adam: bias correction folded into the rate
+    bool rect = true;
+    if (a.opt_mode == kOptRAdam) {
+      const float sma_max = 2.f / (1.f - b2) - 1.f;
+      const float sma = sma_max - 2.f * t * b2t / fix2;
+      rect = sma >= 5.f;
+      lr_t = rect ? lr * sqrtf(fix2 * (sma - 4.f) / (sma_max - 4.f) * (sma - 2.f) / sma * sma_max / (sma_max - 2.f)) / fix1
+                  : lr / fix1;
+    }
+    // thinc's update_averages: decay = min((1 + t) / (10 + t), 0.9999); ema -= (1 - decay) * (ema - w)
+    const float avg_mix = 1.f - fminf((1.f + t) / (10.f + t), 0.9999f);
+    const int b = a.blk_begin + blockIdx.x;
     const int k = a.blk_key[b];
     const int64_t base = a.key_off[k] + (int64_t)a.blk_off[b] * kCommChunk;
     const int64_t end = a.key_off[k] + a.key_len[k];
@@ -222,10 +213,8 @@ __global__ void __launch_bounds__(256, 3) fused_bucket_kernel(FusedCommArgs a) {
       const float norm = sqrtf(a.norms_sq[k]);
       if (norm >= clip) scale = clip / fmaxf(norm, 1e-30f);
     }
-    // two passes of two vectors each: 2 x 5 independent 16-byte loads in flight per thread, and few
-    // enough live registers (<= 85) that a CTA of this kernel fits on an SM NEXT TO a CTA of the
-    // tcgen05 GEMM kernels (320 threads x 128 registers) - that co-residency is what lets the
-    // exchange of a finished bucket run under the rest of the backward pass
+    // two passes of two vectors each: 2 x 5 independent 16-byte loads in flight per thread and few
+    // enough live registers (80) that three CTAs fit on an SM - or one NEXT TO a tcgen05 GEMM CTA
     const float* gsrc = keep_red ? a.red : (my_grad + s0);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
@@ -292,27 +281,38 @@ __global__ void __launch_bounds__(256, 3) fused_bucket_kernel(FusedCommArgs a) {
       }
     }
   }
-  if (n_items > 0) {
-    __threadfence_system();
-    if (!grid_barrier(bar, tmo)) { if (threadIdx.x == 0) atomicExch(a.error, 3); return; }
+  // ---------------- the last CTA to finish publishes the bucket --------------------------------
+  // (stores -> fence -> counter: the classic last-block pattern; the publishing CTA's acquire of the
+  //  counter + its release of the flag order every CTA's weight / zero stores before the flag)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(a.bar + 2 * bkt, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
   }
-  // ---------------- published: the first consumer of these weights on each rank waits for this
-  if (blockIdx.x == 0) {
-    if (W > 1 && threadIdx.x < W) {
-      __threadfence_system();
-      st_release_sys(a.signal[threadIdx.x] + flag_pub_idx(bkt, rank), epoch);
-    }
-    for (int k = a.key_begin + (int)threadIdx.x; k < a.key_end; k += blockDim.x) a.norms_sq[k] = 0.f;
-    if (a.last && threadIdx.x == 0) {
-      *a.step = *(const volatile int32_t*)a.step + 1;
-      __threadfence();
-      *(volatile uint32_t*)a.epoch = epoch;
-    }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) a.bar[2 * bkt] = 0u;
+  if (W > 1 && threadIdx.x < W) st_release_sys(a.signal[threadIdx.x] + flag_pub_idx(bkt, rank), epoch);
+  for (int k = a.key_begin + (int)threadIdx.x; k < a.key_end; k += blockDim.x) a.norms_sq[k] = 0.f;
+  if (a.last && threadIdx.x == 0) {
+    *a.step = *(const volatile int32_t*)a.step + 1;
+    __threadfence();
+    *(volatile uint32_t*)a.epoch = epoch;
   }
 }
 
 cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s) {
-  fused_bucket_kernel<<<grid, 256, 0, s>>>(a);
+  const int n_items = a.blk_end - a.blk_begin;
+  const int g = n_items > 0 ? n_items : 1;
+  (void)grid;
+  if (n_items > 0 || a.world > 1) {
+    bucket_reduce_kernel<<<g, 256, 0, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  bucket_update_kernel<<<g, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

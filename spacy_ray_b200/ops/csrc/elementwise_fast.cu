@@ -448,7 +448,7 @@ void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool pe
 // A block covers a contiguous row range; thread = (row sub-group, 16-byte column vector).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
-                                                          int T, int C, int ld, int rows_per_block) {
+                                                          int T, int C, int ld, int rows_per_block, int n_valid) {
   extern __shared__ float cs_red[];                 // [rsubs][C]
   const int c8 = C / 8;
   const int rsubs = blockDim.x / c8;
@@ -481,11 +481,11 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float t = 0.f;
     for (int j = 0; j < rsubs; ++j) t += cs_red[(size_t)j * C + c];
-    if (t != 0.f) atomicAdd(out + c, t);
+    if (t != 0.f && c < n_valid) atomicAdd(out + c, t);      // columns >= n_valid are pitch padding
   }
 }
 
-bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, cudaStream_t s) {
+bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, int n_valid, cudaStream_t s) {
   if (C % 8 != 0 || C / 8 > 256 || C <= 0 || T <= 0 || ld % 8 != 0) return false;
   const int c8 = C / 8, rsubs = 256 / c8;
   int blocks = 148 * 4;
@@ -493,8 +493,36 @@ bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, cud
   if (rows_per_block < 4 * rsubs) rows_per_block = 4 * rsubs;
   blocks = (T + rows_per_block - 1) / rows_per_block;
   const size_t smem = sizeof(float) * (size_t)rsubs * C;     // <= 256 * 8 * 4 = 8 KB
-  colsum_bf16_kernel<<<blocks, 256, smem, s>>>((const __nv_bfloat16*)X, out, T, C, ld, rows_per_block);
+  colsum_bf16_kernel<<<blocks, 256, smem, s>>>((const __nv_bfloat16*)X, out, T, C, ld, rows_per_block,
+                                               n_valid > 0 ? n_valid : C);
   return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// dst (bf16) = src (fp32); src = 0.  One pass: the fp32 scatter target of the transition backward
+// (dYf) is converted for the tcgen05 GEMMs that consume it AND left clear for the next step, so
+// the step needs neither a memset of the accumulator nor a separate dtype copy.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) f32_to_bf16_zero_kernel(float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                               size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float4* p = (float4*)(src + i * 8);
+    const float4 a = p[0], b = p[1];
+    bf16x8 o;
+    o.v[0] = f2bf(a.x); o.v[1] = f2bf(a.y); o.v[2] = f2bf(a.z); o.v[3] = f2bf(a.w);
+    o.v[4] = f2bf(b.x); o.v[5] = f2bf(b.y); o.v[6] = f2bf(b.z); o.v[7] = f2bf(b.w);
+    *(bf16x8*)(dst + i * 8) = o;
+    p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+void launch_f32_to_bf16_zero(float* src, void* dst, size_t n, cudaStream_t s) {
+  const size_t n8 = n / 8;
+  if (n8 == 0) return;
+  size_t blocks = (n8 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  f32_to_bf16_zero_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, (__nv_bfloat16*)dst, n8);
 }
 
 }  // namespace srb

@@ -57,7 +57,9 @@ bool try_launch_linear_softmax_xent(const void* X, const void* W, const void* b,
                                     int64_t* guesses, float* loss, int Tp, int w, int nC, int ldd, cudaStream_t s);
 
 // out[c] += sum_t X[t, c]  (bf16 in, fp32 accumulate); false = shape not supported.
-bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, cudaStream_t s);
+bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, int n_valid, cudaStream_t s);
+// dst (bf16, n elements) = src (fp32); src = 0   (n % 8 == 0)
+void launch_f32_to_bf16_zero(float* src, void* dst, size_t n, cudaStream_t s);
 
 // K4 helpers for the library-GEMM path: materialised window / its transpose-add.
 void launch_seq2col(const void* X, void* Xw, int Tp, int nI, cudaStream_t s);

@@ -3,8 +3,8 @@
 What the reference does with hundreds of Ray RPCs per step (gradient push
 ``/root/reference/spacy_ray/proxies.py:102-104``, owner-side optimizer ``proxies.py:126-128``,
 parameter push ``proxies.py:71-75``, lazy adoption at the next read ``proxies.py:111-118``)
-becomes a handful of launches of ONE sm_100a kernel (``ops/csrc/comm_kernels.cu``,
-``fused_bucket_kernel``):
+becomes a handful of launches of one sm_100a kernel pair (``ops/csrc/comm_kernels.cu``,
+``bucket_reduce_kernel`` + ``bucket_update_kernel``):
 
 * the flat gradient bucket is cut into a few **buckets in the order the backward pass
   completes them** (learned from the ``inc_grad`` sequence of the first step);
@@ -312,15 +312,9 @@ class FusedSymmComm:
                     self._ptr_bucket[int(v.data_ptr())] = b
 
     def _grid_for(self, b: int) -> int:
+        """One CTA per 4096-element work item (the launcher derives the grid from the item range)."""
         bb, be, _kb, _ke = self.tables["ranges"][b]
-        n = be - bb
-        if self._grid_override:
-            return max(1, min(int(self._grid_override), max(n, 1)))
-        # persistent, co-resident grid (the kernel has device-wide barriers).  Buckets that run under
-        # the backward pass share each SM with a CTA of the tcgen05 GEMM kernels (registers allow one
-        # CTA of this kernel next to one of those); the last bucket has the device to itself.
-        per_sm = 2 if b == self.plan.n - 1 else 1
-        return max(1, min(per_sm * self._sms, n))
+        return max(1, be - bb)
 
     # ------------------------------------------------------------------ the step
     def begin_step(self, proxy, overlap: bool) -> None:
@@ -379,7 +373,7 @@ class FusedSymmComm:
                 bool(b == self.plan.n - 1), self.rank, self._grid_for(b), int(self.opt_mode), float(self.timeout_s),
                 int(self.test_delay_us),
             )
-        self.launches += 1
+        self.launches += 2 if (be > bb or self.world_size > 1) else 1     # reduce + update kernels
 
     def fused_step(self, proxy) -> None:
         if self.master is None:

@@ -255,7 +255,36 @@ class Language:
 
     def make_batch(self, docs: Sequence[Doc], *, capacity_rows: Optional[int] = None) -> TokenBatch:
         ops = get_current_ops()
-        return make_token_batch([d.to_array() for d in docs], ops.device, capacity_rows=capacity_rows)
+        batch = make_token_batch([d.to_array() for d in docs], ops.device, capacity_rows=capacity_rows)
+        vectors = self.vectors
+        if vectors is not None:
+            # static vectors: each token's row in the table (-1 = out of vocabulary), padded-ragged layout
+            import numpy as np
+
+            from ..nn.batch import to_device
+
+            rows = np.full((batch.n_rows,), -1, dtype=np.int64)
+            for doc, s in zip(docs, batch.starts):
+                r = doc.user_data.get("vec_rows")
+                if r is None or doc.user_data.get("vec_table") is not vectors:
+                    r = vectors.rows_for(doc.words)
+                    doc.user_data["vec_rows"], doc.user_data["vec_table"] = r, vectors
+                rows[s:s + len(r)] = r
+            batch.extra["vec_rows"] = to_device(rows, ops.device)
+        return batch
+
+    # ---- static vectors -------------------------------------------------------
+    @property
+    def vectors(self):
+        from ..nn.staticvectors import get_vectors
+
+        return get_vectors()
+
+    def load_vectors(self, path) -> None:
+        """``[initialize] vectors = <path>``: .npz (``keys`` | ``words`` + ``data``) or word2vec text."""
+        from ..nn.staticvectors import Vectors, set_vectors
+
+        set_vectors(Vectors.from_disk(path))
 
     # ---- training -----------------------------------------------------------
     def initialize(self, get_examples: Optional[Callable[[], Iterable[Example]]] = None, *, sgd=None):
@@ -268,7 +297,10 @@ class Language:
                 cache.extend(get_examples())
             return cache
 
-        init_cfg = (self._config.interpolate().get("initialize", {}) or {}).get("components", {}) or {}
+        init_all = self._config.interpolate().get("initialize", {}) or {}
+        if init_all.get("vectors"):
+            self.load_vectors(init_all["vectors"])
+        init_cfg = init_all.get("components", {}) or {}
         for name, comp in self._components:
             if hasattr(comp, "initialize"):
                 kwargs = dict(init_cfg.get(name, {}) or {})
@@ -391,15 +423,23 @@ class Language:
         (path / "vocab" / "strings.json").write_text(json.dumps(
             sorted({l for _, c in self._components for l in getattr(c, "labels", [])})
         ))
+        if self.vectors is not None and self._uses_static_vectors():
+            self.vectors.to_disk(path / "vocab" / "vectors.npz")
         for name, comp in self._components:
             if name in exclude or not hasattr(comp, "to_disk"):
                 continue
             comp.to_disk(path / name)
 
+    def _uses_static_vectors(self) -> bool:
+        return any(node.name == "staticvectors" for _n, c in self._components if hasattr(c, "model")
+                   for node in c.model.walk())
+
     def from_disk(self, path: Union[str, Path], *, exclude: Sequence[str] = ()) -> "Language":
         path = Path(path)
         if (path / "meta.json").exists():
             self._meta = json.loads((path / "meta.json").read_text())
+        if (path / "vocab" / "vectors.npz").exists():
+            self.load_vectors(path / "vocab" / "vectors.npz")
         for name, comp in self._components:
             if name in exclude or not hasattr(comp, "from_disk"):
                 continue

@@ -40,6 +40,11 @@ class TransitionGold:
     labels: Optional[List[List[int]]] = None
     heads_flat: Optional[torch.Tensor] = None   # (T,) int32 doc-relative gold heads (self = root, -1 = missing)
     labels_flat: Optional[torch.Tensor] = None  # (T,) int32 gold labels (-1 = unknown)
+    # training only: advance each state by the oracle's action (BILUO: the single zero-cost action when
+    # there is one; arc-eager: the first minimum-cost action) instead of the model's arg-max.  Makes
+    # two implementations follow identical trajectories, so their losses / gradients can be compared
+    # tightly (tests); the default (False) is spaCy's behaviour.
+    teacher_forced: bool = False
 
 
 @dataclass
@@ -243,9 +248,12 @@ def _biluo_steps_reference(system: BiluoSystem, Yf, params, batch, gold, is_trai
             which_l.append(which.to(torch.uint8))
             hid_l.append(hid)
             d_l.append(d)
+        actions_flat[(tok_off + st["i"])[idx]] = guess              # the record is always the model's prediction
+        if is_train and have_gold and getattr(gold, "teacher_forced", False):
+            ga_ok = (ga >= 0) & valid.gather(1, ga.clamp(min=0).unsqueeze(1)).squeeze(1)
+            guess = torch.where(ga_ok, ga, guess)
         full_guess = torch.zeros(B, dtype=torch.int64, device=dev)
         full_guess[idx] = guess
-        actions_flat[(tok_off + st["i"])[idx]] = guess
         st = system.batch_apply(st, full_guess, gold.actions if have_gold else None, gold.offsets if have_gold else None)
     rec: Dict[str, Any] = {"actions_flat": actions_flat, "n_steps": 0, "loss": loss}
     if feats_l:
@@ -298,6 +306,8 @@ def _arc_steps_reference(system: ArcEagerSystem, Yf, params, batch, gold, is_tra
             which_l.append(which.to(torch.uint8))
             hid_l.append(hid)
             d_l.append(d)
+            if getattr(gold, "teacher_forced", False):
+                guess = gold_mask.to(torch.int8).argmax(dim=1).tolist()      # first minimum-cost action
         for d, a in zip(live, guess):
             system.apply(states[d], int(a))
     rec: Dict[str, Any] = {"states": states, "n_steps": 0, "loss": loss,

@@ -463,6 +463,7 @@ class B200Ops(TorchOps):
             Yf.contiguous(), params["pad"].contiguous(), params["b"].contiguous(), params["Wu"].contiguous(),
             params["bu"].contiguous(), batch.doc_starts, batch.doc_lens, tok_off, gold_t, inv_active,
             batch.n_tokens, nO, nP, system.n_labels, bool(is_train and gold_t is not None),
+            bool(getattr(gold, "teacher_forced", False)),
         )
         self.launches += 1
         rec: Dict[str, Any] = {"actions_flat": actions, "loss": loss, "n_steps": 0}      # int32
@@ -500,6 +501,7 @@ class B200Ops(TorchOps):
             Yf.contiguous(), params["pad"].contiguous(), params["b"].contiguous(), params["Wu"].contiguous(),
             params["bu"].contiguous(), batch.doc_starts, batch.doc_lens, extra["tok_off"], extra["step_off"],
             gh, gl, batch.n_tokens, S_cap, nO, nP, 1.0 / max(1, batch.n_docs), train,
+            bool(getattr(gold, "teacher_forced", False)),
         )
         self.launches += 1
         rec: Dict[str, Any] = {"arc_heads": heads, "arc_labels": labels, "loss": loss, "n_steps": 0,

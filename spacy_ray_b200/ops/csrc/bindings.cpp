@@ -218,7 +218,7 @@ void adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, c10::optional<Tensor> 
 std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tensor& b, const Tensor& Wu,
                                 const Tensor& bu, const Tensor& doc_starts, const Tensor& doc_lens,
                                 const Tensor& tok_off, const c10::optional<Tensor>& gold, const Tensor& inv_active,
-                                int64_t n_tokens, int64_t nO, int64_t nP, int64_t n_labels, bool train) {
+                                int64_t n_tokens, int64_t nO, int64_t nP, int64_t n_labels, bool train, bool teacher) {
   SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
   TORCH_CHECK(nP == 2 && nO % 32 == 0 && (nO * nP) / 32 <= 8, "biluo_steps: hidden width/pieces not supported");
   c10::cuda::CUDAGuard guard(Yf.device());
@@ -243,7 +243,7 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   a.feats = feats.data_ptr<int32_t>(); a.which = which.data_ptr<uint8_t>(); a.hid = hid.data_ptr();
   a.d_scores = d_scores.data_ptr(); a.actions = actions.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
   a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad; a.ld_scores = (int)ldd;
-  a.n_labels = (int)n_labels; a.train = train ? 1 : 0;
+  a.n_labels = (int)n_labels; a.train = train ? 1 : 0; a.teacher = (train && teacher) ? 1 : 0;
   srb::launch_biluo_steps(a, cur_stream());
   return {feats, which, hid, d_scores, actions, loss};
 }
@@ -253,7 +253,7 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
                                     const Tensor& tok_off, const Tensor& step_off,
                                     const c10::optional<Tensor>& gold_heads, const c10::optional<Tensor>& gold_labels,
                                     int64_t n_tokens, int64_t n_steps_cap, int64_t nO, int64_t nP, double scale,
-                                    bool train) {
+                                    bool train, bool teacher) {
   SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
   c10::cuda::CUDAGuard guard(Yf.device());
   const int64_t nA = Wu.size(0);
@@ -283,6 +283,7 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   a.heads_out = heads.data_ptr<int32_t>(); a.labels_out = labels.data_ptr<int32_t>();
   a.n_steps = n_steps.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
   a.scale = (float)scale;
+  a.teacher = (train && teacher) ? 1 : 0;
   a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad; a.ld_scores = (int)ldd;
   a.train = train ? 1 : 0;
   TORCH_CHECK(srb::launch_arc_eager_steps(a, cur_stream()), "arc_eager_steps: unsupported hidden width / pieces / #actions");
@@ -313,8 +314,8 @@ TORCH_LIBRARY(srb, m) {
   m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");
   m.def("linear_softmax_xent(Tensor X, Tensor W, Tensor b, Tensor labels) -> Tensor[]");
   m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
-  m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train) -> Tensor[]");
-  m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train) -> Tensor[]");
+  m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train, bool teacher) -> Tensor[]");
+  m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train, bool teacher) -> Tensor[]");
   m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
   srb::register_gemm_ops(m);
   srb::register_comm_ops(m);

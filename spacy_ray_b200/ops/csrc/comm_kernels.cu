@@ -64,44 +64,56 @@ __device__ __forceinline__ void multimem_st_v2_b32(void* mc, uint32_t a, uint32_
                "f"(__uint_as_float(b))
                : "memory");
 }
-// A zero vector that the compiler cannot hoist above the load that produced `v`: the store that
-// clears a gradient word must not be issued before the (switch-side) read of that word returned.
+// A zero vector that neither nvcc nor ptxas can materialise before the load that produced `v` has
+// returned: x - x is +0 for every finite x and NaN otherwise (so it cannot be constant-folded - an
+// integer `and 0` was folded to RZ by ptxas and the store lost its dependency), and min(NaN, 0) = 0.
+// The store that clears a gradient word must not be issued before the (switch-side) read of that
+// word has completed; the data dependency is what enforces it.
 __device__ __forceinline__ float4 zero_after(const float4& v) {
-  uint32_t z;
-  asm volatile("and.b32 %0, %1, 0;" : "=r"(z) : "r"(__float_as_uint(v.x)));
-  const float f = __uint_as_float(z);
-  return make_float4(f, f, f, f);
+  return make_float4(fminf(v.x - v.x, 0.f), fminf(v.y - v.y, 0.f), fminf(v.z - v.z, 0.f), fminf(v.w - v.w, 0.f));
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // One work item (= one 4096-element chunk of one owned key) per CTA, two launches per bucket:
-//   bucket_reduce_kernel  phases 0 + 1 (flags, reduce + clear, per-key sum of squares)
+//   bucket_signal_wait_kernel  phase 0 (one warp: my grad-ready flag out, everybody's in)
+//   bucket_reduce_kernel  phase 1 (reduce + clear, per-key sum of squares)
 //   bucket_update_kernel  phase 2 (clip, optimizer, weight stores) + publication by the last CTA
 // The kernel boundary is the "all of this key's partial norms are in" barrier.  No device-wide
 // barrier inside a kernel means no co-residency requirement: the grids can be as large as the
 // bucket, and the CTAs (80 registers x 256 threads) slot in next to the CTAs of whatever the
 // backward pass is running (a tcgen05 GEMM CTA leaves room for exactly one of them per SM).
-__global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) {
+// phase 0 as its own ONE-WARP kernel: "my gradients of bucket b are complete" -> every rank's signal
+// page, then wait for everybody else's.  The wait can last as long as the slowest rank's backward
+// pass; doing it in the reduce kernel would park hundreds of spinning CTAs on the SMs and starve
+// this rank's own backward GEMMs of registers exactly while they should be running.
+__global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a) {
   const int W = a.world, rank = a.rank, bkt = a.bucket;
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
-  const int n_items = a.blk_end - a.blk_begin;
-  __shared__ int s_fail;
-  __shared__ float s_part[8];
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
-  // ---------------- phase 0: every rank's gradients of this bucket are complete --------------
-  if (W > 1) {
-    if (blockIdx.x == 0 && threadIdx.x < W) {
-      __threadfence_system();
-      st_release_sys(a.signal[threadIdx.x] + flag_grad_idx(bkt, rank), epoch);
-    }
-    if (n_items == 0) return;
-    if (threadIdx.x < W) {
-      if (!wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, threadIdx.x), epoch, a.timeout_ns)) s_fail = 1;
-    }
-    __syncthreads();
-    if (s_fail) { if (threadIdx.x == 0) atomicExch(a.error, 1); return; }
+  const int lane = threadIdx.x;
+  if (W > 1 && lane < W) {
+    fence_acq_rel_sys();
+    st_release_sys(a.signal[lane] + flag_grad_idx(bkt, rank), epoch);
   }
-  if (n_items == 0) return;
+  if (a.blk_end - a.blk_begin == 0) {
+    // nothing of this bucket is mine: there is nothing to wait for, and nothing to publish but the flag
+    // (consumers wait for every rank's flag of a bucket)
+    if (W > 1 && lane < W) st_release_sys(a.signal[lane] + flag_pub_idx(bkt, rank), epoch);
+    if (a.last && lane == 0) {             // ... except, for the step's last bucket, the counters
+      *a.step = *(const volatile int32_t*)a.step + 1;
+      __threadfence();
+      *(volatile uint32_t*)a.epoch = epoch;
+    }
+    return;
+  }
+  if (lane < W && !wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, lane), epoch, a.timeout_ns)) atomicExch(a.error, 1);
+}
+
+__global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) {
+  const int W = a.world, rank = a.rank;
+  const int n_items = a.blk_end - a.blk_begin;
+  __shared__ float s_part[8];
+  if (n_items == 0 || *(const volatile int32_t*)a.error != 0) return;
   const int64_t s0 = a.shard_start;
   float* my_grad = a.grad[rank];
   const float l2 = a.hyper[5];
@@ -284,15 +296,16 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
   // ---------------- the last CTA to finish publishes the bucket --------------------------------
   // (stores -> fence -> counter: the classic last-block pattern; the publishing CTA's acquire of the
   //  counter + its release of the flag order every CTA's weight / zero stores before the flag)
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();                        // every thread's stores are ordered before thread 0's fence (CTA scope) ...
   if (threadIdx.x == 0) {
+    if (W > 1) fence_acq_rel_sys();       // ... which releases them at system scope: ONE fence per CTA, not 256
+    else fence_acq_rel_gpu();
     const uint32_t prev = atomicAdd(a.bar + 2 * bkt, 1u);
     s_last = (prev == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  if (W > 1) fence_acq_rel_sys(); else fence_acq_rel_gpu();
   if (threadIdx.x == 0) a.bar[2 * bkt] = 0u;
   if (W > 1 && threadIdx.x < W) st_release_sys(a.signal[threadIdx.x] + flag_pub_idx(bkt, rank), epoch);
   for (int k = a.key_begin + (int)threadIdx.x; k < a.key_end; k += blockDim.x) a.norms_sq[k] = 0.f;
@@ -305,14 +318,16 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
 
 cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s) {
   const int n_items = a.blk_end - a.blk_begin;
-  const int g = n_items > 0 ? n_items : 1;
   (void)grid;
-  if (n_items > 0 || a.world > 1) {
-    bucket_reduce_kernel<<<g, 256, 0, s>>>(a);
+  if (a.world > 1 || n_items == 0) {
+    bucket_signal_wait_kernel<<<1, 32, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || n_items == 0) return e;      // a rank that owns nothing of the bucket is done
   }
-  bucket_update_kernel<<<g, 256, 0, s>>>(a);
+  bucket_reduce_kernel<<<n_items, 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  bucket_update_kernel<<<n_items, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

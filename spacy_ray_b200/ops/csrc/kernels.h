@@ -104,6 +104,7 @@ struct BiluoArgs {
   int32_t* actions;            // (T)
   float* loss;                 // scalar accumulator
   int B, nO, nP, nA, nA_pad, n_labels, train;
+  int teacher;                 // train only: advance by the oracle's action (when it names one) instead of the arg-max
 };
 void launch_biluo_steps(BiluoArgs a, cudaStream_t s);
 // Scatter d_hid (T, nO) through `which` into dYf (Tp, nF*nOP) fp32, dpad (nF, nOP), db (nOP).
@@ -135,6 +136,7 @@ struct ArcArgs {
   float* loss;
   float scale;                 // gradient scale per step (1 / #docs)
   int B, nO, nP, nA, nA_pad, train;
+  int teacher;                 // train only: advance by the first minimum-cost action instead of the arg-max
 };
 bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s);
 int arc_eager_max_doc_len();

@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
       if (i < 64) g = __shfl_sync(0xffffffffu, i < 32 ? g_lo : g_hi, i & 31);
       else g = A.gold[tok];
     }
+    int ga = -1;
     if (A.train) {
       // oracle: a single zero-cost action, or -1 = every valid action is zero-cost
-      int ga = -1;
       if (have_gold && g >= 0) {
         const int gk = g > 0 ? ((g - 1) & 3) : -1, gl = g > 0 ? ((g - 1) >> 2) : -1;
         if (!is_open) ga = (gk == -1 || gk == 0 || gk == 3) ? g : 0;
@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoA
       }
     }
     if (lane == 0) A.actions[tok] = arg;
-    // ---- advance by the predicted action ------------------------------------------------
+    // ---- advance by the predicted action (teacher forcing: by the oracle's, when it names one) --
+    if (A.teacher && ga >= 0) arg = ga;
     const int kind = arg > 0 ? ((arg - 1) & 3) : -1;
     if (kind == 0) {
       ent_start = i; ent_label = (arg - 1) >> 2; ent_ok = (g == arg);

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
       const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
       if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
     }
+    int teach = -1;
     if (A.train) {
       // ---- dynamic oracle ------------------------------------------------------------------
       int cnt_stack_b0 = 0, cnt_buf_s0 = 0;
@@ -195,6 +196,14 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      if (A.teacher) {                 // first minimum-cost valid action (what the host loop follows too)
+        int ga = 1 << 20;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) if (ok[j] && cost[j] == cmin) ga = min(ga, lane + 32 * j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ga = min(ga, __shfl_xor_sync(0xffffffffu, ga, o));
+        if (ga < (1 << 20)) teach = ga;
+      }
       float e[NJ], eg[NJ];
       float sum = 0.f, gsum = 0.f;
 #pragma unroll
@@ -221,8 +230,9 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
         A.feats[rec * 8 + lane] = fv >= 0 ? row0 + fv : -1;
       }
     }
+    if (teach >= 0) arg = teach;
     if (A.history && lane == 0) A.history[rec] = arg;
-    // ---- apply the predicted action -------------------------------------------------------------
+    // ---- apply the predicted (or teacher-forced) action ----------------------------------------
     __syncwarp();      // every lane has finished reading the state (oracle ballots) before lane 0 mutates it
     if (lane == 0) {
       if (arg == 0) { S.stack[sp] = b; S.in_stack[b] = 1; }

@@ -182,7 +182,7 @@ class FusedSymmComm:
         self.ops = ops
         self.timeout_s = timeout_s
         self.launches = 0
-        self.n_buckets_target = int(n_buckets or os.environ.get("SRB_COMM_BUCKETS", 6))
+        self.n_buckets_target = int(n_buckets or os.environ.get("SRB_COMM_BUCKETS", 4))
         self.overlap = os.environ.get("SRB_COMM_OVERLAP", "1") != "0"
         self.terminal_wait = os.environ.get("SRB_GATE_ALWAYS", "0") == "1"    # debugging: round-1 behaviour
         self.test_delay_us = 0               # tests: make this rank a late publisher (see tests/mgpu_worker.py)
@@ -311,6 +311,14 @@ class FusedSymmComm:
                 if v is not None:
                     self._ptr_bucket[int(v.data_ptr())] = b
 
+    def kernels_for(self, b: int) -> int:
+        """Launches bucket ``b`` costs on this rank: [signal/wait (one warp; only with peers)] + reduce +
+        update; a rank that owns nothing of the bucket only signals."""
+        bb, be, _kb, _ke = self.tables["ranges"][b]
+        if be == bb:
+            return 1
+        return 2 + (1 if self.world_size > 1 else 0)
+
     def _grid_for(self, b: int) -> int:
         """One CTA per 4096-element work item (the launcher derives the grid from the item range)."""
         bb, be, _kb, _ke = self.tables["ranges"][b]
@@ -373,7 +381,7 @@ class FusedSymmComm:
                 bool(b == self.plan.n - 1), self.rank, self._grid_for(b), int(self.opt_mode), float(self.timeout_s),
                 int(self.test_delay_us),
             )
-        self.launches += 2 if (be > bb or self.world_size > 1) else 1     # reduce + update kernels
+        self.launches += self.kernels_for(b)
 
     def fused_step(self, proxy) -> None:
         if self.master is None:

@@ -39,8 +39,8 @@ def _close(a, b, rtol, atol, name=""):
     a, b = a.float(), b.float()
     err = (a - b).abs()
     tol = atol + rtol * b.abs()
-    bad = (err > tol).float().mean().item()
-    assert bad < 1e-3, f"{name}: {bad:.4%} elements out of tolerance, max err {err.max().item():.4g}"
+    bad = int((err > tol).sum().item())
+    assert bad == 0, f"{name}: {bad} of {err.numel()} elements out of tolerance, max err {err.max().item():.4g}"
 
 
 # ---------------------------------------------------------------------------- K1
@@ -362,6 +362,64 @@ def test_biluo_kernel_matches_reference_loop(ops, ref):
     _close(g["dWu"], gr["dWu"], 3e-2, 5e-2, "dWu")
 
 
+def test_biluo_kernel_teacher_forced_matches_reference_tightly(ops):
+    """Teacher forcing makes the kernel and the fp32 reference loop walk the same (gold) trajectory,
+    so loss and every row of d_scores are compared at bf16 resolution - not the 25 % / 97 % of the
+    free-running comparison above."""
+    from spacy_ray_b200.models.transition_model import TransitionGold, _biluo_steps_reference
+    from spacy_ray_b200.models.transitions import BiluoSystem, spans_to_biluo_actions
+    from spacy_ray_b200.nn.batch import make_token_batch
+    import random
+
+    rng = random.Random(3)
+    torch.manual_seed(9)
+    L = 6
+    system = BiluoSystem([f"L{i}" for i in range(L)])
+    lens = [rng.randint(1, 70) for _ in range(45)]          # beyond 64 tokens: gold comes from memory, not registers
+    batch = make_token_batch([np.ones((n, 4), dtype=np.uint64) for n in lens], "cuda:0")
+    golds = []
+    for n in lens:
+        spans, t = [], 0
+        while t < n:
+            if rng.random() < 0.3:
+                ln = min(n - t, rng.randint(1, 4))
+                spans.append((t, t + ln, rng.randint(0, L - 1)))
+                t += ln
+            t += 1
+        golds.append(spans_to_biluo_actions(n, spans))
+    flat = torch.tensor([a for g in golds for a in g], device="cuda")
+    offs = torch.tensor([sum(lens[:i]) for i in range(len(lens))], device="cuda")
+    gold = TransitionGold(actions=flat, offsets=offs, teacher_forced=True)
+    nF, nO, nP = 3, 64, 2
+    Tp = batch.n_rows
+    Yf = (torch.randn(Tp, nF * nO * nP, device="cuda") * batch.mask).bfloat16()
+    params = {
+        "pad": (torch.randn(nF, nO * nP, device="cuda") * 0.3).bfloat16(),
+        "b": (torch.randn(nO * nP, device="cuda") * 0.3).bfloat16(),
+        "Wu": (torch.randn(system.n_actions, nO, device="cuda") * 0.3).bfloat16(),
+        "bu": (torch.randn(system.n_actions, device="cuda") * 0.1).bfloat16(),
+        "nF": nF, "nO": nO, "nP": nP,
+    }
+    rec = ops.transition_steps(system, Yf, params, batch, gold, True)
+    pf = {k: (v.float() if torch.is_tensor(v) else v) for k, v in params.items()}
+    rref = _biluo_steps_reference(system, Yf.float(), pf, batch, gold, True)
+    torch.cuda.synchronize()
+    assert abs(float(rec["loss"]) - float(rref["loss"])) <= 1e-2 * max(float(rref["loss"]), 1e-9)
+    # one record per token in both; key both by the padded row of the token (feature slot 0)
+    A = system.n_actions
+    key_k = rec["feats"][:, 0].long()
+    key_r = rref["feats"][:, 0].long()
+    assert torch.equal(torch.sort(key_k).values, torch.sort(key_r).values)
+    dk = rec["d_scores"].float()[:, :A][torch.argsort(key_k)]
+    dr = rref["d_scores"][torch.argsort(key_r)]
+    err = (dk - dr).abs()
+    assert float(err.max()) < 1e-2 * float(dr.abs().max()) + 1e-3, float(err.max())
+    assert torch.equal(rec["feats"][torch.argsort(key_k)].long(), rref["feats"][torch.argsort(key_r)].long())
+    hk = rec["hid"].float()[torch.argsort(key_k)]
+    hr = rref["hid"][torch.argsort(key_r)]
+    assert float((hk - hr).abs().max()) < 2e-2 * float(hr.abs().max())
+
+
 # ---------------------------------------------------------------------------- end to end
 def test_gpu_training_loss_goes_down_and_uses_native_kernels():
     from conftest import multi_cfg
@@ -384,7 +442,7 @@ def test_gpu_training_loss_goes_down_and_uses_native_kernels():
         w.proxy.step()
         hist.append(float(losses["ner"]))
     w.proxy.comm.check()
-    assert ops.launches > 0 and w.proxy.comm.launches == 100 * 2 * w.proxy.comm.plan.n
+    assert ops.launches > 0 and w.proxy.comm.launches == 100 * sum(w.proxy.comm.kernels_for(b) for b in range(w.proxy.comm.plan.n))
     assert sum(hist[-5:]) < 0.5 * sum(hist[:5]), hist[::6]
     scores = nlp.evaluate(exs[:100])
     assert scores["ents_f"] > 0.25, scores

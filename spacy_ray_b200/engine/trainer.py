@@ -223,11 +223,24 @@ class Trainer:
                     return f"{name}: hidden_width/maxout_pieces outside the BILUO kernel's range"
                 if kind == "parser" and (nO % 32 or nO // 32 not in (1, 2, 4) or nP not in (2, 3) or nA > 192):
                     return f"{name}: hidden_width/maxout_pieces/labels outside the arc-eager kernel's range"
-                if kind == "parser" and max_len is not None and max_len > 128:
-                    return f"{name}: documents longer than 128 tokens"
+                if kind == "parser" and max_len is not None:
+                    cap = Trainer.parser_doc_capacity(comp)
+                    if max_len > cap:
+                        return f"{name}: documents longer than {cap} tokens"
         if all(kind == "tok2vec" for _, _, kind in heads):
             return "no head component"
         return None
+
+    @staticmethod
+    def parser_doc_capacity(comp) -> int:
+        """Longest doc the device arc-eager kernel can hold for this parser head (its per-warp state
+        lives in shared memory next to the staged upper-layer weights)."""
+        ops = comp.model.ops
+        fn = getattr(ops, "arc_eager_capacity", None)
+        if fn is None:
+            return 128
+        _nF, nO, nP, _nI = comp.model.get_ref("lower").get_param("W").shape
+        return int(fn(int(nO), int(nP), int(comp.system.n_actions)))
 
     def __init__(self, nlp, proxy, examples: Sequence[Any], *, docs_per_batch: int, dropout: float = 0.1,
                  component: Optional[str] = None, use_graphs: bool = True, bucket_rows: int = 256,
@@ -242,9 +255,10 @@ class Trainer:
         self.dropout = float(dropout)
         self.B = int(docs_per_batch)
         self.store = ExampleStore(examples, self.heads)
-        # the arc-eager kernel keeps a document's state in shared memory sized for 128 tokens: longer
-        # documents stay in the store but batches containing one are handed back to the generic path
-        self.max_doc_len = 128 if any(k == "parser" for _n, _c, k in self.heads) else None
+        # the arc-eager kernel keeps a document's state in shared memory (several hundred tokens fit):
+        # longer documents stay in the store but batches containing one are handed back to the generic path
+        caps = [self.parser_doc_capacity(c) for _n, c, k in self.heads if k == "parser"]
+        self.max_doc_len = min(caps) if caps else None
         cap_len = self.store.max_len if self.max_doc_len is None else min(self.store.max_len, self.max_doc_len)
         why = self.unsupported_reason(nlp, cap_len)
         if why is not None:
@@ -345,6 +359,7 @@ class Trainer:
         )
         tb.extra["tok_off"] = dv.tok_off
         tb.extra["inv_active"] = dv.inv_active
+        tb.extra["max_len"] = int(self.lay.lmax)
         if self.host_grouping:
             n_attr = self.lay.n_attr
             tb.extra["embed_perm"] = dv.perm[: n_attr * rows].view(n_attr, rows)

@@ -93,6 +93,7 @@ class B200Ops(TorchOps):
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self._arc_cap: Dict[tuple, int] = {}
         self.max_rows_hint = 0               # engine.Trainer: largest row count any captured step will use
         # C2: consumer-side gates.  ``FusedSymmComm`` installs itself here; kernels that read
         # parameters ask it which buckets of freshly exchanged weights they are the first to touch
@@ -479,9 +480,12 @@ class B200Ops(TorchOps):
         from ..nn.batch import to_device
 
         nO, nP = params["nO"], params["nP"]
-        max_len = max(batch.lengths) if batch.lengths else 0
-        if nO % 32 != 0 or nO // 32 not in (1, 2, 4) or nP not in (2, 3) or max_len > 128 or system.n_actions > 192:
+        # longest doc of the batch: host-side lengths, or the engine's staging capacity
+        max_len = max(batch.lengths) if batch.lengths else int(batch.extra.get("max_len", 128))
+        if nO % 32 != 0 or nO // 32 not in (1, 2, 4) or nP not in (2, 3) or system.n_actions > 192:
             return None                       # host state machine (reference loop)
+        if max_len > self.arc_eager_capacity(nO, nP, system.n_actions):
+            return None                       # the per-warp parser state would not fit in shared memory
         dev = Yf.device
         extra = batch.extra
         if "tok_off" not in extra:
@@ -501,7 +505,7 @@ class B200Ops(TorchOps):
             Yf.contiguous(), params["pad"].contiguous(), params["b"].contiguous(), params["Wu"].contiguous(),
             params["bu"].contiguous(), batch.doc_starts, batch.doc_lens, extra["tok_off"], extra["step_off"],
             gh, gl, batch.n_tokens, S_cap, nO, nP, 1.0 / max(1, batch.n_docs), train,
-            bool(getattr(gold, "teacher_forced", False)),
+            bool(getattr(gold, "teacher_forced", False)), int(max(max_len, 1)),
         )
         self.launches += 1
         rec: Dict[str, Any] = {"arc_heads": heads, "arc_labels": labels, "loss": loss, "n_steps": 0,
@@ -521,6 +525,14 @@ class B200Ops(TorchOps):
             ws = self._ws[key] = torch.zeros((max(rows, int(self.max_rows_hint)), cols), dtype=torch.float32,
                                              device=self.device)
         return ws[:rows]
+
+    def arc_eager_capacity(self, nO: int, nP: int, n_actions: int) -> int:
+        """Longest doc (tokens) the device arc-eager kernel handles for this head shape."""
+        key = (nO, nP, n_actions)
+        cap = self._arc_cap.get(key)
+        if cap is None:
+            cap = self._arc_cap[key] = int(self.k.arc_eager_capacity(nO, nP, n_actions))
+        return cap
 
     def transition_backward(self, rec, params, n_rows, grad_out: Optional[Dict[str, torch.Tensor]] = None):
         if rec["d_scores"].dtype != torch.bfloat16:

@@ -253,7 +253,7 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
                                     const Tensor& tok_off, const Tensor& step_off,
                                     const c10::optional<Tensor>& gold_heads, const c10::optional<Tensor>& gold_labels,
                                     int64_t n_tokens, int64_t n_steps_cap, int64_t nO, int64_t nP, double scale,
-                                    bool train, bool teacher) {
+                                    bool train, bool teacher, int64_t max_len) {
   SRB_CHECK_CUDA(Yf); SRB_CHECK_BF16(Yf); SRB_CHECK_BF16(pad); SRB_CHECK_BF16(b); SRB_CHECK_BF16(Wu); SRB_CHECK_BF16(bu);
   c10::cuda::CUDAGuard guard(Yf.device());
   const int64_t nA = Wu.size(0);
@@ -284,6 +284,7 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   a.n_steps = n_steps.data_ptr<int32_t>(); a.loss = loss.data_ptr<float>();
   a.scale = (float)scale;
   a.teacher = (train && teacher) ? 1 : 0;
+  a.max_n = (int)max_len;
   a.B = (int)doc_lens.numel(); a.nO = (int)nO; a.nP = (int)nP; a.nA = (int)nA; a.nA_pad = (int)nA_pad; a.ld_scores = (int)ldd;
   a.train = train ? 1 : 0;
   TORCH_CHECK(srb::launch_arc_eager_steps(a, cur_stream()), "arc_eager_steps: unsupported hidden width / pieces / #actions");
@@ -315,7 +316,10 @@ TORCH_LIBRARY(srb, m) {
   m.def("linear_softmax_xent(Tensor X, Tensor W, Tensor b, Tensor labels) -> Tensor[]");
   m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
   m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train, bool teacher) -> Tensor[]");
-  m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train, bool teacher) -> Tensor[]");
+  m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train, bool teacher, int max_len) -> Tensor[]");
+  m.def("arc_eager_capacity(int nO, int nP, int nA) -> int", [](int64_t nO, int64_t nP, int64_t nA) -> int64_t {
+    return (int64_t)srb::arc_eager_max_doc_len((int)nO, (int)nP, (int)nA);
+  });
   m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
   srb::register_gemm_ops(m);
   srb::register_comm_ops(m);

@@ -136,9 +136,10 @@ struct ArcArgs {
   float* loss;
   float scale;                 // gradient scale per step (1 / #docs)
   int B, nO, nP, nA, nA_pad, train;
+  int max_n;                   // longest doc of the batch (the launcher rounds it up to a multiple of 32)
   int teacher;                 // train only: advance by the first minimum-cost action instead of the arg-max
 };
 bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s);
-int arc_eager_max_doc_len();
+int arc_eager_max_doc_len(int nO, int nP, int nA);
 
 }  // namespace srb

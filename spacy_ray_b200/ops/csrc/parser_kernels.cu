@@ -22,18 +22,29 @@
 namespace srb {
 
 constexpr int kArcWarps = 4;
-constexpr int kArcMaxN = 128;      // tokens per doc handled on the device (longer docs: host path)
+constexpr int kArcSmemLimit = 200 * 1024;
 
+// Per-warp parser state in shared memory, sized at launch for the longest doc of the batch
+// (A.max_n, a multiple of 32): 7 int arrays + 1 byte array of max_n entries.
 struct ArcWarpState {
-  int stack[kArcMaxN];
-  int heads[kArcMaxN];
-  int labels[kArcMaxN];
-  int lc[kArcMaxN];
-  int rc[kArcMaxN];
-  int gh[kArcMaxN];                // gold head: -2 missing, -1 root, else doc-relative index
-  int gl[kArcMaxN];                // gold label or -1
-  unsigned char in_stack[kArcMaxN];
+  int* stack;
+  int* heads;
+  int* labels;
+  int* lc;
+  int* rc;
+  int* gh;                         // gold head: -2 missing, -1 root, else doc-relative index
+  int* gl;                         // gold label or -1
+  unsigned char* in_stack;
 };
+__host__ __device__ inline size_t arc_state_bytes(int max_n) { return (size_t)max_n * (7 * sizeof(int) + 1); }
+__device__ __forceinline__ ArcWarpState arc_state(unsigned char* base, int warp, int max_n) {
+  unsigned char* p = base + (size_t)warp * arc_state_bytes(max_n);
+  ArcWarpState S;
+  S.stack = (int*)p; S.heads = S.stack + max_n; S.labels = S.heads + max_n; S.lc = S.labels + max_n;
+  S.rc = S.lc + max_n; S.gh = S.rc + max_n; S.gl = S.gh + max_n;
+  S.in_stack = (unsigned char*)(S.gl + max_n);
+  return S;
+}
 
 template <int NP, int UPL, int NJ>
 __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs A) {
@@ -44,7 +55,7 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
   float* bu_s = (float*)smem_raw + (size_t)nO * A.nA_pad;         // [nA_pad]
   float* pad_s = bu_s + A.nA_pad;                                 // [8][nOP]
   float* hid_s = pad_s + 8 * nOP;                                 // [warps][nO]
-  ArcWarpState* states = (ArcWarpState*)(hid_s + kArcWarps * nO);
+  unsigned char* state_base = (unsigned char*)(hid_s + kArcWarps * nO);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_upper_weights(Wu4, bu_s, (const __nv_bfloat16*)A.Wu, (const __nv_bfloat16*)A.bu, nO, nA, A.nA_pad);
   for (int i = threadIdx.x; i < 8 * nOP; i += blockDim.x) pad_s[i] = bf2f(((const __nv_bfloat16*)A.pad)[i]);
@@ -52,14 +63,14 @@ __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs
 
   const int d = blockIdx.x * kArcWarps + warp;
   if (d >= A.B) return;
-  const int n = A.doc_lens[d];
+  const int n = min(A.doc_lens[d], A.max_n);       // the host sizes max_n for the longest doc of the batch
   const int row0 = A.doc_starts[d];
   const int tok0 = A.tok_off[d];
   const int rec0 = A.step_off[d];
-  ArcWarpState& S = states[warp];
+  const ArcWarpState S = arc_state(state_base, warp, A.max_n);
   float* hid_w = hid_s + warp * nO;
   const bool have_gold = A.gold_heads != nullptr;
-  for (int t = lane; t < n && t < kArcMaxN; t += 32) {
+  for (int t = lane; t < n; t += 32) {
     S.heads[t] = -1; S.labels[t] = -1; S.lc[t] = -1; S.rc[t] = -1; S.in_stack[t] = 0;
     int g = -2, l = -1;
     if (have_gold) {
@@ -287,12 +298,17 @@ static void launch_arc_nj(const ArcArgs& a, int blocks, size_t smem, cudaStream_
   }
 }
 
+static size_t arc_fixed_smem(int nO, int nP, int nA_pad) {
+  return sizeof(float) * ((size_t)nO * nA_pad + nA_pad + 8 * nO * nP + kArcWarps * nO);
+}
+
 bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s) {
   if (a.B <= 0) return true;
   if (a.nO % 32 != 0 || a.nA_pad > 192) return false;
   const int upl = a.nO / 32;
-  const size_t smem = sizeof(float) * ((size_t)a.nO * a.nA_pad + a.nA_pad + 8 * a.nO * a.nP + kArcWarps * a.nO) +
-                      kArcWarps * sizeof(ArcWarpState);
+  a.max_n = ((a.max_n > 0 ? a.max_n : 128) + 31) / 32 * 32;
+  const size_t smem = arc_fixed_smem(a.nO, a.nP, a.nA_pad) + kArcWarps * arc_state_bytes(a.max_n);
+  if (smem > (size_t)kArcSmemLimit) return false;            // docs this long: host state machine
   const int blocks = (a.B + kArcWarps - 1) / kArcWarps;
 #define SRB_ARC(NP_, UPL_) \
   if (a.nP == NP_ && upl == UPL_) { launch_arc_nj<NP_, UPL_>(a, blocks, smem, s); return true; }
@@ -301,6 +317,14 @@ bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s) {
   return false;
 }
 
-int arc_eager_max_doc_len() { return kArcMaxN; }
+// Longest doc (tokens) the device kernel can hold for this head shape: the per-warp state has to fit
+// in shared memory next to the staged upper-layer weights.
+int arc_eager_max_doc_len(int nO, int nP, int nA) {
+  const int nA_pad = (nA + 7) / 8 * 8;
+  const size_t fixed = arc_fixed_smem(nO, nP, nA_pad);
+  if (fixed >= (size_t)kArcSmemLimit) return 0;
+  const size_t per_tok = kArcWarps * (7 * sizeof(int) + 1);
+  return (int)(((size_t)kArcSmemLimit - fixed) / per_tok / 32 * 32);
+}
 
 }  // namespace srb

@@ -339,16 +339,32 @@ class DependencyParser(TrainablePipe):
             self.model.set_dim("nO", self.system.n_actions)
 
     def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        """Labels come from the PROJECTIVIZED gold trees (pseudo-projective parsing, ``models/nonproj.py``):
+        a lifted arc's label is decorated ``dep||headdep``; decorated labels seen fewer than
+        ``min_action_freq`` times (cfg, default 30 as upstream) fall back to the plain label."""
         if labels is not None:
             for l in labels:
                 self.add_label(l)
         else:
-            seen = set()
+            from collections import Counter
+
+            from ..models import nonproj
+
+            counts: Counter = Counter()
             for eg in get_examples():
-                for d in (eg.reference.deps or []):
+                ref = eg.reference
+                deps = ref.deps or []
+                if ref.heads is not None and deps and nonproj.is_nonproj_tree(
+                        [h if (h is not None and 0 <= h < len(ref)) else t for t, h in enumerate(ref.heads)]):
+                    _ph, deps = nonproj.projectivize(
+                        [h if (h is not None and 0 <= h < len(ref)) else t for t, h in enumerate(ref.heads)], list(deps))
+                for d in deps:
                     if d:
-                        seen.add(d)
-            for l in sorted(seen):
+                        counts[d] += 1
+            min_freq = int(self.cfg.get("min_action_freq", 30))
+            for l in sorted(counts):
+                if nonproj.is_decorated(l) and counts[l] < min_freq:
+                    continue
                 self.add_label(l)
         if not self._labels:
             self.add_label("dep")
@@ -363,11 +379,18 @@ class DependencyParser(TrainablePipe):
             if ref.heads is None:
                 g = ([-1] * n, [-1] * n)
             else:
+                from ..models import nonproj
+
                 index = {l: i for i, l in enumerate(self._labels)}
                 heads = [h if (h is not None and 0 <= h < n) else -1 for h in ref.heads]
-                if not is_projective([h if h >= 0 else t for t, h in enumerate(heads)]):
-                    heads = [-1] * n           # non-projective trees can't be reached: treat as unannotated
-                deps = ref.deps or [None] * n
+                deps = list(ref.deps or [None] * n)
+                full = [h if h >= 0 else t for t, h in enumerate(heads)]
+                if not is_projective(full):
+                    # pseudo-projective: lift the crossing arcs, decorate their labels (a decorated label
+                    # that was pruned from the label set falls back to the plain one)
+                    lifted, deco = nonproj.projectivize(full, deps)
+                    heads = [lifted[t] if heads[t] >= 0 else -1 for t in range(n)]
+                    deps = [d if (d in index or not nonproj.is_decorated(d)) else nonproj.decompose(d)[0] for d in deco]
                 g = (heads, [index.get(d, -1) if d else -1 for d in deps])
             ref.user_data[key] = g
         return g
@@ -407,14 +430,22 @@ class DependencyParser(TrainablePipe):
             pos = 0
             for doc in docs:
                 n = len(doc)
-                doc.heads = heads_all[pos:pos + n]
-                doc.deps = [self._labels[l] if l >= 0 else "ROOT" for l in labs_all[pos:pos + n]]
+                self._annotate(doc, heads_all[pos:pos + n], labs_all[pos:pos + n])
                 pos += n
             return
         for doc, st in zip(docs, out.states):
             heads, labs = self.system.finalize(st)
-            doc.heads = heads
-            doc.deps = [self._labels[l] if l >= 0 else "ROOT" for l in labs]
+            self._annotate(doc, heads, labs)
+
+    def _annotate(self, doc: Doc, heads, labs) -> None:
+        from ..models import nonproj
+
+        deps = [self._labels[l] if l >= 0 else "ROOT" for l in labs]
+        heads = list(heads)
+        if any(nonproj.is_decorated(d) for d in deps):          # undo the pseudo-projective lifting
+            heads, deps = nonproj.deprojectivize(heads, deps)
+        doc.heads, doc.deps = heads, deps
+        doc.user_data["sent_starts"] = nonproj.sentence_starts(heads)
 
     def score(self, examples):
         return S.score_deps(examples)

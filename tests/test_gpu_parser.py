@@ -303,3 +303,44 @@ def test_arc_eager_kernel_teacher_forced_matches_reference_tightly(nO, nP, n_lab
     assert dr.shape[0] == len(order)
     err = (dk[order] - dr).abs()
     assert float(err.max()) < 1e-2 * max(float(dr.abs().max()), 1e-3) + 2e-3, float(err.max())
+
+
+def test_arc_eager_kernel_handles_docs_longer_than_128_tokens():
+    """The per-warp parser state is sized at launch for the longest doc of the batch (round 1 fell
+    back to the host loop beyond 128 tokens)."""
+    from spacy_ray_b200.models.transition_model import TransitionGold, _arc_steps_reference
+    from spacy_ray_b200.models.transitions import ArcEagerSystem
+    from spacy_ray_b200.nn.batch import make_token_batch
+    from spacy_ray_b200.ops.b200_ops import B200Ops
+
+    ops = B200Ops("cuda:0")
+    rng = random.Random(2)
+    torch.manual_seed(2)
+    n_labels, nO, nP, nF = 7, 64, 2, 8
+    system = ArcEagerSystem([f"d{i}" for i in range(n_labels)])
+    assert ops.arc_eager_capacity(nO, nP, system.n_actions) >= 512
+    lens = [300, 5, 129, 511, 40, 1, 257]
+    batch = make_token_batch([np.ones((n, 4), dtype=np.uint64) for n in lens], "cuda:0")
+    heads = [_projective(n, rng) for n in lens]
+    labels = [[rng.randrange(n_labels) if h != t else -1 for t, h in enumerate(hs)] for hs in heads]
+    gold = TransitionGold(heads=heads, labels=labels, teacher_forced=True)
+    Tp = batch.n_rows
+    Yf = (torch.randn(Tp, nF * nO * nP, device="cuda") * batch.mask).bfloat16()
+    params = {
+        "pad": (torch.randn(nF, nO * nP, device="cuda") * 0.3).bfloat16(),
+        "b": (torch.randn(nO * nP, device="cuda") * 0.3).bfloat16(),
+        "Wu": (torch.randn(system.n_actions, nO, device="cuda") * 0.3).bfloat16(),
+        "bu": (torch.randn(system.n_actions, device="cuda") * 0.1).bfloat16(),
+        "nF": nF, "nO": nO, "nP": nP,
+    }
+    rec = ops.transition_steps(system, Yf, params, batch, gold, True)
+    assert rec is not None and "arc_heads" in rec, "long docs must stay on the device kernel"
+    pf = {k: (v.float() if torch.is_tensor(v) else v) for k, v in params.items()}
+    rref = _arc_steps_reference(system, Yf.float(), pf, batch, gold, True)
+    torch.cuda.synchronize()
+    got = rec["arc_heads"].cpu().tolist()
+    tok = 0
+    for d, n in enumerate(lens):
+        assert got[tok:tok + n] == heads[d], d           # teacher forced: the gold tree comes out
+        tok += n
+    assert abs(float(rec["loss"]) - float(rref["loss"])) <= 1e-2 * max(float(rref["loss"]), 1e-6)

@@ -167,8 +167,9 @@ def make_stage(lay: _Layout, store: ExampleStore, pin: bool = True) -> dict:
     return {"buf": hb, "np": arrs, "event": None, "rows": 0, "docs": 0, "words": 0}
 
 
-def fill_stage(st: ExampleStore, lay: _Layout, stage: dict, ids: np.ndarray) -> None:
-    """Gather docs ``ids`` into the packed staging buffer (native memcpy loops)."""
+def fill_stage(st: ExampleStore, lay: _Layout, stage: dict, ids: np.ndarray, hist: Optional[np.ndarray] = None) -> None:
+    """Gather docs ``ids`` into the packed staging buffer (native memcpy loops).  ``hist``: counting-sort
+    scratch sized for ``st``'s vocabulary (default: the stage's own, sized for the trainer's store)."""
     if stage["event"] is not None:
         stage["event"].synchronize()               # previous H2D out of this buffer has completed
     a = stage["np"]
@@ -199,7 +200,7 @@ def fill_stage(st: ExampleStore, lay: _Layout, stage: dict, ids: np.ndarray) -> 
     # HashEmbed backward: rows grouped by id per attribute column, laid out for the row bucket
     # the step will run with (the captured graph reads perm as (n_attr, rb))
     rb = min(lay.rows, _align(int(rows), lay.bucket))
-    native.group_rows(st.gid, st.n_groups, st.doc_off, ids, rb, a["perm"], a["hist"])
+    native.group_rows(st.gid, st.n_groups, st.doc_off, ids, rb, a["perm"], a["hist"] if hist is None else hist)
     stage["rows"], stage["docs"], stage["words"] = int(rows), len(ids), int(words)
 
 
@@ -244,8 +245,11 @@ class Trainer:
 
     def __init__(self, nlp, proxy, examples: Sequence[Any], *, docs_per_batch: int, dropout: float = 0.1,
                  component: Optional[str] = None, use_graphs: bool = True, bucket_rows: int = 256,
-                 prefetch: bool = True, n_stage: int = 3):
+                 prefetch: bool = True, n_stage: int = 3, exchange: bool = True):
         self.nlp, self.proxy = nlp, proxy
+        # exchange=False: the captured step only ACCUMULATES gradients (accumulate_gradient > 1: the caller
+        # runs proxy.step() once per full batch, after the last micro-batch)
+        self.exchange = bool(exchange)
         self.heads = [(n, c, _kind(c)) for n, c in nlp.pipeline if getattr(c, "is_trainable", False)]
         self.loss_names = [n for n, _c, k in self.heads if k != "tok2vec"]
         self.ops = self.heads[0][1].model.ops
@@ -295,6 +299,7 @@ class Trainer:
         self._launches_per_replay: Dict[int, int] = {}
         self.h2d_bytes_per_step = self.lay.nbytes
         self.steps = 0
+        self.adhoc_batches = 0               # batches collated from a throw-away store (docs not in the store)
         self._stage_i = 0
         self._prefetch = prefetch
         self._q_in: "queue.Queue" = queue.Queue()
@@ -370,7 +375,10 @@ class Trainer:
         Returns the per-head losses as one small device vector (``loss_names`` order)."""
         tb = self._batch_views(rows)
         gold = self.dv.gold
-        if hasattr(self.proxy, "begin_step"):
+        stamp = getattr(self.proxy.comm, "stamp", None)
+        if stamp is not None:
+            stamp(0)                                        # trace: step start
+        if self.exchange and hasattr(self.proxy, "begin_step"):
             self.proxy.begin_step(overlap=True)             # buckets are exchanged under the backward pass
         self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
         shared = [c for _n, c, k in self.heads if k == "tok2vec"]
@@ -407,7 +415,16 @@ class Trainer:
             for stream in forked:
                 main.wait_stream(stream)
             shared[0].finish_backprop()
-        self.proxy.step()
+        if stamp is not None:
+            stamp(1)                                        # trace: forward + backward enqueued, before the final join
+        if self.exchange:
+            self.proxy.step()
+        else:
+            join = getattr(self.ops, "join_side", None)
+            if join is not None:
+                join()                                      # side-stream weight-gradient GEMMs rejoin the capture stream
+        if stamp is not None:
+            stamp(2)                                        # trace: exchange joined = step end
         return losses[0].reshape(1) if len(losses) == 1 else torch.stack(losses)
 
     def _head_stream(self, i: int) -> "torch.cuda.Stream":
@@ -433,7 +450,7 @@ class Trainer:
         if hasattr(comm, "_sync_hyper"):
             comm._sync_hyper()                 # learning-rate schedules: the kernel reads the device copy
         g.replay()
-        if hasattr(comm, "host_bookkeeping"):
+        if self.exchange and hasattr(comm, "host_bookkeeping"):
             comm.host_bookkeeping()
         n_ops, n_comm = self._launches_per_replay[rb]
         self.ops.launches += n_ops
@@ -548,12 +565,29 @@ class Trainer:
         return out
 
     def update_examples(self, examples: Sequence[Any]) -> Optional[torch.Tensor]:
-        """``nlp.update`` fast path: returns the loss tensor (no host sync), or None when the
-        batch cannot be served from the store (the caller then takes the generic path)."""
+        """``nlp.update`` fast path: returns the loss tensor (no host sync), or None when the batch does
+        not fit the staging capacity (the caller then takes the generic path).  Batches whose docs are
+        not in the store - a streamed corpus (``max_epochs = -1``), a corpus too large to pre-load - are
+        collated through a throw-away store built from the batch itself."""
         ids = self.ids_for(examples)
-        if ids is None:
+        if ids is not None:
+            self.prepare(ids)
+            return self.step_async()
+        if len(examples) > self.B:
             return None
-        self.prepare(ids)
+        lens = [len(eg) for eg in examples]
+        if not lens or sum(lens) + len(lens) + 1 > self.lay.rows or max(lens) > self.lay.lmax:
+            return None
+        if self.max_doc_len is not None and max(lens) > self.max_doc_len:
+            return None
+        adhoc = ExampleStore(examples, self.heads)
+        stage = self.stages[self._stage_i]
+        self._stage_i = (self._stage_i + 1) % len(self.stages)
+        hist = np.zeros(int(adhoc.n_groups.sum()) + len(adhoc.n_groups), dtype=np.int32)
+        fill_stage(adhoc, self.lay, stage, np.arange(len(examples), dtype=np.int64), hist=hist)
+        self._upload(stage)
+        self._q_out.put((stage, None))
+        self.adhoc_batches += 1
         return self.step_async()
 
     def batches(self, n: int, seed: int = 0, tokens_per_batch: Optional[int] = None) -> List[np.ndarray]:

@@ -18,7 +18,7 @@ void fused_comm_bucket(std::vector<int64_t> grad_ptrs, std::vector<int64_t> para
                        const Tensor& key_off, const Tensor& key_len, const Tensor& hyper, Tensor step, Tensor epoch,
                        Tensor bar, Tensor error, int64_t shard_start, int64_t blk_begin, int64_t blk_end,
                        int64_t key_begin, int64_t key_end, int64_t bucket, bool last, int64_t rank, int64_t grid,
-                       int64_t opt_mode, double timeout_s, int64_t test_delay_us) {
+                       int64_t opt_mode, double timeout_s, int64_t test_delay_us, const c10::optional<Tensor>& trace) {
   const int W = (int)grad_ptrs.size();
   TORCH_CHECK(W >= 1 && W <= kMaxWorld && (int)param_ptrs.size() == W && (int)signal_ptrs.size() == W);
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && red.scalar_type() == at::kFloat);
@@ -51,8 +51,22 @@ void fused_comm_bucket(std::vector<int64_t> grad_ptrs, std::vector<int64_t> para
   a.bucket = (int)bucket; a.last = last ? 1 : 0;
   a.world = W; a.rank = (int)rank; a.opt_mode = (int)opt_mode;
   a.test_delay_ns = (uint64_t)test_delay_us * 1000ull;
+  if (trace.has_value() && trace->defined()) {
+    TORCH_CHECK(trace->scalar_type() == at::kLong && trace->numel() >= kMaxBuckets * kTraceWords);
+    a.trace = reinterpret_cast<unsigned long long*>(trace->data_ptr<int64_t>());
+  }
   cudaError_t e = launch_fused_bucket(a, (int)grid, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(e == cudaSuccess, "fused_comm_bucket launch failed: ", cudaGetErrorString(e));
+}
+
+// trace[index] = %globaltimer on the current stream (one-thread kernel): step / phase boundaries for the
+// overlap trace (benchmarks/exchange_trace.py)
+void stamp(Tensor trace, int64_t index) {
+  TORCH_CHECK(trace.is_cuda() && trace.scalar_type() == at::kLong && index >= 0 && index < trace.numel());
+  c10::cuda::CUDAGuard guard(trace.device());
+  cudaError_t e = launch_stamp(reinterpret_cast<unsigned long long*>(trace.data_ptr<int64_t>()) + index,
+                               at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(e == cudaSuccess, "stamp launch failed: ", cudaGetErrorString(e));
 }
 
 // Stand-alone consumer gate (one warp): used in front of consumers without an in-kernel gate.
@@ -96,7 +110,8 @@ void register_comm_ops(torch::Library& m) {
       "Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor hyper, Tensor(e!) step, "
       "Tensor(f!) epoch, Tensor(g!) bar, Tensor(h!) error, int shard_start, int blk_begin, int blk_end, "
       "int key_begin, int key_end, int bucket, bool last, int rank, int grid, int opt_mode, float timeout_s, "
-      "int test_delay_us) -> ()");
+      "int test_delay_us, Tensor(t!)? trace) -> ()");
+  m.def("stamp(Tensor(a!) trace, int index) -> ()");
   m.def("gate_wait(Tensor epoch, int[] gate) -> ()");
   m.def(
       "p2p_collective(int kind, int[] buf_ptrs, int[] signal_ptrs, int mc, Tensor(a!) local, Tensor(b!) epoch, "
@@ -105,6 +120,7 @@ void register_comm_ops(torch::Library& m) {
 void register_comm_impls(torch::Library& m) {
   m.impl("fused_comm_bucket", fused_comm_bucket);
   m.impl("gate_wait", gate_wait);
+  m.impl("stamp", stamp);
   m.impl("p2p_collective", p2p_collective);
 }
 

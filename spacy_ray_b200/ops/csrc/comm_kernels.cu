@@ -91,6 +91,10 @@ __global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a)
   const int W = a.world, rank = a.rank, bkt = a.bucket;
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
   const int lane = threadIdx.x;
+  unsigned long long* tr = a.trace ? a.trace + (size_t)bkt * kTraceWords : nullptr;
+  if (tr && lane == 0) {
+    tr[0] = globaltimer_ns(); tr[1] = 0ull; tr[2] = ~0ull; tr[3] = 0ull; tr[4] = ~0ull; tr[5] = 0ull;
+  }
   if (W > 1 && lane < W) {
     fence_acq_rel_sys();
     st_release_sys(a.signal[lane] + flag_grad_idx(bkt, rank), epoch);
@@ -107,6 +111,8 @@ __global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a)
     return;
   }
   if (lane < W && !wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, lane), epoch, a.timeout_ns)) atomicExch(a.error, 1);
+  __syncwarp();
+  if (tr && lane == 0) tr[1] = globaltimer_ns();
 }
 
 __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) {
@@ -114,6 +120,8 @@ __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) 
   const int n_items = a.blk_end - a.blk_begin;
   __shared__ float s_part[8];
   if (n_items == 0 || *(const volatile int32_t*)a.error != 0) return;
+  unsigned long long* tr = a.trace ? a.trace + (size_t)a.bucket * kTraceWords : nullptr;
+  if (tr && threadIdx.x == 0) atomicMin(tr + 2, (unsigned long long)globaltimer_ns());
   const int64_t s0 = a.shard_start;
   float* my_grad = a.grad[rank];
   const float l2 = a.hyper[5];
@@ -179,6 +187,7 @@ __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) 
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += s_part[i];
     atomicAdd(a.norms_sq + k, t);
+    if (tr) atomicMax(tr + 3, (unsigned long long)globaltimer_ns());
   }
 }
 
@@ -187,6 +196,8 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;
   const int n_items = a.blk_end - a.blk_begin;
   __shared__ int s_last;
+  unsigned long long* tr = a.trace ? a.trace + (size_t)bkt * kTraceWords : nullptr;
+  if (tr && threadIdx.x == 0) atomicMin(tr + 4, (unsigned long long)globaltimer_ns());
   if (n_items > 0 && *(const volatile int32_t*)a.error == 0) {
     if (a.test_delay_ns) {          // test hook: a slow owner (the consumers' gates must hold them back)
       if (threadIdx.x == 0) {
@@ -314,6 +325,13 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
     __threadfence();
     *(volatile uint32_t*)a.epoch = epoch;
   }
+  if (tr && threadIdx.x == 0) tr[5] = globaltimer_ns();
+}
+
+__global__ void stamp_kernel(unsigned long long* dst) { *dst = globaltimer_ns(); }
+cudaError_t launch_stamp(unsigned long long* dst, cudaStream_t s) {
+  stamp_kernel<<<1, 1, 0, s>>>(dst);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s) {

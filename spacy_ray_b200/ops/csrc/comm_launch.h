@@ -79,7 +79,12 @@ struct FusedCommArgs {
   int world, rank;
   int opt_mode;                  // kOptAdam / kOptRAdam / kOptSGD
   uint64_t test_delay_ns;        // tests only: hold the weight publication back by this long (late publisher)
+  // optional %globaltimer trace (null = off), 8 words per bucket:
+  //   [0] signal kernel start  [1] all peers' gradients seen  [2] first reduce CTA start  [3] last reduce CTA end
+  //   [4] first update CTA start  [5] bucket published (last update CTA)  [6..7] spare
+  unsigned long long* trace;
 };
+constexpr int kTraceWords = 8;
 
 struct P2PCollArgs {
   void* buf[kMaxWorld];          // every rank's symmetric buffer
@@ -96,6 +101,7 @@ struct P2PCollArgs {
 
 cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_gate_wait(const GateArgs& g, cudaStream_t s);
+cudaError_t launch_stamp(unsigned long long* dst, cudaStream_t s);     // *dst = %globaltimer (one thread)
 cudaError_t launch_p2p_reduce_scatter(const P2PCollArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_p2p_all_gather(const P2PCollArgs& a, int grid, cudaStream_t s);
 

@@ -186,6 +186,12 @@ class FusedSymmComm:
         self.overlap = os.environ.get("SRB_COMM_OVERLAP", "1") != "0"
         self.terminal_wait = os.environ.get("SRB_GATE_ALWAYS", "0") == "1"    # debugging: round-1 behaviour
         self.test_delay_us = 0               # tests: make this rank a late publisher (see tests/mgpu_worker.py)
+        # %globaltimer trace of the exchange kernels (8 words per bucket) + free stamp slots behind them;
+        # SRB_COMM_TRACE=1 or benchmarks/exchange_trace.py switch it on (it adds a few atomics per CTA)
+        self.trace: Optional[torch.Tensor] = None
+        self.trace_keys: Dict[int, KeyT] = {}
+        if os.environ.get("SRB_COMM_TRACE", "0") == "1":
+            self.enable_trace()
         total = layout.total
         # NVLS (multimem.ld_reduce / multimem.st through the NVSwitch) whenever a multicast mapping
         # exists; SRB_NVLS=0 forces the plain peer-pointer variant.
@@ -283,6 +289,16 @@ class FusedSymmComm:
                 out[k] = self.master[o:o + n].view(layout.shape[k]).detach().to("cpu")
         return out
 
+    def enable_trace(self) -> torch.Tensor:
+        if self.trace is None:
+            self.trace = torch.zeros(_MAX_BUCKETS * 8 + 64, dtype=torch.int64, device=self.device)
+        return self.trace
+
+    def stamp(self, slot: int) -> None:
+        """Record %globaltimer on the current stream into free trace slot ``slot`` (0..63)."""
+        if self.trace is not None:
+            torch.ops.srb.stamp(self.trace, _MAX_BUCKETS * 8 + int(slot))
+
     def _sync_hyper(self) -> None:
         opt = self.optimizer
         vals = [float(opt.learn_rate), float(opt.b1), float(opt.b2), float(opt.eps), float(opt.grad_clip or 0.0),
@@ -293,7 +309,7 @@ class FusedSymmComm:
 
     def _comm_stream(self) -> "torch.cuda.Stream":
         if self._stream is None:
-            self._stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SRB_COMM_PRIO", "-1")))
+            self._stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SRB_COMM_PRIO", "0")))
         return self._stream
 
     # ------------------------------------------------------------------ plan
@@ -345,6 +361,9 @@ class FusedSymmComm:
         if b is None:
             return
         self._seen.add(key)
+        if self.trace is not None and len(self._seen) <= 48:
+            self.stamp(8 + len(self._seen) - 1)       # trace: when the backward pass completed this key
+            self.trace_keys[len(self._seen) - 1] = key
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -379,7 +398,7 @@ class FusedSymmComm:
                 self.hyper, self.step_t, self.epoch, self.bar, self.error,
                 int(L.shard_start[self.rank]), int(bb), int(be), int(kb), int(ke), int(b),
                 bool(b == self.plan.n - 1), self.rank, self._grid_for(b), int(self.opt_mode), float(self.timeout_s),
-                int(self.test_delay_us),
+                int(self.test_delay_us), self.trace,
             )
         self.launches += self.kernels_for(b)
 

@@ -351,7 +351,7 @@ class Language:
             if loss is not None:
                 for head, value in trainer.losses_dict(loss).items():
                     C._add_loss(losses, head, value)
-                self._trainer_stepped = True
+                self._trainer_stepped = bool(getattr(trainer, "exchange", True))    # False: caller runs proxy.step()
                 return losses
         batch = self.make_batch([eg.predicted for eg in examples])
         for name, comp in self.pipeline:

@@ -376,11 +376,6 @@ class Worker:
             return
         if set(self.T["frozen_components"]) or set(self.T["annotating_components"]):
             return
-        if int(self.T["accumulate_gradient"]) > 1:
-            # the captured step ends with the exchange + optimizer; micro-batch accumulation needs the
-            # generic path (one proxy.step() per full batch)
-            logger.info("rank %d: generic training path (accumulate_gradient > 1)", self.rank)
-            return
         try:
             from .engine import Trainer
 
@@ -388,12 +383,23 @@ class Worker:
             if why is not None:
                 logger.info("rank %d: generic training path (%s)", self.rank, why)
                 return
-            examples = list(self.train_corpus(self.nlp))
+            # The store is sized from (a sample of) the corpus.  A finite corpus is indexed whole - its
+            # batches are then collated by doc id on the native path; a streamed corpus (max_epochs = -1)
+            # or one beyond SRB_FAST_PATH_STORE_DOCS contributes only its first docs, and batches of
+            # unseen docs go through a throw-away per-batch store (Trainer.update_examples).
+            import itertools
+
+            limit = int(os.environ.get("SRB_FAST_PATH_STORE_DOCS", 2_000_000))
+            if int(self.T["max_epochs"]) < 0:
+                limit = min(limit, int(os.environ.get("SRB_FAST_PATH_SAMPLE", 4096)))
+            examples = list(itertools.islice(self.train_corpus(self.nlp), limit))
             if not examples:
                 return
             cap = int(os.environ.get("SRB_FAST_PATH_MAX_DOCS", 2048))
+            acc = int(self.T["accumulate_gradient"])
             self.nlp._trainer = Trainer(self.nlp, self.proxy, examples, docs_per_batch=min(cap, len(examples)),
-                                        dropout=float(self.T["dropout"]), prefetch=False)
+                                        dropout=float(self.T["dropout"]), prefetch=False,
+                                        exchange=(acc <= 1))      # accumulate_gradient > 1: exchange once per full batch
             logger.info("rank %d: device-resident training engine enabled", self.rank)
         except Exception as e:       # never fatal: the generic path is always available
             logger.warning("rank %d: fast path unavailable (%s); using the generic path", self.rank, e)

@@ -474,3 +474,39 @@ size = 64
     assert (tmp_path / "model-last" / "ner" / "model").exists()
     stats = w.get_stats()
     assert stats["docs"] > 0 and stats["docs_per_sec"] > 0
+
+
+def test_engine_serves_accumulate_gradient_and_streamed_corpora(tmp_path):
+    """Round 1 dropped to the per-op path for accumulate_gradient > 1 and needed the whole corpus in
+    memory.  Now micro-batches replay an accumulate-only graph (the exchange runs once per full batch)
+    and batches of docs that are not in the pre-built store are collated from a per-batch store."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.worker import Worker
+
+    text = multi_cfg(["ner"], width=64, depth=2, n_docs=600, max_len=16, hidden=64)
+    text = text.replace("max_steps = 10", "max_steps = 24").replace("eval_frequency = 5", "eval_frequency = 12")
+    text = text.replace("[training]\n", "[training]\naccumulate_gradient = 2\nmax_epochs = -1\n")
+    text += """
+[training.batcher]
+@batchers = "spacy.batch_by_sequence.v1"
+size = 64
+"""
+    import os
+
+    os.environ["SRB_FAST_PATH_SAMPLE"] = "128"          # the store only knows the first 128 docs of the stream
+    try:
+        w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0)
+        w.set_proxy(None)
+        w.train(None, None)
+        w.join(timeout=300)
+    finally:
+        os.environ.pop("SRB_FAST_PATH_SAMPLE", None)
+    assert w.get_error() is None
+    trainer = getattr(w.nlp, "_trainer", None)
+    assert trainer is not None and trainer.exchange is False
+    assert trainer.steps >= 2 * 23, "micro-batches did not go through the engine"
+    assert trainer.adhoc_batches > 0, "streamed docs outside the store must use the per-batch store"
+    comm = w.proxy.comm
+    assert int(comm.step_t.item()) == 24, "one optimizer step per FULL batch"
+    assert float(w.proxy.grad_flat.abs().sum()) == 0.0

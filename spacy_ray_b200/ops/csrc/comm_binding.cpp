@@ -55,8 +55,22 @@ void fused_comm_bucket(std::vector<int64_t> grad_ptrs, std::vector<int64_t> para
     TORCH_CHECK(trace->scalar_type() == at::kLong && trace->numel() >= kMaxBuckets * kTraceWords);
     a.trace = reinterpret_cast<unsigned long long*>(trace->data_ptr<int64_t>());
   }
+  // `grid` carries the launch mode: 0 = whole pipeline, 1 = grad-ready signal only, 2 = wait + reduce + update
   cudaError_t e = launch_fused_bucket(a, (int)grid, at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(e == cudaSuccess, "fused_comm_bucket launch failed: ", cudaGetErrorString(e));
+}
+
+// Wait for the owners' "published" flags of the gate's buckets, then clear my gradient accumulators
+// of those buckets (see bucket_gate_zero_kernel).
+void gate_zero(Tensor grad, std::vector<int64_t> gate, const Tensor& ext_off, const Tensor& ext_len, int64_t ext_begin,
+               int64_t ext_end, int64_t grid) {
+  TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && ext_off.scalar_type() == at::kLong &&
+              ext_len.scalar_type() == at::kLong && ext_end <= ext_off.numel() && grid >= 1);
+  c10::cuda::CUDAGuard guard(grad.device());
+  GateArgs g = make_gate_args(gate.data(), gate.size());
+  cudaError_t e = launch_gate_zero(g, grad.data_ptr<float>(), ext_off.data_ptr<int64_t>(), ext_len.data_ptr<int64_t>(),
+                                   (int)ext_begin, (int)ext_end, (int)grid, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(e == cudaSuccess, "gate_zero launch failed: ", cudaGetErrorString(e));
 }
 
 // trace[index] = %globaltimer on the current stream (one-thread kernel): step / phase boundaries for the
@@ -112,6 +126,7 @@ void register_comm_ops(torch::Library& m) {
       "int key_begin, int key_end, int bucket, bool last, int rank, int grid, int opt_mode, float timeout_s, "
       "int test_delay_us, Tensor(t!)? trace) -> ()");
   m.def("stamp(Tensor(a!) trace, int index) -> ()");
+  m.def("gate_zero(Tensor(a!) grad, int[] gate, Tensor ext_off, Tensor ext_len, int ext_begin, int ext_end, int grid) -> ()");
   m.def("gate_wait(Tensor epoch, int[] gate) -> ()");
   m.def(
       "p2p_collective(int kind, int[] buf_ptrs, int[] signal_ptrs, int mc, Tensor(a!) local, Tensor(b!) epoch, "
@@ -121,6 +136,7 @@ void register_comm_impls(torch::Library& m) {
   m.impl("fused_comm_bucket", fused_comm_bucket);
   m.impl("gate_wait", gate_wait);
   m.impl("stamp", stamp);
+  m.impl("gate_zero", gate_zero);
   m.impl("p2p_collective", p2p_collective);
 }
 

@@ -11,9 +11,7 @@
 //   phase 0  "my gradients of bucket b, epoch e, are complete" -> every rank's signal page;
 //            owners wait for all ranks' flags
 //   phase 1  for my keys of the bucket: g = sum_p peer_grad_p  (one multimem.ld_reduce through the
-//            NVSwitch, or P2P ld.relaxed.sys from every peer), every rank's copy of that extent is
-//            ZEROED in the same pass (multimem.st / P2P st) - the buffers are accumulators and the
-//            next backward pass must find them clear -, g -> local scratch, per-key sum of squares
+//            NVSwitch, or P2P ld.relaxed.sys from every peer), g -> local scratch, per-key sum of squares
 //   (kernel boundary: one CTA per 4096-element work item, so the two phases are two launches)
 //   phase 2  per-key clip, Adam / RAdam / SGD on the fp32 master (+ moments, + parameter averages),
 //            bf16 weights stored straight into ALL ranks' weight buffers (multimem.st / P2P st);
@@ -21,9 +19,9 @@
 //
 // Nothing waits for the publication here: the first consumer of a bucket's weights in the next
 // forward pass does (gate.cuh; gemm_tcgen05.cu's TMA producer warp, hash_embed_fwd_kernel).
-// The same flag also orders the remote zeroing against the next step's gradient writes: a rank
-// only writes gradients of bucket b after its forward pass consumed bucket b's weights, i.e. after
-// it has seen every owner's published flag, which the owner releases after its zero stores.
+// The same flag tells a rank that the owners are done READING its gradients of the bucket: the
+// accumulators are cleared locally at the start of the next step (bucket_gate_zero_kernel, side
+// stream, under the forward pass) - no clear stores over NVLink, no "read done" flag round.
 //
 // Every spin has a wall-clock timeout (%globaltimer); on timeout the kernel records an
 // error code and exits instead of hanging the GPU (a dead peer must
@@ -41,10 +39,6 @@ __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
                : "l"(p)
                : "memory");
   return v;
-}
-__device__ __forceinline__ void st_relaxed_sys_v4(float* p, float4 v) {
-  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
 }
 __device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* mc) {
   float4 v;
@@ -64,30 +58,24 @@ __device__ __forceinline__ void multimem_st_v2_b32(void* mc, uint32_t a, uint32_
                "f"(__uint_as_float(b))
                : "memory");
 }
-// A zero vector that neither nvcc nor ptxas can materialise before the load that produced `v` has
-// returned: x - x is +0 for every finite x and NaN otherwise (so it cannot be constant-folded - an
-// integer `and 0` was folded to RZ by ptxas and the store lost its dependency), and min(NaN, 0) = 0.
-// The store that clears a gradient word must not be issued before the (switch-side) read of that
-// word has completed; the data dependency is what enforces it.
-__device__ __forceinline__ float4 zero_after(const float4& v) {
-  return make_float4(fminf(v.x - v.x, 0.f), fminf(v.y - v.y, 0.f), fminf(v.z - v.z, 0.f), fminf(v.w - v.w, 0.f));
-}
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // One work item (= one 4096-element chunk of one owned key) per CTA, two launches per bucket:
-//   bucket_signal_wait_kernel  phase 0 (one warp: my grad-ready flag out, everybody's in)
+//   bucket_signal_kernel / bucket_wait_kernel  phase 0 (one warp each: my grad-ready flag out; everybody's in)
 //   bucket_reduce_kernel  phase 1 (reduce + clear, per-key sum of squares)
 //   bucket_update_kernel  phase 2 (clip, optimizer, weight stores) + publication by the last CTA
 // The kernel boundary is the "all of this key's partial norms are in" barrier.  No device-wide
 // barrier inside a kernel means no co-residency requirement: the grids can be as large as the
 // bucket, and the CTAs (80 registers x 256 threads) slot in next to the CTAs of whatever the
 // backward pass is running (a tcgen05 GEMM CTA leaves room for exactly one of them per SM).
-// phase 0 as its own ONE-WARP kernel: "my gradients of bucket b are complete" -> every rank's signal
-// page, then wait for everybody else's.  The wait can last as long as the slowest rank's backward
-// pass; doing it in the reduce kernel would park hundreds of spinning CTAs on the SMs and starve
-// this rank's own backward GEMMs of registers exactly while they should be running.
-__global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a) {
+// phase 0 as ONE-WARP kernels: "my gradients of bucket b are complete" -> every rank's signal page
+// (bucket_signal_kernel, on its own stream: it must go out the moment the gradients exist, not after
+// the exchange of the previous bucket), and the wait for everybody else's (bucket_wait_kernel, at the
+// head of the bucket's exchange).  The wait can last as long as the slowest rank's backward pass;
+// doing it inside the reduce kernel would park hundreds of spinning CTAs on the SMs and starve this
+// rank's own backward GEMMs of registers exactly while they should be running.
+__global__ void __launch_bounds__(32) bucket_signal_kernel(FusedCommArgs a) {
   const int W = a.world, rank = a.rank, bkt = a.bucket;
   const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;   // flag value of this exchange
   const int lane = threadIdx.x;
@@ -99,6 +87,13 @@ __global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a)
     fence_acq_rel_sys();
     st_release_sys(a.signal[lane] + flag_grad_idx(bkt, rank), epoch);
   }
+}
+
+__global__ void __launch_bounds__(32) bucket_wait_kernel(FusedCommArgs a) {
+  const int W = a.world, rank = a.rank, bkt = a.bucket;
+  const uint32_t epoch = *(const volatile uint32_t*)a.epoch + 1;
+  const int lane = threadIdx.x;
+  unsigned long long* tr = a.trace ? a.trace + (size_t)bkt * kTraceWords : nullptr;
   if (a.blk_end - a.blk_begin == 0) {
     // nothing of this bucket is mine: there is nothing to wait for, and nothing to publish but the flag
     // (consumers wait for every rank's flag of a bucket)
@@ -110,9 +105,28 @@ __global__ void __launch_bounds__(32) bucket_signal_wait_kernel(FusedCommArgs a)
     }
     return;
   }
-  if (lane < W && !wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, lane), epoch, a.timeout_ns)) atomicExch(a.error, 1);
+  if (W > 1 && lane < W && !wait_flag_sys(a.signal[rank] + flag_grad_idx(bkt, lane), epoch, a.timeout_ns))
+    atomicExch(a.error, 1);
   __syncwarp();
   if (tr && lane == 0) tr[1] = globaltimer_ns();
+}
+
+// Clear my gradient accumulators of a bucket once every owner has published it (= finished reading
+// them).  Runs at the start of the next step on a side stream, under the forward pass; the first
+// gradient write of the step waits for it.  (Round 1 zero-filled inside the exchange kernel after a
+// "read done" flag round; an owner-side multimem.st of zeros doubled the NVLink bytes of the reduce.)
+__global__ void __launch_bounds__(256) bucket_gate_zero_kernel(GateArgs g, float* __restrict__ grad,
+                                                               const int64_t* __restrict__ ext_off,
+                                                               const int64_t* __restrict__ ext_len, int ext_begin,
+                                                               int ext_end) {
+  if (threadIdx.x < 32) gate_wait_warp(g);
+  __syncthreads();
+  for (int e = ext_begin; e < ext_end; ++e) {
+    float4* p = (float4*)(grad + ext_off[e]);
+    const int64_t n4 = ext_len[e] >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+      p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) {
@@ -149,8 +163,6 @@ __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) 
     } else if (a.grad_mc) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (ok[j]) s[j] = multimem_ld_reduce_v4(a.grad_mc + s0 + t0 + j * 1024);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (ok[j]) multimem_st_v4(a.grad_mc + s0 + t0 + j * 1024, zero_after(s[j]));
     } else {
 #pragma unroll 2
       for (int p = 0; p < W; ++p) {
@@ -161,7 +173,6 @@ __global__ void __launch_bounds__(256, 3) bucket_reduce_kernel(FusedCommArgs a) 
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (ok[j]) {
           s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w;
-          st_relaxed_sys_v4(src + j * 1024, zero_after(v[j]));
         }
       }
     }
@@ -334,18 +345,27 @@ cudaError_t launch_stamp(unsigned long long* dst, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_fused_bucket(const FusedCommArgs& a, int mode, cudaStream_t s) {
   const int n_items = a.blk_end - a.blk_begin;
-  (void)grid;
+  cudaError_t e = cudaSuccess;
+  if (mode != 2 && (a.world > 1 || a.trace)) {
+    bucket_signal_kernel<<<1, 32, 0, s>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (mode == 1) return e;
   if (a.world > 1 || n_items == 0) {
-    bucket_signal_wait_kernel<<<1, 32, 0, s>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || n_items == 0) return e;      // a rank that owns nothing of the bucket is done
+    bucket_wait_kernel<<<1, 32, 0, s>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess || n_items == 0) return e;   // a rank that owns nothing of the bucket is done
   }
   bucket_reduce_kernel<<<n_items, 256, 0, s>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   bucket_update_kernel<<<n_items, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_zero(const GateArgs& g, float* grad, const int64_t* ext_off, const int64_t* ext_len,
+                             int ext_begin, int ext_end, int grid, cudaStream_t s) {
+  bucket_gate_zero_kernel<<<grid, 256, 0, s>>>(g, grad, ext_off, ext_len, ext_begin, ext_end);
   return cudaGetLastError();
 }
 

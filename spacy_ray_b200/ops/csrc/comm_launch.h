@@ -99,7 +99,13 @@ struct P2PCollArgs {
   int world, rank;
 };
 
-cudaError_t launch_fused_bucket(const FusedCommArgs& a, int grid, cudaStream_t s);
+// mode 0: the whole bucket pipeline on one stream; 1: only the grad-ready signal (own stream, so a
+// bucket's signal never queues behind an earlier bucket's exchange); 2: wait for the peers + reduce + update
+cudaError_t launch_fused_bucket(const FusedCommArgs& a, int mode, cudaStream_t s);
+// wait until every owner has published bucket(s) `g.mask` (= they are done reading my gradients of
+// that bucket), then clear my gradient accumulators of the bucket: extents [ext_begin, ext_end)
+cudaError_t launch_gate_zero(const GateArgs& g, float* grad, const int64_t* ext_off, const int64_t* ext_len,
+                             int ext_begin, int ext_end, int grid, cudaStream_t s);
 cudaError_t launch_gate_wait(const GateArgs& g, cudaStream_t s);
 cudaError_t launch_stamp(unsigned long long* dst, cudaStream_t s);     // *dst = %globaltimer (one thread)
 cudaError_t launch_p2p_reduce_scatter(const P2PCollArgs& a, int grid, cudaStream_t s);

@@ -241,6 +241,11 @@ class FusedSymmComm:
         self.master: Optional[torch.Tensor] = None
         self._steps_since_check = 0
         self._stream: Optional[torch.cuda.Stream] = None
+        self._sig_stream: Optional[torch.cuda.Stream] = None       # grad-ready signals (never behind an exchange)
+        self._zero_stream: Optional[torch.cuda.Stream] = None      # gate + clear of the gradient accumulators
+        self._zero_event: Optional[torch.cuda.Event] = None
+        self._zero_waited: set = set()
+        self.ext: Optional[Dict[str, Any]] = None
         # bucket plan: built at the first exchange from the gradient-completion order of the first step
         self.plan: Optional[BucketPlan] = None
         self.tables: Optional[Dict[str, Any]] = None
@@ -310,6 +315,8 @@ class FusedSymmComm:
     def _comm_stream(self) -> "torch.cuda.Stream":
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SRB_COMM_PRIO", "0")))
+            self._sig_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._zero_stream = torch.cuda.Stream(device=self.device, priority=0)
         return self._stream
 
     # ------------------------------------------------------------------ plan
@@ -320,6 +327,21 @@ class FusedSymmComm:
         self._all_mask = (1 << self.plan.n) - 1
         had_grad = set(order)
         self._expected = [set(k for k in ks if k in had_grad) for ks in self.plan.buckets]
+        # per bucket: the extents of ALL its keys (any owner) in my gradient buffer - what
+        # bucket_gate_zero_kernel clears once the owners have published (adjacent extents merged)
+        offs, lens, ranges = [], [], []
+        for ks in self.plan.buckets:
+            e0 = len(offs)
+            for o, n in sorted((self.layout.offset[k], _round_up(self.layout.numel[k], ALIGN)) for k in ks):
+                if len(offs) > e0 and offs[-1] + lens[-1] == o:
+                    lens[-1] += n
+                else:
+                    offs.append(o)
+                    lens.append(n)
+            ranges.append((e0, len(offs)))
+        self.ext = {"off": torch.tensor(offs, dtype=torch.int64, device=self.device),
+                    "len": torch.tensor(lens, dtype=torch.int64, device=self.device), "ranges": ranges,
+                    "elems": [sum(lens[a:b]) for a, b in ranges]}
         self._ptr_bucket = {}
         if proxy is not None:
             for k, b in self.plan.bucket_of.items():
@@ -328,12 +350,13 @@ class FusedSymmComm:
                     self._ptr_bucket[int(v.data_ptr())] = b
 
     def kernels_for(self, b: int) -> int:
-        """Launches bucket ``b`` costs on this rank: [signal/wait (one warp; only with peers)] + reduce +
-        update; a rank that owns nothing of the bucket only signals."""
+        """Launches bucket ``b`` costs on this rank: with peers a signal and a wait kernel (one warp
+        each), then reduce + update; a rank that owns nothing of the bucket only signals and waits."""
         bb, be, _kb, _ke = self.tables["ranges"][b]
+        peers = 2 if self.world_size > 1 else 0
         if be == bb:
-            return 1
-        return 2 + (1 if self.world_size > 1 else 0)
+            return max(peers, 1)
+        return 2 + peers
 
     def _grid_for(self, b: int) -> int:
         """One CTA per 4096-element work item (the launcher derives the grid from the item range)."""
@@ -347,9 +370,44 @@ class FusedSymmComm:
         self._next = 0
         self._seen = set()
         self._events = {}
+        self._signalled = set()
+        self._sig_events = {}
         self._hooked = bool(overlap and self.overlap and self.plan is not None)
         if not torch.cuda.is_current_stream_capturing():
             self._sync_hyper()                    # learning-rate schedules: the kernels read the device copy
+        self._zero_event = None
+        self._zero_waited = set()
+        if self.world_size > 1 and self.plan is not None:
+            # Clear my gradient accumulators bucket by bucket as soon as every owner has published the
+            # bucket (= is done reading them): side stream, under the forward pass.  The first gradient
+            # write of the step waits for the event (ensure_zeroed).
+            cur = torch.cuda.current_stream(self.device)
+            self._comm_stream()
+            zs = self._zero_stream
+            zs.wait_stream(cur)
+            with torch.cuda.stream(zs):
+                for b in range(self.plan.n):
+                    e0, e1 = self.ext["ranges"][b]
+                    if e1 == e0:
+                        continue
+                    gate = [int(self.flags.data_ptr()), int(self.epoch.data_ptr()), int(self.error.data_ptr()),
+                            1 << b, int(self.world_size), int(self.timeout_s * 1000)]
+                    grid = max(1, min(2 * self._sms, self.ext["elems"][b] // 8192))
+                    torch.ops.srb.gate_zero(self.grad, gate, self.ext["off"], self.ext["len"], int(e0), int(e1), int(grid))
+                    self.launches += 1
+                ev = torch.cuda.Event()
+                ev.record(zs)
+            self._zero_event = ev
+
+    def ensure_zeroed(self) -> None:
+        """The current stream is about to write gradients: order it after this step's accumulator clear."""
+        ev = self._zero_event
+        if ev is None:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream not in self._zero_waited:
+            cur.wait_event(ev)
+            self._zero_waited.add(cur.cuda_stream)
 
     def key_ready(self, key: KeyT, proxy) -> None:
         """Called by the proxy from ``inc_grad`` (overlap mode): ``key``'s gradient for this step
@@ -370,37 +428,62 @@ class FusedSymmComm:
         self._events.setdefault(b, {})[cur.cuda_stream] = ev
         # buckets are launched in plan order on every rank (a rank that launched them in a different
         # order than its peers would deadlock on the grad-ready flags)
+        if self._expected[b] and self._expected[b] <= self._seen and b not in self._signalled:
+            self._signal(b, proxy)               # my gradients of bucket b exist: tell the owners NOW
         while self._next < plan.n and self._expected[self._next] and self._expected[self._next] <= self._seen:
             self._launch(self._next, proxy)
             self._next += 1
 
-    def _launch(self, b: int, proxy) -> None:
-        if self.master is None:
-            self.bind(proxy)
+    def _bucket_args(self, b: int, mode: int):
         t, L = self.tables, self.layout
         bb, be, kb, ke = t["ranges"][b]
-        cs = self._comm_stream()
-        evs = self._events.pop(b, None)
-        if evs:
-            for ev in evs.values():
-                cs.wait_event(ev)
-        else:
-            cs.wait_stream(torch.cuda.current_stream(self.device))
-        side_fn = getattr(self.ops, "side_stream_if_pending", None)
-        side = side_fn() if side_fn is not None else None
-        if side is not None:
-            cs.wait_stream(side)             # weight-gradient GEMMs accumulate into the bucket on the ops' side stream
-        with torch.cuda.stream(cs):
-            torch.ops.srb.fused_comm_bucket(
-                self.grad_ptrs, self.param_ptrs, self.flag_ptrs, int(self.grad_mc), int(self.param_mc),
+        return (self.grad_ptrs, self.param_ptrs, self.flag_ptrs, int(self.grad_mc), int(self.param_mc),
                 self.red, self.master, self.m1, self.m2, self.avg, self.norms,
                 t["blk_key"], t["blk_off"], t["key_off"], t["key_len"],
                 self.hyper, self.step_t, self.epoch, self.bar, self.error,
                 int(L.shard_start[self.rank]), int(bb), int(be), int(kb), int(ke), int(b),
-                bool(b == self.plan.n - 1), self.rank, self._grid_for(b), int(self.opt_mode), float(self.timeout_s),
-                int(self.test_delay_us), self.trace,
-            )
-        self.launches += self.kernels_for(b)
+                bool(b == self.plan.n - 1), self.rank, int(mode), int(self.opt_mode), float(self.timeout_s),
+                int(self.test_delay_us), self.trace)
+
+    def _wait_producers(self, stream, b: int, proxy) -> None:
+        evs = self._events.get(b)
+        if evs:
+            for ev in evs.values():
+                stream.wait_event(ev)
+        else:
+            stream.wait_stream(torch.cuda.current_stream(self.device))
+        side_fn = getattr(self.ops, "side_stream_if_pending", None)
+        side = side_fn() if side_fn is not None else None
+        if side is not None:
+            stream.wait_stream(side)         # weight-gradient GEMMs accumulate into the bucket on the ops' side stream
+
+    def _signal(self, b: int, proxy) -> None:
+        """Grad-ready flag of bucket ``b`` to every rank, on the signal stream, ordered only after the
+        kernels that produced the gradients - never after another bucket's exchange."""
+        if self.master is None:
+            self.bind(proxy)
+        self._comm_stream()
+        ss = self._sig_stream
+        self._wait_producers(ss, b, proxy)
+        with torch.cuda.stream(ss):
+            torch.ops.srb.fused_comm_bucket(*self._bucket_args(b, 1))
+            ev = torch.cuda.Event()
+            ev.record(ss)
+        self._sig_events[b] = ev
+        self._signalled.add(b)
+        if self.world_size > 1 or self.trace is not None:
+            self.launches += 1
+
+    def _launch(self, b: int, proxy) -> None:
+        """Exchange of bucket ``b`` on the comm stream: wait for the peers' flags, reduce, update, publish."""
+        if b not in self._signalled:
+            self._signal(b, proxy)
+        cs = self._comm_stream()
+        cs.wait_event(self._sig_events[b])       # includes the producers of my own gradients
+        self._events.pop(b, None)
+        with torch.cuda.stream(cs):
+            torch.ops.srb.fused_comm_bucket(*self._bucket_args(b, 2))
+        self.launches += self.kernels_for(b) - (1 if self.world_size > 1 else 0)
 
     def fused_step(self, proxy) -> None:
         if self.master is None:
@@ -411,10 +494,12 @@ class FusedSymmComm:
             self._sync_hyper()
         cur = torch.cuda.current_stream(self.device)
         while self._next < self.plan.n:
-            self._events.pop(self._next, None)       # everything is on / joined into the current stream by now
             self._launch(self._next, proxy)
             self._next += 1
         cur.wait_stream(self._comm_stream())
+        cur.wait_stream(self._sig_stream)
+        if self._zero_event is not None:
+            cur.wait_event(self._zero_event)         # (already reached by every gradient writer; joins the capture)
         self._hooked = False
         self._waited = 0
         if self.terminal_wait and self.world_size > 1:

@@ -222,6 +222,7 @@ class ShardedSyncProxy:
         self._grad_order: List[KeyT] = []           # gradient-completion order of the first step(s)
         self._order_taken = not hasattr(self.comm, "set_order")
         self._hook = getattr(self.comm, "key_ready", None)
+        self._ensure_zeroed = getattr(self.comm, "ensure_zeroed", None)
         self._in_step = False
 
     # ---- ParamServer-facing ------------------------------------------------
@@ -239,8 +240,17 @@ class ShardedSyncProxy:
     def get_param(self, id: int, name: str) -> torch.Tensor:
         return self._views_p[make_key(id, name)]
 
+    def _before_grad_write(self) -> None:
+        """A gradient is about to be written: a lazily begun step (generic path: nobody called
+        ``begin_step``) starts here, and the writer is ordered after this step's accumulator clear."""
+        if not self._in_step:
+            self.begin_step(overlap=False)
+        if self._ensure_zeroed is not None:
+            self._ensure_zeroed()
+
     def inc_grad(self, id: int, name: str, value: torch.Tensor) -> None:
         key = make_key(id, name)
+        self._before_grad_write()
         view = self._views_g[key]
         if value.data_ptr() != view.data_ptr():          # kernels may have written in place
             view.add_(value.reshape(view.shape))
@@ -252,11 +262,13 @@ class ShardedSyncProxy:
 
     def set_grad(self, id: int, name: str, value: torch.Tensor) -> None:
         key = make_key(id, name)
+        self._before_grad_write()
         self._views_g[key].copy_(value.reshape(self._views_g[key].shape))
         self._grad_counts[key] = 1
 
     def grad_buffer(self, id: int, name: str) -> torch.Tensor:
         """Destination view for kernels that accumulate a gradient in place."""
+        self._before_grad_write()
         return self._views_g[make_key(id, name)]
 
     # ---- worker-facing (protocol compatibility) -------------------------------

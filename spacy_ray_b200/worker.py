@@ -399,7 +399,10 @@ class Worker:
             acc = int(self.T["accumulate_gradient"])
             self.nlp._trainer = Trainer(self.nlp, self.proxy, examples, docs_per_batch=min(cap, len(examples)),
                                         dropout=float(self.T["dropout"]), prefetch=False,
-                                        exchange=(acc <= 1))      # accumulate_gradient > 1: exchange once per full batch
+                                        exchange=(acc <= 1),      # accumulate_gradient > 1: exchange once per full batch
+                                        # (with peers the per-step accumulator clear must not be replayed for
+                                        #  every micro-batch: same kernels, launched eagerly)
+                                        use_graphs=(acc <= 1 or self.num_workers == 1))
             logger.info("rank %d: device-resident training engine enabled", self.rank)
         except Exception as e:       # never fatal: the generic path is always available
             logger.warning("rank %d: fast path unavailable (%s); using the generic path", self.rank, e)

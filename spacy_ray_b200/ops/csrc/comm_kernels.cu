@@ -53,9 +53,9 @@ __device__ __forceinline__ void multimem_st_v4(float* mc, float4 v) {
                "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void multimem_st_v2_b32(void* mc, uint32_t a, uint32_t b) {
-  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(a)),
-               "f"(__uint_as_float(b))
+__device__ __forceinline__ void multimem_st_v4_b32(void* mc, const uint32_t v[4]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v[0])),
+               "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])), "f"(__uint_as_float(v[3]))
                : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
@@ -247,32 +247,29 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
       const float norm = sqrtf(a.norms_sq[k]);
       if (norm >= clip) scale = clip / fmaxf(norm, 1e-30f);
     }
-    // two passes of two vectors each: 2 x 5 independent 16-byte loads in flight per thread and few
-    // enough live registers (80) that three CTAs fit on an SM - or one NEXT TO a tcgen05 GEMM CTA
+    // Two passes; in each a thread owns EIGHT consecutive elements: 2 x 5 independent 16-byte loads in
+    // flight, and the refreshed weights leave as ONE 16-byte bf16x8 store per thread and pass (8-byte
+    // multimem / peer stores were the slow part of this kernel with peers: half the payload per
+    // NVLink packet).  80 registers: three CTAs fit on an SM - or one NEXT TO a tcgen05 GEMM CTA.
     const float* gsrc = keep_red ? a.red : (my_grad + s0);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      const int64_t t0 = base + threadIdx.x * 4 + half * 2048;
+      const int64_t idx = base + half * 2048 + threadIdx.x * 8;
+      if (idx >= end) continue;                       // key_len is a multiple of 128: all 8 or none
       float4 g4[2], w4[2], a4[2], b4[2], e4[2];
-      bool ok[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int64_t idx = t0 + j * 1024;
-        ok[j] = idx < end;
-        if (ok[j]) {
-          g4[j] = *(const float4*)(gsrc + idx);
-          w4[j] = *(const float4*)(a.master + idx);
-          if (a.opt_mode != kOptSGD) {
-            a4[j] = *(const float4*)(a.m1 + idx);
-            b4[j] = *(const float4*)(a.m2 + idx);
-          }
-          if (a.avg) e4[j] = *(const float4*)(a.avg + idx);
+        g4[j] = *(const float4*)(gsrc + idx + 4 * j);
+        w4[j] = *(const float4*)(a.master + idx + 4 * j);
+        if (a.opt_mode != kOptSGD) {
+          a4[j] = *(const float4*)(a.m1 + idx + 4 * j);
+          b4[j] = *(const float4*)(a.m2 + idx + 4 * j);
         }
+        if (a.avg) e4[j] = *(const float4*)(a.avg + idx + 4 * j);
       }
+      uint32_t packed[4];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if (!ok[j]) continue;
-        const int64_t idx = t0 + j * 1024;
         float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w}, wv[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
         float av[4] = {a4[j].x, a4[j].y, a4[j].z, a4[j].w}, bv[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
 #pragma unroll
@@ -288,29 +285,30 @@ __global__ void __launch_bounds__(256, 3) bucket_update_kernel(FusedCommArgs a) 
           }
           if (wd && l2 != 0.f) wv[e] *= (1.f - lr * l2);
         }
-        *(float4*)(a.master + idx) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        *(float4*)(a.master + idx + 4 * j) = make_float4(wv[0], wv[1], wv[2], wv[3]);
         if (a.opt_mode != kOptSGD) {
-          *(float4*)(a.m1 + idx) = make_float4(av[0], av[1], av[2], av[3]);
-          *(float4*)(a.m2 + idx) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+          *(float4*)(a.m1 + idx + 4 * j) = make_float4(av[0], av[1], av[2], av[3]);
+          *(float4*)(a.m2 + idx + 4 * j) = make_float4(bv[0], bv[1], bv[2], bv[3]);
         }
         if (a.avg) {
           float ev[4] = {e4[j].x, e4[j].y, e4[j].z, e4[j].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) ev[e] -= avg_mix * (ev[e] - wv[e]);
-          *(float4*)(a.avg + idx) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+          *(float4*)(a.avg + idx + 4 * j) = make_float4(ev[0], ev[1], ev[2], ev[3]);
         }
-        if (W == 1) *(float4*)(my_grad + s0 + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(wv[0], wv[1]);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(wv[2], wv[3]);
-        const uint32_t ulo = *(uint32_t*)&lo, uhi = *(uint32_t*)&hi;
-        if (a.param_mc) {
-          multimem_st_v2_b32((__nv_bfloat16*)a.param_mc + s0 + idx, ulo, uhi);
-        } else {
+        if (W == 1) *(float4*)(my_grad + s0 + idx + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(wv[0], wv[1]);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(wv[2], wv[3]);
+        packed[2 * j] = *(const uint32_t*)&lo;
+        packed[2 * j + 1] = *(const uint32_t*)&hi;
+      }
+      if (a.param_mc) {
+        multimem_st_v4_b32((__nv_bfloat16*)a.param_mc + s0 + idx, packed);
+      } else {
 #pragma unroll 8
-          for (int p = 0; p < W; ++p) {
-            const int peer = (rank + p) % W;
-            *(uint2*)((__nv_bfloat16*)a.param[peer] + s0 + idx) = make_uint2(ulo, uhi);
-          }
+        for (int p = 0; p < W; ++p) {
+          const int peer = (rank + p) % W;
+          *(uint4*)((__nv_bfloat16*)a.param[peer] + s0 + idx) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
       }
     }

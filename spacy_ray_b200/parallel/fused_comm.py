@@ -193,9 +193,11 @@ class FusedSymmComm:
         if os.environ.get("SRB_COMM_TRACE", "0") == "1":
             self.enable_trace()
         total = layout.total
-        # NVLS (multimem.ld_reduce / multimem.st through the NVSwitch) whenever a multicast mapping
-        # exists; SRB_NVLS=0 forces the plain peer-pointer variant.
-        self.use_nvls = os.environ.get("SRB_NVLS", "1") != "0"
+        # NVLS (multimem.ld_reduce / multimem.st through the NVSwitch: the switch does the fan-in / fan-out)
+        # from 4 ranks up; with 2 ranks plain peer loads/stores have the shorter round trip (measured:
+        # profiles/r2_exchange_trace_2gpu.md).  SRB_NVLS=1 / 0 forces it on / off.
+        env_nvls = os.environ.get("SRB_NVLS", "auto")
+        self.use_nvls = (world_size >= 4) if env_nvls not in ("0", "1") else env_nvls == "1"
         if world_size > 1:
             import torch.distributed as dist
 

@@ -324,10 +324,13 @@ def run_arm(args, impl: str, rank: int, world: int, local_rank: int):
                             [trainer.rows_for(ids) for ids in id_batches[n_total:]])
     for item in dev_inputs[1: warmup]:
         device_step(item)
-    barrier()
     launches0 = ops.launches + getattr(proxy.comm, "launches", 0)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    # the sampler thread (NVML init, ~ms, different on every rank) starts BEFORE the barrier: the start
+    # event must follow the barrier immediately, or the rank that gets going first spends the difference
+    # waiting for its peers inside its first timed step and max-over-ranks reports start skew as step time
     with ClockSampler(local_rank) as clocks:
+        barrier()
         evs[0].record()
         for i, item in enumerate(dev_inputs[warmup: n_total]):
             device_step(item)
@@ -353,10 +356,10 @@ def run_arm(args, impl: str, rank: int, world: int, local_rank: int):
         for i in range(warmup):
             trainer.prepare(rest[i + 1])
             trainer.train_step()
-        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         docs_local = 0
         with ClockSampler(local_rank) as clocks_e:
+            barrier()
             e0.record()
             for i in range(warmup, n_total):
                 trainer.prepare(rest[i + 1])          # prefetch the NEXT batch while this one runs

@@ -116,7 +116,11 @@ class B200Ops(TorchOps):
 
     # ------------------------------------------------------------------ GEMM helpers
     def _tc_ok(self, *dims: int) -> bool:
-        return self.use_tc and all(d % 64 == 0 and d > 0 for d in dims)
+        """Dimensions the tcgen05 kernels take: multiples of 16 (UMMA N granularity; TMA needs 16-byte
+        row pitches).  K need not be a multiple of the 64-element k-block and N not of the tile width:
+        the TMA zero-fills what lies outside the tensor and the epilogue masks the partial last tile
+        (width 96 - BASELINE config 1's model - went to cuBLAS + seq2col in round 1)."""
+        return self.use_tc and all(d % 16 == 0 and d > 0 for d in dims)
 
     def tc_gemm(self, A, B, out, *, mode, epi, block_n, M, N, K, a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,),
                 b_col_off=(0,), splits=1, win_w=0, bias=None, which=None, add_src=None, row_scale=None, m_dev=None,
@@ -128,10 +132,13 @@ class B200Ops(TorchOps):
 
     @staticmethod
     def _pick_block_n(N: int, options=(256, 192, 128, 64)) -> int:
+        """Widest tile that divides N; otherwise the tile that wastes the least of a masked last tile."""
         for bn in options:
             if N % bn == 0:
                 return bn
-        return 0
+        if N % 16:
+            return 0
+        return min(options, key=lambda bn: (-(-N // bn) * bn, -bn))
 
     def _linear_tc(self, X: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         M, K = X.shape
@@ -151,10 +158,16 @@ class B200Ops(TorchOps):
         columns are zero); ``out`` may then be the (n_valid, k) gradient buffer itself."""
         T, N = dZ.shape
         w = X.shape[1]
-        Kt = w * (3 if window else 1)
-        # N % 64: a 64-row operand fills half of the 128-row M tile, the TMA zero-fills the rest
-        if not (self.use_tc and self.tc_dw and N % 64 == 0 and w % 64 == 0):
+        if not (self.use_tc and self.tc_dw and N % 16 == 0 and w % 16 == 0):
             return None
+        if window and w % 64:
+            # the in-kernel window shift needs N tiles that do not straddle two shifts (64-column atoms):
+            # for other widths the window is materialised once (seq2col) and the GEMM is a plain one
+            X = self.k.seq2col(X.contiguous())
+            self.launches += 1
+            w, window = X.shape[1], 0
+        Kt = w * (3 if window else 1)
+        # partial tiles: a 64-row operand fills half of the 128-row M tile, the TMA zero-fills the rest
         bn = 256 if w % 256 == 0 else (128 if w % 128 == 0 else 64)
         rows = N if n_valid is None else int(n_valid)
         if out is None:
@@ -210,9 +223,10 @@ class B200Ops(TorchOps):
         m1 = _mask1d(mask)
         drop = float(dropout) if (is_train and dropout > 0.0) else 0.0
         w_in = X.shape[1]
-        use_tc = nP == 3 and self._tc_ok(nO, w_in) and window in (0, 1)
+        use_tc = nP == 3 and self._tc_ok(w_in) and nO % 32 == 0 and window in (0, 1)
         if use_tc:
             # one tcgen05 kernel: (window) GEMM + bias + maxout; then LN/dropout/residual
+            fwd_bn = 192 if nO % 64 == 0 else 96            # a tile holds all 3 pieces of 64 / 32 units
             H = torch.empty((Tp, nO), dtype=torch.bfloat16, device=X.device)
             which = torch.empty((Tp, nO), dtype=torch.uint8, device=X.device)
             if window:
@@ -220,7 +234,7 @@ class B200Ops(TorchOps):
                               b_col_off=(0, w_in, 2 * w_in))
             else:
                 shifts = {}
-            self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=192, M=Tp, N=nO * nP, K=w_in,
+            self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=fwd_bn, M=Tp, N=nO * nP, K=w_in,
                          bias=b.reshape(-1), which=which, gate=self._gate(W, b, G, beta), **shifts)
             Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed,
                                                        self.seed_dev)

@@ -34,7 +34,8 @@ void tc_gemm(const Tensor& A, const Tensor& B, Tensor out, int64_t mode, int64_t
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "tc_gemm: row-major 2D operands");
   TORCH_CHECK((A.stride(0) * 2) % 16 == 0 && (B.stride(0) * 2) % 16 == 0, "tc_gemm: row pitch must be 16B aligned");
   TORCH_CHECK(((uintptr_t)A.data_ptr() % 16) == 0 && ((uintptr_t)B.data_ptr() % 16) == 0, "tc_gemm: 16B-aligned bases");
-  TORCH_CHECK(N % block_n == 0, "tc_gemm: N must be a multiple of block_n");
+  TORCH_CHECK(N % 16 == 0 && (epi != EPI_MAXOUT3 || N % block_n == 0),
+              "tc_gemm: N must be a multiple of 16 (of block_n for the maxout epilogue)");
   TORCH_CHECK(N <= 4096 || !(bias.has_value() && bias->defined()), "tc_gemm: bias supported for N <= 4096");
   const int n_shifts = (int)a_row_shift.size();
   TORCH_CHECK(n_shifts >= 1 && n_shifts <= 3 && a_col_off.size() == a_row_shift.size() &&

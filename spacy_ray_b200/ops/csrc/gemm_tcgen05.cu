@@ -91,7 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
   const int m_tiles = (p.M + BM - 1) / BM;
-  const int n_tiles = p.N / BLOCK_N;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;    // a partial last N tile is masked in the epilogue (TMA zero-fills B)
   const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
   const int total_kb = (MODE != MODE_MNMN && !HALO ? p.n_shifts : 1) * kpb;
   const int splits = p.splits > 0 ? p.splits : 1;
@@ -360,6 +360,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (c + hh * 16 >= HN) break;
               float* vv = v + hh * 16;
               const int cc = c + hh * 16;
+              if (n0 + cc >= p.N) break;                 // partial last N tile (N % 16 == 0): nothing to store
               if (p.bias) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) vv[i] += bias_s[n0 + cc + i];
@@ -419,7 +420,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float* dst = out + (size_t)row * p.ldo + n0 + c;
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
-              if (c + i < HN) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (c + i < HN && n0 + c + i < p.N) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
         }
       }
@@ -480,7 +481,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.N / BLOCK_N;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int m_groups = (m_tiles + CL - 1) / CL;
   const int items = m_groups * n_tiles * (p.splits > 0 ? p.splits : 1);
   int clusters = num_sms / CL;
@@ -544,6 +545,7 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
   SRB_CASE1(64, MODE_KK, EPI_STORE)
   SRB_CASE(192, MODE_KK, EPI_MAXOUT3)
   SRB_CASE1(96, MODE_KK, EPI_MAXOUT3)
+  SRB_CASE1(96, MODE_KK, EPI_STORE)
   SRB_CASE(256, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE(128, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE1(64, MODE_MNMN, EPI_ATOMIC_F32)

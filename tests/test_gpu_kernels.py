@@ -209,7 +209,8 @@ def test_tc_dw_mn_major_split_k(ops, ref, window, cluster, w, N):
 
 # ---------------------------------------------------------------------------- fused blocks
 @pytest.mark.parametrize("use_tc", [False, True])
-@pytest.mark.parametrize("window,residual,w", [(0, False, 64), (1, True, 64), (1, True, 256)])
+@pytest.mark.parametrize("window,residual,w", [(0, False, 64), (1, True, 64), (1, True, 256), (1, True, 96), (0, False, 96),
+                                                (1, True, 160)])
 def test_maxout_block_fwd_bwd(ref, use_tc, window, residual, w):
     from spacy_ray_b200.ops.b200_ops import B200Ops
 
@@ -291,6 +292,37 @@ def test_adam_shard_matches_reference(ops, ref):
     _close(m2, m2r, 1e-4, 1e-7, "adam m2")
     _close(w_bf, wr, 1e-2, 1e-2, "adam bf16 out")
     assert float(g.abs().sum()) == 0.0
+
+
+def test_width_96_runs_on_the_tcgen05_kernels_not_on_the_library_path(ops):
+    """BASELINE config 1's model (tok2vec width 96): K = 96 / 288 is not a multiple of the 64-element
+    k-block and N = 96 / 288 not of any tile width.  Round 1 sent it to cuBLAS + seq2col; now the TMA
+    zero-fills the K tail and the epilogue masks the partial last N tile - count the launches."""
+    torch.manual_seed(11)
+    w, nO, nP = 96, 96, 3
+    X, mask = _padded_batch((5, 17, 40, 2), w)
+    Xb = X.bfloat16()
+    W = (torch.randn(nO, nP, 3 * w, device="cuda") * 0.1).bfloat16()
+    b = (torch.randn(nO, nP, device="cuda") * 0.1).bfloat16()
+    G = torch.ones(nO, device="cuda").bfloat16()
+    beta = torch.zeros(nO, device="cuda").bfloat16()
+    l0 = ops.launches
+    Y, ctx = ops.maxout_block(Xb, W, b, G, beta, mask, window=1, residual=True, dropout=0.0, is_train=True, seed=3)
+    assert ops.launches - l0 == 2, "forward = one tcgen05 GEMM (window + bias + maxout) + one LN kernel"
+    dY = (torch.randn_like(Y.float()) * mask).bfloat16()
+    l0 = ops.launches
+    dX, dW, db, dG, dbeta = ops.maxout_block_backward(dY, ctx)
+    torch.cuda.synchronize()
+    # LN-bwd + seq2col (window materialised for the split-K dW at this width) + dW GEMM + dX GEMM
+    assert ops.launches - l0 == 4, ops.launches - l0
+    # linear layers at K = 96 (tagger / transition heads on a width-96 tok2vec)
+    Wl = (torch.randn(64, 96, device="cuda") * 0.1).bfloat16()
+    bl = torch.zeros(64, device="cuda").bfloat16()
+    l0 = ops.launches
+    out = ops.linear(Xb, Wl, bl)
+    assert ops.launches - l0 == 1
+    want = Xb.float() @ Wl.float().t()
+    _close(out, want, 2e-2, 2e-2 * math.sqrt(96), "linear K=96")
 
 
 # ---------------------------------------------------------------------------- K7

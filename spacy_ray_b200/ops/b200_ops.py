@@ -25,6 +25,7 @@ Environment switches (all default to the fast path): ``SRB_USE_TC``, ``SRB_TC_DW
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from pathlib import Path
 from typing import Any, Dict, Optional
@@ -90,6 +91,7 @@ class B200Ops(TorchOps):
         # leaves idle in its last, partial wave (201 M-tiles on 148 SMs = 1.36 waves).  The
         # consumer of the bucket (ShardedSyncProxy.step) joins the stream.
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
+        self._pdl_side = os.environ.get("SRB_PDL_SIDE", "0") == "1"
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
         self._ws: Dict[tuple, torch.Tensor] = {}
@@ -262,6 +264,21 @@ class B200Ops(TorchOps):
         self._side_pending = True
         return self._side
 
+    @contextlib.contextmanager
+    def _side_launches(self, *tensors: torch.Tensor):
+        """Launch on the side stream.  Programmatic dependent launch (csrc/launch.h) is switched off
+        for these launches: their predecessor is an event of the main stream, not the previous
+        kernel of their own stream (``SRB_PDL_SIDE=1`` keeps it on)."""
+        with torch.cuda.stream(self._fork_side(*tensors)):
+            if self._pdl_side:
+                yield
+                return
+            was = self.k.set_pdl(False)
+            try:
+                yield
+            finally:
+                self.k.set_pdl(was)
+
     def join_side(self) -> None:
         """Make the current stream wait for the side-stream gradient GEMMs (no-op if none ran)."""
         if self._side_pending:
@@ -328,7 +345,7 @@ class B200Ops(TorchOps):
         if dW_dst is not None and not (dW_dst.dtype == torch.float32 and dW_dst.is_contiguous()):
             dW_dst = None
         if dW_dst is not None and self.side_dw and self.use_tc and self.tc_dw:
-            with torch.cuda.stream(self._fork_side(dZ, X)):
+            with self._side_launches(dZ, X):
                 dW = self._dw_tc(dZ, X, window, out=dW_dst.view(nO * nP, nI))
             if dW is None:
                 self.join_side()

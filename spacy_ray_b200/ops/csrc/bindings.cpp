@@ -320,6 +320,12 @@ TORCH_LIBRARY(srb, m) {
   m.def("arc_eager_capacity(int nO, int nP, int nA) -> int", [](int64_t nO, int64_t nP, int64_t nA) -> int64_t {
     return (int64_t)srb::arc_eager_max_doc_len((int)nO, (int)nP, (int)nA);
   });
+  // programmatic dependent launch switch (launch.h): returns the previous setting
+  m.def("set_pdl(bool on) -> bool", [](bool on) -> bool {
+    const bool was = srb::g_pdl != 0;
+    srb::g_pdl = on ? 1 : 0;
+    return was;
+  });
   m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
   srb::register_gemm_ops(m);
   srb::register_comm_ops(m);

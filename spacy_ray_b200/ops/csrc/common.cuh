@@ -48,6 +48,12 @@ __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint64_t idx, uint
   }
 }
 
+// Programmatic dependent launch (see launch.h): let the next kernel of the stream be scheduled
+// now, and hold this one's first global access until its predecessor has completed and flushed.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

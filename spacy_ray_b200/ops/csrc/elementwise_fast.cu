@@ -7,6 +7,7 @@
 //     table-row updates once per run (vector RED).  The unsorted kernel hammered ~50 hot
 //     PREFIX/SHAPE rows with one atomic per token per element.
 #include "common.cuh"
+#include "launch.h"
 #include "kernels.h"
 
 namespace srb {
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
     const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ Y, uint8_t* __restrict__ which, __nv_bfloat16* __restrict__ xhat_out,
     float* __restrict__ rstd_out, int Tp, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
+  pdl_prologue();
   constexpr int nO = 32 * UPL;
   constexpr int ZPL = UPL * NP;                 // Z elements per lane (multiple of 8)
   if (seed_dev) seed += (uint64_t)*seed_dev;
@@ -140,7 +142,7 @@ static void launch_fwd_vec(const void* Z, const void* bias, const void* G, const
   int blocks = (Tp + 8 * R - 1) / (8 * R);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  maxout_ln_fwd_vec_kernel<NP, UPL, R><<<blocks, 256, 0, s>>>(
+  launch_k(maxout_ln_fwd_vec_kernel<NP, UPL, R>, blocks, 256, 0, s, 
       (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta,
       (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, drop_p, seed,
       seed_dev);
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
     const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ dZ, float* __restrict__ db, float* __restrict__ dG, float* __restrict__ dbeta, int Tp,
     float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
+  pdl_prologue();
   constexpr int nO = 32 * UPL;
   constexpr int ZPL = UPL * NP;
   if (seed_dev) seed += (uint64_t)*seed_dev;
@@ -300,7 +303,7 @@ static void launch_bwd_vec(const void* dY, const void* xhat, const float* rstd, 
     cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  maxout_ln_bwd_vec_kernel<NP, UPL, R><<<blocks, 256, smem, s>>>(
+  launch_k(maxout_ln_bwd_vec_kernel<NP, UPL, R>, blocks, 256, smem, s, 
       (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,
       (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln);
 }
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(128) hash_embed_bwd_sorted_kernel(const int64_
                                                                     const PermT* __restrict__ perm,
                                                                     const float* __restrict__ mask, HashEmbedTables t,
                                                                     const __nv_bfloat16* __restrict__ dY, int R) {
+  pdl_prologue();
   const int a = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -435,10 +439,10 @@ void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool pe
   if (R <= 0) return;
   dim3 grid((R + kSortChunk * 4 - 1) / (kSortChunk * 4), t.n_tables);
   if (perm_is_i32)
-    hash_embed_bwd_sorted_kernel<int32_t><<<grid, 128, 0, s>>>(keys, (const int32_t*)perm, mask, t,
+    launch_k(hash_embed_bwd_sorted_kernel<int32_t>, grid, 128, 0, s, keys, (const int32_t*)perm, mask, t,
                                                                (const __nv_bfloat16*)dY, R);
   else
-    hash_embed_bwd_sorted_kernel<int64_t><<<grid, 128, 0, s>>>(keys, (const int64_t*)perm, mask, t,
+    launch_k(hash_embed_bwd_sorted_kernel<int64_t>, grid, 128, 0, s, keys, (const int64_t*)perm, mask, t,
                                                                (const __nv_bfloat16*)dY, R);
 }
 
@@ -449,6 +453,7 @@ void launch_hash_embed_bwd_sorted(const int64_t* keys, const void* perm, bool pe
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ out,
                                                           int T, int C, int ld, int rows_per_block, int n_valid) {
+  pdl_prologue();
   extern __shared__ float cs_red[];                 // [rsubs][C]
   const int c8 = C / 8;
   const int rsubs = blockDim.x / c8;
@@ -493,7 +498,7 @@ bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, int
   if (rows_per_block < 4 * rsubs) rows_per_block = 4 * rsubs;
   blocks = (T + rows_per_block - 1) / rows_per_block;
   const size_t smem = sizeof(float) * (size_t)rsubs * C;     // <= 256 * 8 * 4 = 8 KB
-  colsum_bf16_kernel<<<blocks, 256, smem, s>>>((const __nv_bfloat16*)X, out, T, C, ld, rows_per_block,
+  launch_k(colsum_bf16_kernel, blocks, 256, smem, s, (const __nv_bfloat16*)X, out, T, C, ld, rows_per_block,
                                                n_valid > 0 ? n_valid : C);
   return true;
 }
@@ -505,6 +510,7 @@ bool try_launch_colsum_bf16(const void* X, float* out, int T, int C, int ld, int
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) f32_to_bf16_zero_kernel(float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                size_t n8) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     float4* p = (float4*)(src + i * 8);
     const float4 a = p[0], b = p[1];
@@ -522,7 +528,7 @@ void launch_f32_to_bf16_zero(float* src, void* dst, size_t n, cudaStream_t s) {
   if (n8 == 0) return;
   size_t blocks = (n8 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  f32_to_bf16_zero_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, (__nv_bfloat16*)dst, n8);
+  launch_k(f32_to_bf16_zero_kernel, (unsigned)blocks, 256, 0, s, src, (__nv_bfloat16*)dst, n8);
 }
 
 }  // namespace srb

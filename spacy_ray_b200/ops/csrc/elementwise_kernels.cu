@@ -1,10 +1,17 @@
 // Fused non-GEMM kernels of the tok2vec / tagger hot path.
 // Each one replaces a chain of thinc/cupy launches with a single pass over HBM.
+#include <cstdlib>
 #include "common.cuh"
+#include "launch.h"
 #include "gate.cuh"
 #include "kernels.h"
 
 namespace srb {
+
+// programmatic dependent launch switch (launch.h): off unless SRB_PDL=1 - measured 1.8 % SLOWER on the
+// flagship step (profiles/r2_pdl.md): the captured step keeps the GPU busy, there is no launch gap to hide
+int g_pdl = []() { const char* e = getenv("SRB_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
+
 
 // =====================================================================================
 // K1  MultiHashEmbed forward: hash -> 4-row gather-sum -> concat, one pass.
@@ -13,6 +20,7 @@ __global__ void __launch_bounds__(256) hash_embed_fwd_kernel(const int64_t* __re
                                                              const float* __restrict__ mask, HashEmbedTables t,
                                                              __nv_bfloat16* __restrict__ out, int Tp,
                                                              GateArgs gate) {
+  pdl_prologue();
   const int row = blockIdx.x;
   const int C = t.n_tables * t.width;
   const bool live = mask[row] != 0.0f;
@@ -54,13 +62,14 @@ void launch_hash_embed_fwd(const int64_t* attrs, const float* mask, HashEmbedTab
   if (Tp <= 0) return;
   int C = t.n_tables * t.width;
   int threads = C / 8 < 256 ? ((C / 8 + 31) / 32) * 32 : 256;
-  hash_embed_fwd_kernel<<<Tp, threads, 0, s>>>(attrs, mask, t, (__nv_bfloat16*)out, Tp, gate);
+  launch_k(hash_embed_fwd_kernel, Tp, threads, 0, s, attrs, mask, t, (__nv_bfloat16*)out, Tp, gate);
 }
 
 // K1 backward: scatter-add into the fp32 table gradients.
 __global__ void __launch_bounds__(256) hash_embed_bwd_kernel(const int64_t* __restrict__ attrs,
                                                              const float* __restrict__ mask, HashEmbedTables t,
                                                              const __nv_bfloat16* __restrict__ dY, int Tp) {
+  pdl_prologue();
   const int row = blockIdx.x;
   if (mask[row] == 0.0f) return;
   const int C = t.n_tables * t.width;
@@ -89,7 +98,7 @@ void launch_hash_embed_bwd(const int64_t* attrs, const float* mask, HashEmbedTab
   if (Tp <= 0) return;
   int C = t.n_tables * t.width;
   int threads = C / 8 < 256 ? ((C / 8 + 31) / 32) * 32 : 256;
-  hash_embed_bwd_kernel<<<Tp, threads, 0, s>>>(attrs, mask, t, (const __nv_bfloat16*)dY, Tp);
+  launch_k(hash_embed_bwd_kernel, Tp, threads, 0, s, attrs, mask, t, (const __nv_bfloat16*)dY, Tp);
 }
 
 // =====================================================================================
@@ -103,6 +112,7 @@ __global__ void __launch_bounds__(128) maxout_ln_fwd_kernel(
     const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ Y, uint8_t* __restrict__ which, __nv_bfloat16* __restrict__ xhat_out,
     float* __restrict__ rstd_out, int Tp, int nO, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (seed_dev) seed += (uint64_t)*seed_dev;     // device-side stream position (advances per CUDA-graph replay)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,7 +192,7 @@ void launch_maxout_ln_fwd(const void* Z, const void* bias, const void* G, const 
   if (blocks > 148 * 16) blocks = 148 * 16;
   size_t smem = (size_t)4 * nO * nP * sizeof(__nv_bfloat16);
 #define SRB_LAUNCH(NP)                                                                                   \
-  maxout_ln_fwd_kernel<NP><<<blocks, 128, smem, s>>>(                                                    \
+  launch_k(maxout_ln_fwd_kernel<NP>, blocks, 128, smem, s,                                                     \
       (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta, \
       (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, nO, drop_p, seed, \
       seed_dev)
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(128) maxout_ln_bwd_kernel(
     const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ dZ, float* __restrict__ db, float* __restrict__ dG, float* __restrict__ dbeta,
     int Tp, int nO, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (seed_dev) seed += (uint64_t)*seed_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,7 +319,7 @@ void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, c
   do {                                                                                                          \
     if (smem > 48 * 1024)                                                                                       \
       cudaFuncSetAttribute(maxout_ln_bwd_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    maxout_ln_bwd_kernel<NP><<<blocks, 128, smem, s>>>(                                                         \
+    launch_k(maxout_ln_bwd_kernel<NP>, blocks, 128, smem, s,                                                          \
         (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,       \
         (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, nO, drop_p, seed, seed_dev, has_ln);                                       \
   } while (0)
@@ -322,6 +333,7 @@ void launch_maxout_ln_bwd(const void* dY, const void* xhat, const float* rstd, c
 // K4 (library-GEMM path only): materialised window and its adjoint.
 // =====================================================================================
 __global__ void seq2col_kernel(const bf16x8* __restrict__ X, bf16x8* __restrict__ Xw, int Tp, int nI8) {
+  pdl_prologue();
   const size_t total = (size_t)Tp * 3 * nI8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (3 * nI8));
@@ -342,12 +354,13 @@ void launch_seq2col(const void* X, void* Xw, int Tp, int nI, cudaStream_t s) {
   size_t total = (size_t)Tp * 3 * (nI / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  seq2col_kernel<<<blocks, 256, 0, s>>>((const bf16x8*)X, (bf16x8*)Xw, Tp, nI / 8);
+  launch_k(seq2col_kernel, blocks, 256, 0, s, (const bf16x8*)X, (bf16x8*)Xw, Tp, nI / 8);
 }
 
 __global__ void col2seq_residual_kernel(const bf16x8* __restrict__ dXw, const bf16x8* __restrict__ dY,
                                         const float* __restrict__ mask, bf16x8* __restrict__ dX, int Tp, int nI8,
                                         int add_res) {
+  pdl_prologue();
   const size_t total = (size_t)Tp * nI8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % nI8);
@@ -384,7 +397,7 @@ void launch_col2seq_residual(const void* dXw, const void* dY, const float* mask,
   size_t total = (size_t)Tp * (nI / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  col2seq_residual_kernel<<<blocks, 256, 0, s>>>((const bf16x8*)dXw, (const bf16x8*)dY, mask, (bf16x8*)dX, Tp,
+  launch_k(col2seq_residual_kernel, blocks, 256, 0, s, (const bf16x8*)dXw, (const bf16x8*)dY, mask, (bf16x8*)dX, Tp,
                                                  nI / 8, add_residual);
 }
 
@@ -396,6 +409,7 @@ __global__ void __launch_bounds__(128) softmax_xent_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ d_out,
                                                            int64_t* __restrict__ guesses, float* __restrict__ loss,
                                                            int Tp, int nC) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float local_loss = 0.f;
   for (int row = blockIdx.x * 4 + warp; row < Tp; row += gridDim.x * 4) {
@@ -445,7 +459,7 @@ void launch_softmax_xent(const float* logits, const int64_t* labels, void* d_out
   if (Tp <= 0) return;
   int blocks = (Tp + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  softmax_xent_kernel<<<blocks, 128, 0, s>>>(logits, labels, (__nv_bfloat16*)d_out, guesses, loss, Tp, nC);
+  launch_k(softmax_xent_kernel, blocks, 128, 0, s, logits, labels, (__nv_bfloat16*)d_out, guesses, loss, Tp, nC);
 }
 
 // =====================================================================================

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gate.cuh"
 #include "gemm_launch.h"
+#include "launch.h"
 #include "gemm_tcgen05.cuh"
 
 namespace srb {
@@ -88,8 +89,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
   float* bias_s = (float*)(smem + C::kStages * C::kStage + 256);
 
+  pdl_trigger();          // the next kernel of the stream may be scheduled behind this one's CTAs (launch.h)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;    // a partial last N tile is masked in the epilogue (TMA zero-fills B)
   const int kpb = (p.K + BK - 1) / BK;                   // k-blocks per shift
@@ -120,21 +121,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr); else tmem_alloc<C::kTmemCols>(tmem_ptr); }
-  if (p.bias && warp >= 2 && p.gate.flags == nullptr) {      // bias -> smem (fp32) once per CTA
-    for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
-  }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (p.gate.flags != nullptr) {
-    // gated launch: the bias is part of the freshly published bucket, read it only now (after the
-    // gate + barrier above), then sync the epilogue warps among themselves
-    if (warp == 0) fence_proxy_async_global();               // peers' generic-proxy stores -> my TMA loads
-    if (p.bias && warp >= 2) {
-      for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
-      asm volatile("bar.sync 1, %0;" ::"n"(kNumThreads - 64) : "memory");
-    }
+  // everything above touched no global memory (descriptors are kernel parameters; gate flags are
+  // written by peers, not by the stream predecessor): with programmatic dependent launch it ran
+  // under the tail of the previous kernel.  From here on its outputs are read and buffers it may
+  // still be reading are written.
+  pdl_wait();
+  const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
+  // gated launch: peers' generic-proxy stores (the freshly published bucket) -> my TMA loads
+  if (p.gate.flags != nullptr && warp == 0) fence_proxy_async_global();
+  if (p.bias && warp >= 2) {                                 // bias -> smem (fp32) once per CTA, epilogue warps only
+    for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kNumThreads - 64) : "memory");
   }
 
   if (warp == 0) {
@@ -492,11 +493,13 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // launch.h
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO>, a, b, p);
 }
 

@@ -141,5 +141,6 @@ struct ArcArgs {
 };
 bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s);
 int arc_eager_max_doc_len(int nO, int nP, int nA);
+extern int g_pdl;                                      // launch.h
 
 }  // namespace srb

@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launch.h"
 #include "kernels.h"
 #include "transition_common.cuh"
 
@@ -42,6 +43,7 @@ __device__ __forceinline__ void load_slot(const __nv_bfloat16* __restrict__ Yf, 
 // NJ = ceil(nA / 32) actions per lane, PPL = nO*nP/32 pre-activations per lane (nP == 2).
 template <int NJ, int PPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) biluo_steps_kernel(BiluoArgs A) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int UPL = PPL / 2;
   const int nO = A.nO, nOP = A.nO * 2, nA = A.nA;
@@ -214,6 +216,7 @@ constexpr int kWuStride = 72;        // bf16 elements per W_u row in smem: 144 B
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 8) biluo_block_kernel(BiluoArgs A) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nO = A.nO, nOP = A.nO * 2, nA = A.nA;
   __nv_bfloat16* Wu_s = (__nv_bfloat16*)smem_raw;                       // [nA_pad][kWuStride]
@@ -375,7 +378,7 @@ static bool launch_biluo_block(const BiluoArgs& a, cudaStream_t s) {
   if (a.nP != 2 || a.nO * 2 > kBlkThreads || a.nA_pad > kBlkThreads || a.nO % 8 != 0 || a.nO > kWuStride) return false;
   const size_t smem = sizeof(__nv_bfloat16) * (size_t)a.nA_pad * kWuStride + sizeof(float) * (2 * a.nO + 2 * (kBlkThreads / 32)) +
                       sizeof(int) * (kBlkThreads / 32);
-  biluo_block_kernel<kBlkThreads><<<a.B, kBlkThreads, smem, s>>>(a);
+  launch_k(biluo_block_kernel<kBlkThreads>, a.B, kBlkThreads, smem, s, a);
   return true;
 }
 
@@ -386,7 +389,7 @@ static void launch_nj(const BiluoArgs& a, int blocks, size_t smem, cudaStream_t 
   if (ppl == P) {                                                                                               \
     if (smem > 48 * 1024)                                                                                       \
       cudaFuncSetAttribute(biluo_steps_kernel<NJ, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    biluo_steps_kernel<NJ, P><<<blocks, kWarpsPerBlock * 32, smem, s>>>(a);                                     \
+    launch_k(biluo_steps_kernel<NJ, P>, blocks, kWarpsPerBlock * 32, smem, s, a);                                     \
     return;                                                                                                     \
   }
   SRB_PPL(2) SRB_PPL(4) SRB_PPL(8)
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(128) transition_scatter_kernel(const __nv_bflo
                                                                  float* __restrict__ dYf, float* __restrict__ dpad,
                                                                  float* __restrict__ db, int S, int nF, int nO,
                                                                  int nP) {
+  pdl_prologue();
   extern __shared__ float sacc[];          // [nF+1][nOP]: dpad rows then db
   const int nOP = nO * nP;
   for (int i = threadIdx.x; i < (nF + 1) * nOP; i += blockDim.x) sacc[i] = 0.f;
@@ -448,7 +452,7 @@ void launch_transition_scatter(const void* d_hid, const uint8_t* which, const in
   int blocks = (S + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
   size_t smem = sizeof(float) * (size_t)(nF + 1) * nO * nP;
-  transition_scatter_kernel<<<blocks, 128, smem, s>>>((const __nv_bfloat16*)d_hid, which, feats, dYf, dpad, db, S,
+  launch_k(transition_scatter_kernel, blocks, 128, smem, s, (const __nv_bfloat16*)d_hid, which, feats, dYf, dpad, db, S,
                                                      nF, nO, nP);
 }
 

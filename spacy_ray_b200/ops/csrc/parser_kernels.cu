@@ -16,6 +16,7 @@
 // pass is the same three batched GEMMs + scatter kernel as for NER.
 // Spec: models/transitions.py::ArcEagerSystem and transition_model.py::_arc_steps_reference.
 #include "common.cuh"
+#include "launch.h"
 #include "kernels.h"
 #include "transition_common.cuh"
 
@@ -48,6 +49,7 @@ __device__ __forceinline__ ArcWarpState arc_state(unsigned char* base, int warp,
 
 template <int NP, int UPL, int NJ>
 __global__ void __launch_bounds__(kArcWarps * 32) arc_eager_steps_kernel(ArcArgs A) {
+  pdl_prologue();
   constexpr int PPL = NP * UPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nO = A.nO, nOP = A.nO * NP, nA = A.nA;
@@ -283,7 +285,7 @@ template <int NP, int UPL, int NJ>
 static void launch_arc(const ArcArgs& a, int blocks, size_t smem, cudaStream_t s) {
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(arc_eager_steps_kernel<NP, UPL, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  arc_eager_steps_kernel<NP, UPL, NJ><<<blocks, kArcWarps * 32, smem, s>>>(a);
+  launch_k(arc_eager_steps_kernel<NP, UPL, NJ>, blocks, kArcWarps * 32, smem, s, a);
 }
 
 template <int NP, int UPL>

@@ -6,6 +6,7 @@
 // d is written with a 128-multiple pitch (zero past n_classes) so dW = d^T X and dX = d W can go
 // straight to the tcgen05 GEMMs.
 #include "common.cuh"
+#include "launch.h"
 #include "kernels.h"
 #include "transition_common.cuh"
 
@@ -18,6 +19,7 @@ __global__ void __launch_bounds__(kTagWarps * 32) linear_softmax_xent_kernel(
     const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ b,
     const int64_t* __restrict__ labels, __nv_bfloat16* __restrict__ d_out, int64_t* __restrict__ guesses,
     float* __restrict__ loss, int Tp, int w, int nC, int nC_pad, int ldd) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* W4 = (float4*)smem_raw;                                   // [w/4][nC_pad] x float4
   float* b_s = (float*)smem_raw + (size_t)w * nC_pad;               // [nC_pad]
@@ -81,7 +83,7 @@ bool try_launch_linear_softmax_xent(const void* X, const void* W, const void* b,
   if (nj == NJ_) {                                                                                                \
     if (smem > 48 * 1024)                                                                                         \
       cudaFuncSetAttribute(linear_softmax_xent_kernel<NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    linear_softmax_xent_kernel<NJ_><<<blocks, kTagWarps * 32, smem, s>>>(                                          \
+    launch_k(linear_softmax_xent_kernel<NJ_>, blocks, kTagWarps * 32, smem, s,                                           \
         (const __nv_bfloat16*)X, (const __nv_bfloat16*)W, (const __nv_bfloat16*)b, labels, (__nv_bfloat16*)d_out,   \
         guesses, loss, Tp, w, nC, nC_pad, ldd);                                                                   \
     return true;                                                                                                  \

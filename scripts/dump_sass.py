@@ -30,21 +30,32 @@ HOT = [
     ("maxout_ln_bwd_vec", "maxout_ln_bwd_vec_kernelILi3ELi8ELi2E"),
     ("hash_embed_fwd", "hash_embed_fwd_kernel"),
     ("hash_embed_bwd_sorted_i32", "hash_embed_bwd_sorted_kernelIiE"),
+    ("biluo_block", "biluo_block_kernel"),
     ("biluo_steps", "biluo_steps_kernelILi3ELi4E"),
     ("arc_eager_steps", "arc_eager_steps_kernel"),
     ("transition_scatter", "transition_scatter_kernel"),
     ("linear_softmax_xent", "linear_softmax_xent_kernel"),
+    ("bucket_signal", "bucket_signal_kernel"),
+    ("bucket_wait", "bucket_wait_kernel"),
     ("bucket_reduce", "bucket_reduce_kernel"),
     ("bucket_update", "bucket_update_kernel"),
+    ("bucket_gate_zero", "bucket_gate_zero_kernel"),
     ("gate_wait", "gate_wait_kernel"),
     ("p2p_reduce_scatter", "p2p_reduce_scatter_kernel"),
     ("p2p_all_gather", "p2p_all_gather_kernel"),
     ("colsum_bf16", "colsum_bf16_kernel"),
     ("f32_to_bf16_zero", "f32_to_bf16_zero_kernel"),
 ]
-PROOF = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGMC", "STGMC",
-         "REDGMC", "MULTIMEM", "RED.E", "ATOMG", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "LD.E.STRONG.SYS", "ST.E.STRONG.SYS",
-         "LDG.E.STRONG.SYS", "STG.E.STRONG.SYS", "HMMA", "ELECT", "UCGABAR"]
+# matched on whole dot-separated fields of the opcode (so HMMA does not match UTCHMMA)
+PROOF = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGMC", "REDG",
+         "RED", "ATOMG", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "LDG.STRONG.SYS", "STG.STRONG.SYS", "STG.128.STRONG.SYS",
+         "HMMA", "ELECT", "UCGABAR", "PREEXIT", "ACQBULK"]
+
+
+def _has(op: str, proof: str) -> bool:
+    """True if the opcode starts with the proof's first field and carries its other fields."""
+    of, pf = op.split("."), proof.split(".")
+    return of[0] == pf[0] and all(f in of[1:] for f in pf[1:])
 
 
 def main() -> int:
@@ -91,10 +102,16 @@ def main() -> int:
                 n_ins += 1
                 op = m.group(1)
                 for p in PROOF:
-                    if op.startswith(p) or p in op:
+                    if _has(op, p):
                         ops[p] += 1
         proof = ", ".join(f"{k} x{v}" for k, v in sorted(ops.items(), key=lambda kv: -kv[1]) if v) or "-"
         index.append(f"| `sass/{short}.sass` | `{name[:90]}` | {n_ins} | {proof} |")
+    index += ["", "Reading the mnemonics: `UTCHMMA(.2CTA)` = `tcgen05.mma` (`cta_group::2`), `LDTM` = `tcgen05.ld`,",
+              "`UTCBAR` = `tcgen05.commit`, `UTMALDG` = TMA tensor load, `SYNCS` = mbarrier ops, `UCGABAR` = cluster barrier,",
+              "`LDGMC` = `multimem.ld_reduce` (NVLS), `STG.128.STRONG.SYS` on a multicast address = `multimem.st`,",
+              "`LDG/STG.STRONG.SYS` = acquire/release flag traffic over NVLink peer memory, `MEMBAR.ALL.SYS` =",
+              "`fence.acq_rel.sys`, `PREEXIT` / `ACQBULK` = `griddepcontrol.launch_dependents` / `.wait`.  No `HMMA`",
+              "(legacy `mma.sync`) appears in any kernel."]
     (ROOT / "profiles" / "sass_index.md").write_text("\n".join(index) + "\n")
     print("\n".join(index))
     return 0

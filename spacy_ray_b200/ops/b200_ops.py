@@ -92,9 +92,12 @@ class B200Ops(TorchOps):
         # consumer of the bucket (ShardedSyncProxy.step) joins the stream.
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
         self._pdl_side = os.environ.get("SRB_PDL_SIDE", "0") == "1"
+        # LayerNorm fused into the forward GEMM's epilogue (EPI_MAXOUT3_LN): correct and tested, but measured
+        # at parity with GEMM + LayerNorm kernel (41.8 vs 41.4 us per layer, profiles/r2_fused_ln.md): off
+        self.fused_ln = os.environ.get("SRB_FUSED_LN", "0") == "1"
         self._side: Optional[torch.cuda.Stream] = None
         self._side_pending = False
-        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._ws: Dict[tuple, Any] = {}
         self._arc_cap: Dict[tuple, int] = {}
         self.max_rows_hint = 0               # engine.Trainer: largest row count any captured step will use
         # C2: consumer-side gates.  ``FusedSymmComm`` installs itself here; kernels that read
@@ -236,11 +239,26 @@ class B200Ops(TorchOps):
                               b_col_off=(0, w_in, 2 * w_in))
             else:
                 shifts = {}
-            self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=fwd_bn, M=Tp, N=nO * nP, K=w_in,
-                         bias=b.reshape(-1), which=which, gate=self._gate(W, b, G, beta), **shifts)
-            Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop, seed,
-                                                       self.seed_dev)
-            self.launches += 1
+            if (self.fused_ln and G is not None and fwd_bn == 192 and nO <= 512 and self.gemm_cluster == 3
+                    and (not residual or w_in == nO)):
+                # ONE kernel for the whole layer: the LayerNorm statistics of a row cross the N tiles as
+                # two numbers per tile, the activations stay in the epilogue's registers (gemm_launch.h)
+                stats, cnt = self._ln_scratch(Tp, (nO * nP) // 192)
+                Y = H
+                xhat = torch.empty((Tp, nO), dtype=torch.bfloat16, device=X.device)
+                rstd = torch.empty((Tp,), dtype=torch.float32, device=X.device)
+                sh = shifts or dict(a_row_shift=(0,), a_col_off=(0,), b_row_off=(0,), b_col_off=(0,))
+                self.k.tc_gemm_maxout_ln(X, W2, Y, which, xhat, rstd, b.reshape(-1), G, beta, X if residual else None,
+                                         m1, stats, cnt, Tp, nO * nP, w_in, list(sh["a_row_shift"]),
+                                         list(sh["a_col_off"]), list(sh["b_row_off"]), list(sh["b_col_off"]), drop,
+                                         seed, self.seed_dev, None, self.gemm_cluster, self._gate(W, b, G, beta))
+                self.launches += 1
+            else:
+                self.tc_gemm(X, W2, H, mode=MODE_KK, epi=EPI_MAXOUT3, block_n=fwd_bn, M=Tp, N=nO * nP, K=w_in,
+                             bias=b.reshape(-1), which=which, gate=self._gate(W, b, G, beta), **shifts)
+                Y, _w, xhat, rstd = self.k.maxout_ln_fwd(H, None, G, beta, X if residual else None, m1, nO, 1, drop,
+                                                           seed, self.seed_dev)
+                self.launches += 1
         else:
             self._gate_now(W, b, G, beta)
             Xw = self.k.seq2col(X) if window else X
@@ -545,6 +563,26 @@ class B200Ops(TorchOps):
             rec.update({"feats": feats, "which": which, "hid": hid, "d_scores": d_scores, "n_steps": S_cap,
                         "nA": system.n_actions})
         return rec
+
+    def _ln_scratch(self, rows: int, n_tiles: int):
+        """Scratch of the fused LayerNorm epilogue (csrc/gemm_launch.h): the tagged per-row partial sums
+        (fp32, zeroed once) and the kernel-maintained [launch tag, finished CTAs, time-out flag] words.
+        Persistent and sized once like ``_workspace`` (``max_rows_hint``)."""
+        need = (rows + 255) // 256 * 256
+        key = ("ln_scratch", n_tiles)
+        cur = self._ws.get(key)
+        if cur is None or cur[2] < need:
+            rows_pad = (max(rows, int(self.max_rows_hint)) + 255) // 256 * 256
+            stats = torch.zeros((rows_pad * n_tiles * 4,), dtype=torch.float32, device=self.device)
+            seq = torch.tensor([1, 0, 0], dtype=torch.int32, device=self.device)
+            cur = self._ws[key] = (stats, seq, rows_pad)
+        return cur[0], cur[1]
+
+    def check_fused_ln(self) -> None:
+        """Raise if a fused-LayerNorm epilogue ever timed out waiting for another tile's statistics."""
+        for key, cur in self._ws.items():
+            if key[0] == "ln_scratch" and int(cur[1][2].item()) != 0:
+                raise RuntimeError("fused LayerNorm epilogue: a wait on the row statistics timed out")
 
     def _workspace(self, name: str, rows: int, cols: int) -> torch.Tensor:
         """Persistent zero-initialised fp32 scratch, (>= rows, cols): allocated once (at the largest row

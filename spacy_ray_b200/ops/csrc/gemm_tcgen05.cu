@@ -60,6 +60,155 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- EPI_MAXOUT3_LN, second phase (see gemm_launch.h and the epilogue below) ------------------
+// What an epilogue thread carries from the first phase of a tile: its 32 maxout outputs of one row
+// (bf16 pairs), their argmax pieces (2 bits each) and where the tile sits.
+struct LnTile {
+  uint32_t hp[16];
+  uint32_t wb[2];
+  int m0, ntile;
+};
+
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// What the second phase needs from memory, requested in one go (ONE L2 round trip per tile).  Nothing is
+// consumed here: the raw 16-byte entries stay in registers until ln_finish.
+struct LnLoads {
+  float mk;
+  uint4 xr[4];
+  float4 st[4];                 // the row's first four tile entries (rows with more tiles: the rest is read late)
+};
+
+__device__ __forceinline__ float4 ld_shared_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void ln_prefetch(const GemmParams& p, const LnTile& t, LnLoads& ld, int M, int n_tiles, int q,
+                                            int half, int lane) {
+  const LnArgs& L = p.ln;
+  const int row = t.m0 + q * 32 + lane;
+  if (row >= M) return;
+  const int unit0 = (t.ntile * BLOCK_N + half * (BLOCK_N / 2)) / 3;
+  ld.mk = L.mask[row];
+  if (L.xres) {
+    const uint4* xp = (const uint4*)(L.xres + (size_t)row * L.ld_res + unit0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ld.xr[g] = xp[g];
+  }
+  const float4* sp = L.stats + (size_t)row * n_tiles;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n_tiles) ld.st[j] = ld_cg_f4(sp + j);
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void ln_finish(const GemmParams& p, const LnTile& t, const LnLoads& ld, const float* bias_s,
+                                          int M, int n_tiles, int q, int half, int lane, uint32_t tag) {
+  constexpr int HN = BLOCK_N / 2;
+  const LnArgs& L = p.ln;
+  const int nO = p.N / 3;
+  const int unit0 = (t.ntile * BLOCK_N + half * HN) / 3;          // my 32 units of the row
+  const int row = t.m0 + q * 32 + lane;
+  if (row >= M) return;                                            // nobody waits for rows past the end
+  __nv_bfloat16* out = (__nv_bfloat16*)p.out;
+  const size_t yo = (size_t)row * p.ldo + unit0;
+  const size_t ro = (size_t)row * nO + unit0;                      // xhat / which / dropout index: dense (rows, nO)
+  const float mk = ld.mk;
+  const uint4* xr = ld.xr;
+  const float4* sp = L.stats + (size_t)row * n_tiles;
+  float t1 = 0.f, t2 = 0.f;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < n_tiles) { ok = ok && (__float_as_uint(ld.st[j].z) == tag); t1 += ld.st[j].x; t2 += ld.st[j].y; }
+  for (int j = 4; j < n_tiles; ++j) {
+    const float4 e = ld_cg_f4(sp + j);
+    ok = ok && (__float_as_uint(e.z) == tag);
+    t1 += e.x; t2 += e.y;
+  }
+  if (!ok) {                                                       // rare: some tile of the row was not published yet
+    const uint64_t t0 = globaltimer_ns();
+    while (true) {
+      ok = true;
+      t1 = 0.f; t2 = 0.f;
+      for (int j = 0; j < n_tiles; ++j) {
+        const float4 e = ld_cg_f4(sp + j);
+        ok = ok && (__float_as_uint(e.z) == tag);
+        t1 += e.x; t2 += e.y;
+      }
+      if (ok) break;
+      if (globaltimer_ns() - t0 > 2000000000ull) { atomicExch(L.seq + 2, 1u); break; }
+      __nanosleep(64);
+    }
+  }
+  if (mk == 0.0f) {                                                // pad row: zeros (the next window GEMM relies on them)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { *(uint4*)(out + yo + g * 8) = z; *(uint4*)(L.xhat + ro + g * 8) = z; }
+    *(uint4*)(p.which + ro) = z; *(uint4*)(p.which + ro + 16) = z;
+    if (t.ntile == 0 && half == 0) L.rstd[row] = 0.f;
+    return;
+  }
+  const float inv_n = 1.f / (float)nO;
+  const float mu = t1 * inv_n;
+  const float rstd = rsqrtf(fmaxf(t2 * inv_n - mu * mu, 0.f) + 1e-8f);
+  uint64_t seed = L.seed;
+  if (L.seed_dev) seed += (uint64_t)*L.seed_dev;
+  const float inv_keep = L.drop_p > 0.f ? 1.0f / (1.0f - L.drop_p) : 1.0f;
+  const uint32_t thr = dropout_thr(L.drop_p);
+  const float* g4 = bias_s + p.N + unit0;                          // LayerNorm gain / shift of my units (smem, fp32)
+  const float* b4 = g4 + nO;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float keep[8];
+    if (L.drop_p > 0.f) dropout_scale8(seed, ro + g * 8, thr, inv_keep, keep);
+    const float4 ga = ld_shared_f4(g4 + 8 * g), gb = ld_shared_f4(g4 + 8 * g + 4);
+    const float4 ba = ld_shared_f4(b4 + 8 * g), bb = ld_shared_f4(b4 + 8 * g + 4);
+    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    const uint32_t xw[4] = {xr[g].x, xr[g].y, xr[g].z, xr[g].w};
+    float yv[8], xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * 8 + i;
+      const uint32_t pr = t.hp[j >> 1];
+      const float hf = __uint_as_float((j & 1) ? (pr & 0xFFFF0000u) : (pr << 16));
+      const float xh = (hf - mu) * rstd;
+      float nv = fmaf(xh, gg[i], bv[i]);
+      if (L.drop_p > 0.f) nv *= keep[i];
+      if (L.xres) nv += __uint_as_float((i & 1) ? (xw[i >> 1] & 0xFFFF0000u) : (xw[i >> 1] << 16));
+      yv[i] = nv; xv[i] = xh;
+    }
+    *(uint4*)(out + yo + g * 8) = make_uint4(pack_bf16x2(yv[0], yv[1]), pack_bf16x2(yv[2], yv[3]),
+                                             pack_bf16x2(yv[4], yv[5]), pack_bf16x2(yv[6], yv[7]));
+    *(uint4*)(L.xhat + ro + g * 8) = make_uint4(pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
+                                                pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
+  }
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t f = t.wb[cc] >> (8 * k);                      // four 2-bit fields -> four bytes
+      w4[k] = (f & 3u) | ((f & 12u) << 6) | ((f & 48u) << 12) | ((f & 192u) << 18);
+    }
+    *(uint4*)(p.which + ro + cc * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+  if (t.ntile == 0 && half == 0) L.rstd[row] = rstd;
+}
+
 // CL = CTAs per cluster (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically
 // adjacent M tiles of the SAME N tile / K range in lockstep and share the B (weight) operand:
 // each CTA TMA-loads half of the B tile and multicasts it into both CTAs' shared memory, so B
@@ -131,10 +280,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // still be reading are written.
   pdl_wait();
   const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
+  const uint32_t ln_tag = EPI == EPI_MAXOUT3_LN ? *(volatile const uint32_t*)p.ln.seq : 0u;
   // gated launch: peers' generic-proxy stores (the freshly published bucket) -> my TMA loads
   if (p.gate.flags != nullptr && warp == 0) fence_proxy_async_global();
-  if (p.bias && warp >= 2) {                                 // bias -> smem (fp32) once per CTA, epilogue warps only
-    for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
+  if ((p.bias || EPI == EPI_MAXOUT3_LN) && warp >= 2) {      // bias (and LayerNorm gain / shift) -> smem (fp32) once per CTA
+    if (p.bias)
+      for (int i = threadIdx.x - 64; i < p.N; i += kNumThreads - 64) bias_s[i] = bf2f(p.bias[i]);
+    if (EPI == EPI_MAXOUT3_LN) {
+      const int nO = p.N / 3;
+      for (int i = threadIdx.x - 64; i < nO; i += kNumThreads - 64) {
+        bias_s[p.N + i] = bf2f(p.ln.G[i]);
+        bias_s[p.N + nO + i] = bf2f(p.ln.beta[i]);
+      }
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kNumThreads - 64) : "memory");
   }
 
@@ -335,6 +493,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;             // which half of the tile's columns
     constexpr int HN = BLOCK_N / 2;
     int it = 0;
+    LnTile ln_prev;                                  // EPI_MAXOUT3_LN: the tile whose second phase is still due
+    LnLoads ln_ld;
+    bool ln_have = false;
     for (int w = first_item; w < total_items; w += item_stride) {
       const int tile = w / splits;
       const int mg = tile / n_tiles;
@@ -409,6 +570,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             *(uint4*)(p.which + uo) = *(const uint4*)wh;
           }
         }
+      } else if (EPI == EPI_MAXOUT3_LN) {
+        // ---- maxout + LayerNorm + dropout + residual + mask, the row never leaves the SM (gemm_launch.h) ----
+        // Software-pipelined by one tile: phase A of tile i (accumulator -> maxout -> partial sums published)
+        // runs BEFORE phase B of tile i-1 (wait for the other tiles' sums, normalise, store), so the other
+        // clusters have a whole tile time to publish and the wait is normally already satisfied.
+        static_assert(EPI != EPI_MAXOUT3_LN || HN == 96, "fused LayerNorm epilogue: 192-column tiles (64 units)");
+        LnTile cur;
+        cur.m0 = m0; cur.ntile = tile % n_tiles;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          float v[48];
+          tmem_ld_x16_nowait(t_base + cc * 48, v);
+          tmem_ld_x16_nowait(t_base + cc * 48 + 16, v + 16);
+          tmem_ld_x16_nowait(t_base + cc * 48 + 32, v + 32);
+          tmem_ld_wait_regs<48>(v);
+          cur.wb[cc] = 0u;
+          if (p.bias) {                                           // 48 consecutive bias values, 16-byte smem loads
+            const float4* b4 = (const float4*)(bias_s + n0 + cc * 48);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+              const float4 bq = b4[k];
+              v[4 * k] += bq.x; v[4 * k + 1] += bq.y; v[4 * k + 2] += bq.z; v[4 * k + 3] += bq.w;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float a = v[3 * u], b = v[3 * u + 1], d = v[3 * u + 2];
+            float best = a; uint32_t bi = 0;
+            if (b > best) { best = b; bi = 1; }
+            if (d > best) { best = d; bi = 2; }
+            // round to bf16 first: the statistics are those of the values the two-kernel path stores
+            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(f2bf(best));
+            const float hf = __uint_as_float(hb << 16);
+            s1 += hf; s2 += hf * hf;
+            if (u & 1) cur.hp[cc * 8 + u / 2] |= hb << 16; else cur.hp[cc * 8 + u / 2] = hb;
+            cur.wb[cc] |= bi << (2 * u);
+          }
+        }
+        // the accumulator stage is free again: the MMAs of the tile after next may start
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && cta_rank != 0) mbar_arrive_cluster(map_to_cta(tmem_empty + acc, 0));
+          else mbar_arrive(tmem_empty + acc);
+        }
+        // the two column halves of a row are in different warps of this CTA: add them up through shared
+        // memory (double-buffered by tile parity), then ONE 16-byte store per row carrying this launch's tag
+        {
+          float2* xch = (float2*)(bias_s + p.N + 2 * (p.N / 3)) + (it & 1) * BM;
+          if (half == 1) xch[q * 32 + lane] = make_float2(s1, s2);
+          asm volatile("bar.sync 2, %0;" ::"n"(kNumThreads - 64) : "memory");
+          if (half == 0) {
+            const float2 o = xch[q * 32 + lane];
+            const int srow = m0 + q * 32 + lane;                  // stats has m_groups * CL * 128 rows: always in range
+            __stcg(p.ln.stats + (size_t)srow * n_tiles + cur.ntile,
+                   make_float4(s1 + o.x, s2 + o.y, __uint_as_float(ln_tag), 0.f));
+          }
+        }
+        if (ln_have) {
+          // (issuing these loads before this tile's accumulator read-out was measured slower: the other
+          // clusters have not published yet at that point and the slow re-read path is taken)
+          ln_prefetch<BLOCK_N>(p, ln_prev, ln_ld, M, n_tiles, q, half, lane);
+          ln_finish<BLOCK_N>(p, ln_prev, ln_ld, bias_s, M, n_tiles, q, half, lane, ln_tag);
+        }
+        ln_prev = cur; ln_have = true;
+        ++it;
+        continue;                                                 // tmem_empty was already signalled above
       } else {  // EPI_ATOMIC_F32: split-K partial sums reduced into the gradient buffer
         float* out = (float*)p.out;
 #pragma unroll 1
@@ -433,10 +662,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       ++it;
     }
+    if (EPI == EPI_MAXOUT3_LN && ln_have) {
+      ln_prefetch<BLOCK_N>(p, ln_prev, ln_ld, M, n_tiles, q, half, lane);
+      ln_finish<BLOCK_N>(p, ln_prev, ln_ld, bias_s, M, n_tiles, q, half, lane, ln_tag);
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while a peer may still write to it
   if (warp == 1) { if (PAIR) tmem_dealloc_pair<C::kTmemCols>(tmem_base); else tmem_dealloc<C::kTmemCols>(tmem_base); }
+  if (EPI == EPI_MAXOUT3_LN && threadIdx.x == 0) {
+    // every CTA read the tag before it got here: the last one to finish arms the next launch
+    __threadfence();
+    if (atomicAdd(p.ln.seq + 1, 1u) == gridDim.x - 1u) {
+      p.ln.seq[1] = 0u;
+      p.ln.seq[0] = ln_tag + 1u == 0u ? 1u : ln_tag + 1u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -507,7 +748,7 @@ int gemm_block_k() { return BK; }
 
 bool gemm_supports_cluster(int block_n, int mode, int epi) {
   if (mode == MODE_KK && (epi == EPI_STORE) && (block_n == 256 || block_n == 192 || block_n == 128)) return true;
-  if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
+  if (mode == MODE_KK && (epi == EPI_MAXOUT3 || epi == EPI_MAXOUT3_LN) && block_n == 192) return true;
   if (mode == MODE_MNMN && epi == EPI_ATOMIC_F32 && (block_n == 256 || block_n == 128)) return true;
   if (mode == MODE_KMN && epi == EPI_STORE && (block_n == 256 || block_n == 128)) return true;
   return false;
@@ -515,6 +756,7 @@ bool gemm_supports_cluster(int block_n, int mode, int epi) {
 
 bool gemm_supports_halo(int block_n, int mode, int epi, int cluster) {
   if (cluster != 1 && cluster != 3) return false;
+  if (mode == MODE_KK && epi == EPI_MAXOUT3_LN && block_n == 192) return cluster == 3;
   if (mode == MODE_KK && epi == EPI_MAXOUT3 && block_n == 192) return true;
   if (mode == MODE_KMN && epi == EPI_STORE && (block_n == 256 || block_n == 128)) return true;
   return false;
@@ -522,6 +764,11 @@ bool gemm_supports_halo(int block_n, int mode, int epi, int cluster) {
 
 cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int block_n, int mode, int epi,
                         int cluster, int num_sms, cudaStream_t s) {
+  if (epi == EPI_MAXOUT3_LN) {       // compiled for the pair-MMA cluster only (b200_ops falls back otherwise)
+    if (block_n != 192 || mode != MODE_KK || cluster != 3) return cudaErrorInvalidValue;
+    if (p.halo) return launch_one<192, MODE_KK, EPI_MAXOUT3_LN, 2, true, true>(a, b, p, num_sms, s);
+    return launch_one<192, MODE_KK, EPI_MAXOUT3_LN, 2, true, false>(a, b, p, num_sms, s);
+  }
   if (p.halo) {
 #define SRB_HALO(BN, MD, EP)                                                                       \
   if (block_n == BN && mode == MD && epi == EP) {                                                  \

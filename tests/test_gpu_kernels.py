@@ -245,6 +245,43 @@ def test_maxout_block_fwd_bwd(ref, use_tc, window, residual, w):
     _close(dbeta, dbetar, 5e-2, 0.05 * math.sqrt(T), "dbeta")
 
 
+@pytest.mark.parametrize("w,window,rows", [(256, 1, 25683), (256, 0, 3000), (128, 1, 20000), (512, 1, 9000), (64, 1, 700)])
+def test_fused_layernorm_epilogue_matches_the_two_kernel_path(w, window, rows):
+    """EPI_MAXOUT3_LN (LayerNorm statistics exchanged between the N tiles of a row, activations kept in
+    the epilogue's registers) against GEMM+maxout followed by the LayerNorm kernel: same winners, same
+    dropout mask, outputs within one bf16 ulp of rounding; run twice (the counters re-arm themselves)."""
+    from spacy_ray_b200.ops.b200_ops import B200Ops
+
+    fused, plain = B200Ops("cuda:0"), B200Ops("cuda:0")
+    fused.fused_ln, plain.fused_ln = True, False
+    assert fused.gemm_cluster == 3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mask = (torch.rand(rows, 1, device="cuda", generator=g) > 0.05).float()
+    nI = w if window else 2 * w
+    X = (torch.randn(rows, nI, device="cuda", generator=g) * mask).bfloat16()
+    W = (torch.randn(w, 3, nI * (3 if window else 1), device="cuda", generator=g) * 0.05).bfloat16()
+    b = (torch.randn(w, 3, device="cuda", generator=g) * 0.1).bfloat16()
+    G = (torch.rand(w, device="cuda", generator=g) + 0.5).bfloat16()
+    beta = (torch.randn(w, device="cuda", generator=g) * 0.1).bfloat16()
+    for rep in range(2):
+        kw = dict(window=window, residual=bool(window), dropout=0.1, is_train=True, seed=5 + rep)
+        Yf, cf = fused.maxout_block(X, W, b, G, beta, mask, **kw)
+        Yp, cp = plain.maxout_block(X, W, b, G, beta, mask, **kw)
+        torch.cuda.synchronize()
+        fused.check_fused_ln()
+        assert fused.launches == rep + 1 and plain.launches == 2 * (rep + 1), "one kernel per layer on the fused path"
+        live = mask[:, 0] != 0            # pad rows: the fused epilogue writes 0, the plain GEMM epilogue the (unused) winner
+        assert torch.equal(cf["which"][live], cp["which"][live]), "different maxout winners"
+        assert int(cf["which"][~live].sum().item()) == 0
+        _close(cf["rstd"], cp["rstd"], 1e-4, 1e-6, "rstd")
+        _close(cf["xhat"], cp["xhat"], 1e-2, 1e-3, "xhat")
+        _close(Yf, Yp, 1e-2, 2e-2, "Y")
+        assert float((Yf.float() * (1 - mask)).abs().sum()) == 0.0
+        assert float(cf["xhat"].float()[mask[:, 0] == 0].abs().sum()) == 0.0
+    scratch = [v for k, v in fused._ws.items() if k[0] == "ln_scratch"]
+    assert scratch and all(v[1].tolist() == [3, 0, 0] for v in scratch), "launch tag / CTA counter not maintained"
+
+
 def test_softmax_xent(ops, ref):
     torch.manual_seed(6)
     X = torch.randn(500, 64, device="cuda").bfloat16()

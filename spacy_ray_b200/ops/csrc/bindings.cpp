@@ -177,6 +177,31 @@ std::vector<Tensor> softmax_xent(const Tensor& logits, const Tensor& labels) {
   return {d, guesses, loss};
 }
 
+// A record arena: one allocation carved into typed views, initialised by ONE kernel of ours
+// (zero part first, then the "-1" part) instead of one library fill per tensor.
+struct Arena {
+  std::vector<int64_t> off, bytes;
+  int64_t zero_bytes = 0, total = 0;
+  bool in_ones = false;
+  static int64_t up16(int64_t n) { return (n + 15) / 16 * 16; }
+  int add(int64_t nbytes, bool ones = false) {
+    TORCH_CHECK(ones || !in_ones, "Arena: zero-initialised parts first");
+    if (ones && !in_ones) { in_ones = true; zero_bytes = total; }
+    off.push_back(total); bytes.push_back(nbytes);
+    total += up16(nbytes);
+    return (int)off.size() - 1;
+  }
+  Tensor buf;
+  void alloc(const at::TensorOptions& o, cudaStream_t s) {
+    if (!in_ones) zero_bytes = total;
+    buf = at::empty({total}, o.dtype(at::kByte));
+    if (total) srb::launch_arena_init(buf.data_ptr(), (size_t)zero_bytes / 4, (size_t)(total - zero_bytes) / 4, s);
+  }
+  Tensor view(int i, at::ScalarType dt, at::IntArrayRef shape) const {
+    return buf.narrow(0, off[i], bytes[i]).view(dt).view(shape);
+  }
+};
+
 // Tagger head in one kernel.  Returns {d (Tp, ldd) bf16 with ldd = 128-multiple and zeros past nC, guesses, loss};
 // an empty list when the shape is outside the kernel's range (caller falls back to GEMM + softmax_xent).
 std::vector<Tensor> linear_softmax_xent(const Tensor& X, const Tensor& W, const Tensor& b, const Tensor& labels) {
@@ -186,9 +211,12 @@ std::vector<Tensor> linear_softmax_xent(const Tensor& X, const Tensor& W, const 
   c10::cuda::CUDAGuard guard(X.device());
   const int Tp = (int)X.size(0), w = (int)X.size(1), nC = (int)W.size(0);
   const int64_t ldd = ((nC + 7) / 8 * 8 + 127) / 128 * 128;
-  Tensor d = at::zeros({Tp, ldd}, X.options());
+  Arena ar;
+  const int i_d = ar.add((int64_t)Tp * ldd * 2), i_loss = ar.add(4);
+  ar.alloc(X.options(), cur_stream());
+  Tensor d = ar.view(i_d, at::kBFloat16, {Tp, ldd});
   Tensor guesses = at::empty({Tp}, X.options().dtype(at::kLong));
-  Tensor loss = at::zeros({}, X.options().dtype(at::kFloat));
+  Tensor loss = ar.view(i_loss, at::kFloat, {});
   const bool ok = srb::try_launch_linear_softmax_xent(X.data_ptr(), W.data_ptr(), b.data_ptr(), labels.data_ptr<int64_t>(),
                                                       d.data_ptr(), guesses.data_ptr<int64_t>(), loss.data_ptr<float>(),
                                                       Tp, w, nC, (int)ldd, cur_stream());
@@ -229,11 +257,15 @@ std::vector<Tensor> biluo_steps(const Tensor& Yf, const Tensor& pad, const Tenso
   const int64_t T = n_tokens;
   Tensor feats = at::empty({train ? T : 0, 3}, o.dtype(at::kInt));
   Tensor which = at::empty({train ? T : 0, nO}, o.dtype(at::kByte));
-  Tensor hid = at::zeros({train ? T : 0, nO}, o);            // rows past the real token count stay zero
   const int64_t ldd = (nA_pad + 127) / 128 * 128;             // GEMM-friendly pitch (dWu / d_hid run on tcgen05)
-  Tensor d_scores = at::zeros({train ? T : 0, ldd}, o);      // (fixed-capacity batches under CUDA graphs)
+  const int64_t Tr = train ? T : 0;
+  Arena ar;                                                   // rows past the real token count stay zero
+  const int i_hid = ar.add(Tr * nO * 2), i_ds = ar.add(Tr * ldd * 2), i_loss = ar.add(4);
+  ar.alloc(o, cur_stream());                                  // (fixed-capacity batches under CUDA graphs)
+  Tensor hid = ar.view(i_hid, at::kBFloat16, {Tr, nO});
+  Tensor d_scores = ar.view(i_ds, at::kBFloat16, {Tr, ldd});
   Tensor actions = at::empty({T}, o.dtype(at::kInt));
-  Tensor loss = at::zeros({}, o.dtype(at::kFloat));
+  Tensor loss = ar.view(i_loss, at::kFloat, {});
   srb::BiluoArgs a{};
   a.Yf = Yf.data_ptr(); a.pad = pad.data_ptr(); a.b = b.data_ptr(); a.Wu = Wu.data_ptr(); a.bu = bu.data_ptr();
   a.doc_starts = doc_starts.data_ptr<int32_t>(); a.doc_lens = doc_lens.data_ptr<int32_t>();
@@ -261,16 +293,21 @@ std::vector<Tensor> arc_eager_steps(const Tensor& Yf, const Tensor& pad, const T
   auto o = Yf.options();
   const int64_t S = train ? n_steps_cap : 0;
   // record slots past a doc's last step stay inert: zero gradient, piece 0, "missing" features
-  Tensor feats = at::full({S, 8}, -1, o.dtype(at::kInt));
-  Tensor which = at::zeros({S, nO}, o.dtype(at::kByte));
-  Tensor hid = at::zeros({S, nO}, o);
   const int64_t ldd = (nA_pad + 127) / 128 * 128;
-  Tensor d_scores = at::zeros({S, ldd}, o);
-  Tensor history = at::full({n_steps_cap}, -1, o.dtype(at::kInt));
+  const int64_t Bn = doc_lens.numel();
+  Arena ar;
+  const int i_which = ar.add(S * nO), i_hid = ar.add(S * nO * 2), i_ds = ar.add(S * ldd * 2), i_ns = ar.add(Bn * 4),
+            i_loss = ar.add(4), i_feats = ar.add(S * 8 * 4, true), i_hist = ar.add(n_steps_cap * 4, true);
+  ar.alloc(o, cur_stream());
+  Tensor feats = ar.view(i_feats, at::kInt, {S, 8});
+  Tensor which = ar.view(i_which, at::kByte, {S, nO});
+  Tensor hid = ar.view(i_hid, at::kBFloat16, {S, nO});
+  Tensor d_scores = ar.view(i_ds, at::kBFloat16, {S, ldd});
+  Tensor history = ar.view(i_hist, at::kInt, {n_steps_cap});
   Tensor heads = at::empty({n_tokens}, o.dtype(at::kInt));
   Tensor labels = at::empty({n_tokens}, o.dtype(at::kInt));
-  Tensor n_steps = at::zeros({doc_lens.numel()}, o.dtype(at::kInt));
-  Tensor loss = at::zeros({}, o.dtype(at::kFloat));
+  Tensor n_steps = ar.view(i_ns, at::kInt, {Bn});
+  Tensor loss = ar.view(i_loss, at::kFloat, {});
   srb::ArcArgs a{};
   a.Yf = Yf.data_ptr(); a.pad = pad.data_ptr(); a.b = b.data_ptr(); a.Wu = Wu.data_ptr(); a.bu = bu.data_ptr();
   a.doc_starts = doc_starts.data_ptr<int32_t>(); a.doc_lens = doc_lens.data_ptr<int32_t>();

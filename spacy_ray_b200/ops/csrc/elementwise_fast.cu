@@ -15,41 +15,60 @@ namespace srb {
 // ------------------------------------------------------------------------------------------
 // forward: Z (Tp, nO*NP) [+bias] -> maxout -> LN -> dropout -> (+X) -> mask
 //
-// One warp per row, a lane owns UPL contiguous units.  A row is only 16-48 B per lane, so a
-// warp walks R rows per iteration and issues every load of all R rows before the first use:
-// that is what keeps enough bytes in flight per SM to cover HBM latency (the one-row version
-// sat at ~35% of copy bandwidth with 24 resident warps x 1 KB).
+// A lane owns UPL contiguous units of a row (16-byte vectors everywhere); a row takes nO / UPL
+// lanes of a SEG-lane segment (SEG = 32: one row per warp; SEG = 16: two rows per warp, for widths
+// up to 128 - round 1 had fast kernels for nO = 32 * UPL only, so width 96 - BASELINE config 1's
+// model - ran the scalar kernels: 62 us per backward call, half of that step).  Lanes past the row
+// idle and contribute zeros to the segment reductions.  A row is only 16-48 B per lane, so a warp
+// walks R row groups per iteration and issues every load of all of them before the first use:
+// that is what keeps enough bytes in flight per SM to cover HBM latency (the one-row version sat
+// at ~35% of copy bandwidth with 24 resident warps x 1 KB).
 // ------------------------------------------------------------------------------------------
-template <int NP, int UPL, int R>
-__global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
+template <int SEG>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// FULL: the row fills its segment exactly (nO == SEG * UPL: 256, 512, 128) - nO is a compile-time
+// constant and no lane idles.  With one row per warp (SEG == 32) pad rows and rows past the end are
+// warp-uniform and leave early; with two rows per warp they are handled after the reductions.
+template <int NP, int UPL, int R, int SEG, bool FULL>
+__global__ void __launch_bounds__(256, 2) maxout_ln_fwd_vec_kernel(
     const __nv_bfloat16* __restrict__ Z, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ G,
     const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ Xres, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ Y, uint8_t* __restrict__ which, __nv_bfloat16* __restrict__ xhat_out,
-    float* __restrict__ rstd_out, int Tp, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
+    float* __restrict__ rstd_out, int Tp, int nO_rt, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev) {
   pdl_prologue();
-  constexpr int nO = 32 * UPL;
   constexpr int ZPL = UPL * NP;                 // Z elements per lane (multiple of 8)
+  constexpr int RPW = 32 / SEG;                 // rows per warp and r
+  constexpr bool UNIFORM = SEG == 32;
+  const int nO = FULL ? SEG * UPL : nO_rt;
   if (seed_dev) seed += (uint64_t)*seed_dev;
   const int lane = threadIdx.x & 31;
+  const int seg = lane / SEG, sl = lane % SEG;
+  const bool active = FULL ? true : (sl * UPL < nO);
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const float inv_n = 1.f / (float)nO;
   const uint32_t thr = dropout_thr(drop_p);
   const bool has_ln = G != nullptr;
-  const int u0 = lane * UPL;
+  const int u0 = active ? sl * UPL : 0;
   float gk[UPL], bk[UPL];
 #pragma unroll
   for (int j = 0; j < UPL; ++j) { gk[j] = has_ln ? bf2f(G[u0 + j]) : 1.f; bk[j] = has_ln ? bf2f(beta[u0 + j]) : 0.f; }
-  const int ngroups = (Tp + R - 1) / R;
+  const int ngroups = (Tp + R * RPW - 1) / (R * RPW);
   for (int grp = gwarp; grp < ngroups; grp += nwarps) {
-    const int row0 = grp * R;
+    const int row0 = grp * R * RPW + seg;
     // ---- phase 1: every load of the R rows (pad rows are valid memory, loaded unconditionally)
     bf16x8 zraw[R][ZPL / 8];
     bf16x8 xraw[R][UPL / 8];
     float mk[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int row = min(row0 + r, Tp - 1);
+      const int row = min(row0 + r * RPW, Tp - 1);
       mk[r] = mask[row];
       const bf16x8* zp = (const bf16x8*)(Z + (size_t)row * nO * NP + u0 * NP);
 #pragma unroll
@@ -63,10 +82,12 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
     // ---- phase 2: one row at a time out of registers
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int row = row0 + r;
-      if (row >= Tp) break;
-      const size_t ro = (size_t)row * nO + u0;
-      if (mk[r] == 0.0f) {
+      const int row = row0 + r * RPW;
+      const bool row_ok = row < Tp;
+      if (UNIFORM && !row_ok) break;
+      const size_t ro = (size_t)(UNIFORM ? row : min(row, Tp - 1)) * nO + u0;
+      const bool pad = mk[r] == 0.0f;
+      auto store_zeros = [&]() {
         bf16x8 zero;
 #pragma unroll
         for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
@@ -76,7 +97,10 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
           if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = zero;
           if (which) *(uint2*)(which + ro + v * 8) = make_uint2(0u, 0u);
         }
-        if (lane == 0 && rstd_out) rstd_out[row] = 0.f;
+        if (sl == 0 && rstd_out) rstd_out[row] = 0.f;
+      };
+      if (UNIFORM && pad) {
+        if (active) store_zeros();
         continue;
       }
       float h[UPL];
@@ -93,15 +117,22 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
           if (bias) zv += bf2f(bias[u0 * NP + e]);
           if (p == 0 || zv > best) { best = zv; bi = p; }
         }
+        if (!FULL && !active) best = 0.f;
         h[j] = best; wh[j] = (uint8_t)bi; sum += best;
       }
       float mu = 0.f, rstd = 1.f;
       if (has_ln) {
-        mu = warp_sum(sum) * (1.f / nO);
+        mu = seg_sum<SEG>(sum) * inv_n;
         float sq = 0.f;
 #pragma unroll
         for (int j = 0; j < UPL; ++j) { const float d = h[j] - mu; sq += d * d; }
-        rstd = rsqrtf(warp_sum(sq) * (1.f / nO) + 1e-8f);
+        if (!FULL && !active) sq = 0.f;
+        rstd = rsqrtf(seg_sum<SEG>(sq) * inv_n + 1e-8f);
+      }
+      if (!active) continue;
+      if (!UNIFORM) {                            // two rows per warp: only now may the halves diverge
+        if (!row_ok) continue;
+        if (pad) { store_zeros(); continue; }
       }
 #pragma unroll
       for (int v = 0; v < UPL / 8; ++v) {
@@ -124,7 +155,7 @@ __global__ void __launch_bounds__(256) maxout_ln_fwd_vec_kernel(
         if (xhat_out) *(bf16x8*)(xhat_out + ro + v * 8) = xo;
         if (which) *(uint2*)(which + ro + v * 8) = *(const uint2*)w8;
       }
-      if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+      if (sl == 0 && rstd_out) rstd_out[row] = rstd;
     }
   }
 }
@@ -134,53 +165,74 @@ constexpr int rows_per_iter(int bytes_per_lane_row) {
   return bytes_per_lane_row <= 32 ? 4 : (bytes_per_lane_row <= 64 ? 2 : 1);
 }
 
-template <int NP, int UPL>
+template <int NP, int UPL, int SEG, bool FULL>
 static void launch_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
-                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, float drop_p,
-                           uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
+                           const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
+                           float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
   constexpr int R = rows_per_iter((UPL * NP + UPL) * 2);
-  int blocks = (Tp + 8 * R - 1) / (8 * R);
+  constexpr int RPB = 8 * R * (32 / SEG);             // rows per block and iteration
+  int blocks = (Tp + RPB - 1) / RPB;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  launch_k(maxout_ln_fwd_vec_kernel<NP, UPL, R>, blocks, 256, 0, s, 
+  launch_k(maxout_ln_fwd_vec_kernel<NP, UPL, R, SEG, FULL>, blocks, 256, 0, s,
       (const __nv_bfloat16*)Z, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)G, (const __nv_bfloat16*)beta,
-      (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, drop_p, seed,
+      (const __nv_bfloat16*)X_res, mask, (__nv_bfloat16*)Y, which, (__nv_bfloat16*)xhat, rstd, Tp, nO, drop_p, seed,
       seed_dev);
+}
+
+// lane layout for a width: 8 units per lane up to 256 units (16-lane segments up to 128), 16 per lane up to 512
+static bool vec_layout(int nO, int* upl, int* seg) {
+  if (nO <= 0 || nO % 8) return false;
+  if (nO <= 256) { *upl = 8; *seg = nO <= 128 ? 16 : 32; return true; }
+  if (nO <= 512 && nO % 16 == 0) { *upl = 16; *seg = 32; return true; }
+  return false;
 }
 
 bool try_launch_maxout_ln_fwd_vec(const void* Z, const void* bias, const void* G, const void* beta, const void* X_res,
                                   const float* mask, void* Y, uint8_t* which, void* xhat, float* rstd, int Tp, int nO,
                                   int nP, float drop_p, uint64_t seed, const int64_t* seed_dev, cudaStream_t s) {
-#define SRB_TRY(NP_, UPL_)                                                                                       \
-  if (nP == NP_ && nO == 32 * UPL_) {                                                                            \
-    launch_fwd_vec<NP_, UPL_>(Z, bias, G, beta, X_res, mask, Y, which, xhat, rstd, Tp, drop_p, seed, seed_dev, s); \
-    return true;                                                                                                 \
+  int upl, seg;
+  if (!vec_layout(nO, &upl, &seg)) return false;
+#define SRB_TRY(NP_, UPL_, SEG_)                                                                                   \
+  if (nP == NP_ && upl == UPL_ && seg == SEG_) {                                                                   \
+    if (nO == UPL_ * SEG_)                                                                                         \
+      launch_fwd_vec<NP_, UPL_, SEG_, true>(Z, bias, G, beta, X_res, mask, Y, which, xhat, rstd, Tp, nO, drop_p, seed, seed_dev, s); \
+    else                                                                                                           \
+      launch_fwd_vec<NP_, UPL_, SEG_, false>(Z, bias, G, beta, X_res, mask, Y, which, xhat, rstd, Tp, nO, drop_p, seed, seed_dev, s); \
+    return true;                                                                                                   \
   }
-  SRB_TRY(1, 8) SRB_TRY(1, 16) SRB_TRY(3, 8) SRB_TRY(3, 16) SRB_TRY(2, 8) SRB_TRY(2, 16)
+  SRB_TRY(1, 8, 32) SRB_TRY(1, 8, 16) SRB_TRY(1, 16, 32)
+  SRB_TRY(3, 8, 32) SRB_TRY(3, 8, 16) SRB_TRY(3, 16, 32)
+  SRB_TRY(2, 8, 32) SRB_TRY(2, 8, 16) SRB_TRY(2, 16, 32)
 #undef SRB_TRY
   return false;
 }
 
 // ------------------------------------------------------------------------------------------
 // backward: dY -> dropout -> LN backward -> routed dZ; accumulates dG, dbeta, db
-// (same R-rows-per-iteration load batching as the forward kernel)
+// (same lane layout and R-rows-per-iteration load batching as the forward kernel)
 // ------------------------------------------------------------------------------------------
-template <int NP, int UPL, int R>
-__global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
+template <int NP, int UPL, int R, int SEG, bool FULL>
+__global__ void __launch_bounds__(256, (UPL > 8 ? 1 : 2)) maxout_ln_bwd_vec_kernel(
     const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ xhat, const float* __restrict__ rstd_in,
     const __nv_bfloat16* __restrict__ G, const uint8_t* __restrict__ which, const float* __restrict__ mask,
     __nv_bfloat16* __restrict__ dZ, float* __restrict__ db, float* __restrict__ dG, float* __restrict__ dbeta, int Tp,
-    float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
+    int nO_rt, float drop_p, uint64_t seed, const int64_t* __restrict__ seed_dev, int has_ln) {
   pdl_prologue();
-  constexpr int nO = 32 * UPL;
   constexpr int ZPL = UPL * NP;
+  constexpr int RPW = 32 / SEG;
+  constexpr bool UNIFORM = SEG == 32;
+  const int nO = FULL ? SEG * UPL : nO_rt;
   if (seed_dev) seed += (uint64_t)*seed_dev;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane / SEG, sl = lane % SEG;
+  const bool active = FULL ? true : (sl * UPL < nO);
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const float inv_n = 1.f / (float)nO;
   const uint32_t thr = dropout_thr(drop_p);
-  const int u0 = lane * UPL;
+  const int u0 = active ? sl * UPL : 0;
   float gk[UPL];
 #pragma unroll
   for (int j = 0; j < UPL; ++j) gk[j] = has_ln ? bf2f(G[u0 + j]) : 1.f;
@@ -189,15 +241,15 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
   for (int j = 0; j < UPL; ++j) { accG[j] = 0.f; accB[j] = 0.f; }
 #pragma unroll
   for (int j = 0; j < ZPL; ++j) accb[j] = 0.f;
-  const int ngroups = (Tp + R - 1) / R;
+  const int ngroups = (Tp + R * RPW - 1) / (R * RPW);
   for (int grp = gwarp; grp < ngroups; grp += nwarps) {
-    const int row0 = grp * R;
+    const int row0 = grp * R * RPW + seg;
     bf16x8 draw[R][UPL / 8], xraw[R][UPL / 8];
     uint2 wraw[R][UPL / 8];
     float mk[R], rs[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int row = min(row0 + r, Tp - 1);
+      const int row = min(row0 + r * RPW, Tp - 1);
       const size_t ro = (size_t)row * nO + u0;
       mk[r] = mask[row];
       rs[r] = has_ln ? rstd_in[row] : 1.f;
@@ -210,18 +262,25 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int row = row0 + r;
-      if (row >= Tp) break;
-      const size_t ro = (size_t)row * nO + u0;
-      bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
-      if (mk[r] == 0.0f) {
-        bf16x8 zero;
+      const int row = row0 + r * RPW;
+      const bool row_ok = row < Tp;
+      if (UNIFORM && !row_ok) break;
+      if (UNIFORM && mk[r] == 0.0f) {           // pad row (warp-uniform): zeros
+        if (active) {
+          bf16x8 zero;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+          for (int i = 0; i < 8; ++i) zero.v[i] = f2bf(0.f);
+          bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
 #pragma unroll
-        for (int v = 0; v < ZPL / 8; ++v) zout[v] = zero;
+          for (int v = 0; v < ZPL / 8; ++v) zout[v] = zero;
+        }
         continue;
       }
+      // two rows per warp / idle lanes: a dead lane's d is forced to 0, which makes every one of its
+      // accumulator contributions and its whole dZ slice exactly zero
+      constexpr bool ALL_LIVE = UNIFORM && FULL;
+      const bool live = UNIFORM ? active : (row_ok && active && mk[r] != 0.0f);
+      const size_t ro = (size_t)(UNIFORM ? row : min(row, Tp - 1)) * nO + u0;
       float dn[UPL], xh[UPL];
       uint8_t wh[UPL];
       float s1 = 0.f, s2 = 0.f;
@@ -233,11 +292,11 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int j = v * 8 + i;
-          float d = bf2f(draw[r][v].v[i]);
+          float d = (ALL_LIVE || live) ? bf2f(draw[r][v].v[i]) : 0.f;
           if (drop_p > 0.f) d *= keep[i];
           wh[j] = wb[i];
           if (has_ln) {
-            xh[j] = bf2f(xraw[r][v].v[i]);
+            xh[j] = (ALL_LIVE || live) ? bf2f(xraw[r][v].v[i]) : 0.f;
             accG[j] += d * xh[j];
             accB[j] += d;
             d *= gk[j];
@@ -250,10 +309,11 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
       }
       float rstd = 1.f;
       if (has_ln) {
-        rstd = rs[r];
-        s1 = warp_sum(s1) * (1.f / nO);
-        s2 = warp_sum(s2) * (1.f / nO);
+        rstd = (ALL_LIVE || live) ? rs[r] : 0.f;
+        s1 = seg_sum<SEG>(s1) * inv_n;
+        s2 = seg_sum<SEG>(s2) * inv_n;
       }
+      if (!active || !row_ok) continue;
       __align__(16) __nv_bfloat16 zo[ZPL];
 #pragma unroll
       for (int j = 0; j < UPL; ++j) {
@@ -265,19 +325,32 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
           accb[j * NP + q] += val;
         }
       }
+      bf16x8* zout = (bf16x8*)(dZ + (size_t)row * nO * NP + u0 * NP);
 #pragma unroll
       for (int v = 0; v < ZPL / 8; ++v) zout[v] = *(const bf16x8*)(zo + v * 8);
     }
   }
+  // two rows per warp: fold the upper segment's accumulators into the lower one first
+  if (SEG == 16) {
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+      accG[j] += __shfl_down_sync(0xffffffffu, accG[j], 16);
+      accB[j] += __shfl_down_sync(0xffffffffu, accB[j], 16);
+    }
+#pragma unroll
+    for (int j = 0; j < ZPL; ++j) accb[j] += __shfl_down_sync(0xffffffffu, accb[j], 16);
+  }
   // combine the 8 warps of the block through shared memory, then one atomic per element
   extern __shared__ float sred[];                  // [8][nO*(NP+2)]
-  float* mine = sred + (size_t)warp * nO * (NP + 2);
-#pragma unroll
-  for (int j = 0; j < UPL; ++j) { mine[u0 + j] = accG[j]; mine[nO + u0 + j] = accB[j]; }
-#pragma unroll
-  for (int j = 0; j < ZPL; ++j) mine[2 * nO + u0 * NP + j] = accb[j];
-  __syncthreads();
   const int per = nO * (NP + 2);
+  float* mine = sred + (size_t)warp * per;
+  if (active && seg == 0) {
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) { mine[u0 + j] = accG[j]; mine[nO + u0 + j] = accB[j]; }
+#pragma unroll
+    for (int j = 0; j < ZPL; ++j) mine[2 * nO + u0 * NP + j] = accb[j];
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < per; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll
@@ -289,35 +362,43 @@ __global__ void __launch_bounds__(256) maxout_ln_bwd_vec_kernel(
   }
 }
 
-template <int NP, int UPL>
+template <int NP, int UPL, int SEG, bool FULL>
 static void launch_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G, const uint8_t* which,
-                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, float drop_p,
+                           const float* mask, void* dZ, float* db, float* dG, float* dbeta, int Tp, int nO, float drop_p,
                            uint64_t seed, const int64_t* seed_dev, int has_ln, cudaStream_t s) {
   constexpr int R = rows_per_iter(UPL * 5);          // dY + xhat (2 B each) + which (1 B) per unit
   int blocks = (Tp + 31) / 32;                       // >= 4 rows per warp so the flush is amortised
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  const size_t smem = sizeof(float) * 8 * 32 * UPL * (NP + 2);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+  const size_t smem = sizeof(float) * 8 * (size_t)nO * (NP + 2);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(maxout_ln_bwd_vec_kernel<NP, UPL, R, SEG, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
   }
-  launch_k(maxout_ln_bwd_vec_kernel<NP, UPL, R>, blocks, 256, smem, s, 
+  launch_k(maxout_ln_bwd_vec_kernel<NP, UPL, R, SEG, FULL>, blocks, 256, smem, s,
       (const __nv_bfloat16*)dY, (const __nv_bfloat16*)xhat, rstd, (const __nv_bfloat16*)G, which, mask,
-      (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln);
+      (__nv_bfloat16*)dZ, db, dG, dbeta, Tp, nO, drop_p, seed, seed_dev, has_ln);
 }
 
 bool try_launch_maxout_ln_bwd_vec(const void* dY, const void* xhat, const float* rstd, const void* G,
                                   const uint8_t* which, const float* mask, void* dZ, float* db, float* dG,
                                   float* dbeta, int Tp, int nO, int nP, float drop_p, uint64_t seed,
                                   const int64_t* seed_dev, int has_ln, cudaStream_t s) {
-#define SRB_TRY(NP_, UPL_)                                                                                          \
-  if (nP == NP_ && nO == 32 * UPL_) {                                                                               \
-    launch_bwd_vec<NP_, UPL_>(dY, xhat, rstd, G, which, mask, dZ, db, dG, dbeta, Tp, drop_p, seed, seed_dev, has_ln, s); \
-    return true;                                                                                                    \
+  int upl, seg;
+  if (!vec_layout(nO, &upl, &seg)) return false;
+#define SRB_TRY(NP_, UPL_, SEG_)                                                                                      \
+  if (nP == NP_ && upl == UPL_ && seg == SEG_) {                                                                      \
+    if (nO == UPL_ * SEG_)                                                                                            \
+      launch_bwd_vec<NP_, UPL_, SEG_, true>(dY, xhat, rstd, G, which, mask, dZ, db, dG, dbeta, Tp, nO, drop_p, seed,  \
+                                            seed_dev, has_ln, s);                                                     \
+    else                                                                                                              \
+      launch_bwd_vec<NP_, UPL_, SEG_, false>(dY, xhat, rstd, G, which, mask, dZ, db, dG, dbeta, Tp, nO, drop_p, seed, \
+                                             seed_dev, has_ln, s);                                                    \
+    return true;                                                                                                      \
   }
-  SRB_TRY(3, 8) SRB_TRY(3, 16) SRB_TRY(2, 8) SRB_TRY(2, 16)
+  SRB_TRY(3, 8, 32) SRB_TRY(3, 8, 16) SRB_TRY(3, 16, 32)
+  SRB_TRY(2, 8, 32) SRB_TRY(2, 8, 16) SRB_TRY(2, 16, 32)
 #undef SRB_TRY
   return false;
 }
@@ -529,6 +610,30 @@ void launch_f32_to_bf16_zero(float* src, void* dst, size_t n, cudaStream_t s) {
   size_t blocks = (n8 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   launch_k(f32_to_bf16_zero_kernel, (unsigned)blocks, 256, 0, s, src, (__nv_bfloat16*)dst, n8);
+}
+
+// ------------------------------------------------------------------------------------------
+// One launch initialises a whole record arena: the first n_zero 32-bit words to 0, the next n_ones
+// words to 0xFFFFFFFF (int32 -1: "missing feature" / "no action").  Replaces the 3-7 library fill
+// kernels per transition head and step (hid, d_scores, which, loss, feats, history, n_steps).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) arena_init_kernel(uint32_t* __restrict__ p, size_t n_zero, size_t n_ones) {
+  pdl_prologue();
+  const size_t n = n_zero + n_ones;
+  const size_t n4 = n / 4;                                   // the arena is 16-byte aligned and padded
+  const size_t z4 = n_zero / 4;                              // n_zero is a multiple of 4 words
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t v = i < z4 ? 0u : 0xFFFFFFFFu;
+    ((uint4*)p)[i] = make_uint4(v, v, v, v);
+  }
+}
+
+void launch_arena_init(void* p, size_t n_zero_words, size_t n_ones_words, cudaStream_t s) {
+  const size_t n4 = (n_zero_words + n_ones_words) / 4;
+  if (n4 == 0) return;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(arena_init_kernel, (unsigned)blocks, 256, 0, s, (uint32_t*)p, n_zero_words, n_ones_words);
 }
 
 }  // namespace srb

@@ -2,7 +2,7 @@
 # round 2, call Q (1 GPU): LayerNorm vec kernels for every width that is a multiple of 8: numerics + benches
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -q -x 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -x 2>&1 | tail -12
 run() { name=$1; shift
   timeout 300 python bench.py "$@" --steps 100 --warmup 10 --no-own-baseline > gpurun_out/r2q_$name.json 2> gpurun_out/r2q_$name.err
   python - "$name" <<'PY'

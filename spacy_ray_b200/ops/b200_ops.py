@@ -92,6 +92,7 @@ class B200Ops(TorchOps):
         # consumer of the bucket (ShardedSyncProxy.step) joins the stream.
         self.side_dw = os.environ.get("SRB_SIDE_DW", "1") != "0" and self.device.type == "cuda"
         self._pdl_side = os.environ.get("SRB_PDL_SIDE", "0") == "1"
+        self.tag_head_tc = os.environ.get("SRB_TAG_HEAD_TC", "1") != "0"
         # LayerNorm fused into the forward GEMM's epilogue (EPI_MAXOUT3_LN): correct and tested, but measured
         # at parity with GEMM + LayerNorm kernel (41.8 vs 41.4 us per layer, profiles/r2_fused_ln.md): off
         self.fused_ln = os.environ.get("SRB_FUSED_LN", "0") == "1"
@@ -451,8 +452,22 @@ class B200Ops(TorchOps):
         X = X.contiguous()
         nC = W.shape[0]
         if X.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and X.shape[1] % 16 == 0 and nC <= 128:
-            # K6 in one kernel: logits GEMM + softmax + CE gradient + loss + argmax
-            out = self.k.linear_softmax_xent(X, W.contiguous(), b.to(torch.bfloat16).contiguous(), labels.contiguous())
+            out = None
+            if self.use_tc and self.tag_head_tc:
+                # K6 on the tensor cores: logits = X W^T accumulated into a persistent zeroed fp32 scratch by the
+                # tcgen05 GEMM (rows of W past nC are zero-filled by the TMA), then ONE kernel for bias + softmax +
+                # CE gradient + loss + argmax, which also leaves the scratch zeroed for the next step
+                T, w = X.shape
+                n16 = (nC + 15) // 16 * 16
+                bn = 64 if n16 <= 64 else 128
+                logits = self._workspace("tag_logits", T, bn)
+                self.tc_gemm(X, W.contiguous(), logits, mode=MODE_KK, epi=EPI_ATOMIC_F32, block_n=bn, M=T, N=n16, K=w,
+                             splits=1, cluster=1)
+                out = self.k.softmax_xent_bias(logits, b.to(torch.bfloat16).contiguous(), labels.contiguous(), nC)
+            else:
+                # K6 in one CUDA-core kernel (W in shared memory): fine for narrow models only
+                out = self.k.linear_softmax_xent(X, W.contiguous(), b.to(torch.bfloat16).contiguous(),
+                                                 labels.contiguous())
             if out:
                 dp, guesses, loss = out                        # dp: (T, 128k) bf16, zero past nC
                 self.launches += 1

@@ -224,6 +224,29 @@ std::vector<Tensor> linear_softmax_xent(const Tensor& X, const Tensor& W, const 
   return {d, guesses, loss};
 }
 
+// Second half of the tensor-core tagger head: logits (Tp, ldl) fp32 without bias -> {d (Tp, ldd) bf16, zeros past
+// nC, guesses, loss}; `logits` is zeroed again on the way (persistent scratch of the caller).
+std::vector<Tensor> softmax_xent_bias(Tensor logits, const Tensor& b, const Tensor& labels, int64_t nC) {
+  SRB_CHECK_CUDA(logits); SRB_CHECK_CUDA(b); SRB_CHECK_BF16(b); SRB_CHECK_CUDA(labels);
+  TORCH_CHECK(logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.stride(1) == 1 &&
+              labels.scalar_type() == at::kLong && b.numel() >= nC && nC <= 128);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int Tp = (int)logits.size(0);
+  const int64_t ldd = ((nC + 7) / 8 * 8 + 127) / 128 * 128;
+  auto o = logits.options();
+  Arena ar;
+  const int i_d = ar.add((int64_t)Tp * ldd * 2), i_loss = ar.add(4);
+  ar.alloc(o, cur_stream());
+  Tensor d = ar.view(i_d, at::kBFloat16, {Tp, ldd});
+  Tensor guesses = at::empty({Tp}, o.dtype(at::kLong));
+  Tensor loss = ar.view(i_loss, at::kFloat, {});
+  TORCH_CHECK(srb::launch_softmax_xent_bias(logits.data_ptr<float>(), b.data_ptr(), labels.data_ptr<int64_t>(),
+                                            d.data_ptr(), guesses.data_ptr<int64_t>(), loss.data_ptr<float>(), Tp,
+                                            (int)nC, (int)logits.stride(0), (int)ldd, cur_stream()),
+              "softmax_xent_bias: unsupported class count");
+  return {d, guesses, loss};
+}
+
 void adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, c10::optional<Tensor> w_out, const Tensor& blk_key,
                 const Tensor& blk_off, const Tensor& key_off, const Tensor& key_len, Tensor norms, const Tensor& hyper,
                 const Tensor& step) {
@@ -351,6 +374,7 @@ TORCH_LIBRARY(srb, m) {
   m.def("col2seq_residual(Tensor dXw, Tensor? dY, Tensor mask) -> Tensor");
   m.def("softmax_xent(Tensor logits, Tensor labels) -> Tensor[]");
   m.def("linear_softmax_xent(Tensor X, Tensor W, Tensor b, Tensor labels) -> Tensor[]");
+  m.def("softmax_xent_bias(Tensor(a!) logits, Tensor b, Tensor labels, int nC) -> Tensor[]");
   m.def("adam_shard(Tensor g, Tensor w, Tensor m1, Tensor m2, Tensor? w_out, Tensor blk_key, Tensor blk_off, Tensor key_off, Tensor key_len, Tensor norms, Tensor hyper, Tensor step) -> ()");
   m.def("biluo_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor? gold, Tensor inv_active, int n_tokens, int nO, int nP, int n_labels, bool train, bool teacher) -> Tensor[]");
   m.def("arc_eager_steps(Tensor Yf, Tensor pad, Tensor b, Tensor Wu, Tensor bu, Tensor doc_starts, Tensor doc_lens, Tensor tok_off, Tensor step_off, Tensor? gold_heads, Tensor? gold_labels, int n_tokens, int n_steps_cap, int nO, int nP, float scale, bool train, bool teacher, int max_len) -> Tensor[]");
@@ -380,6 +404,7 @@ TORCH_LIBRARY_IMPL(srb, CUDA, m) {
   m.impl("col2seq_residual", col2seq_residual);
   m.impl("softmax_xent", softmax_xent);
   m.impl("linear_softmax_xent", linear_softmax_xent);
+  m.impl("softmax_xent_bias", softmax_xent_bias);
   m.impl("adam_shard", adam_shard);
   m.impl("biluo_steps", biluo_steps);
   m.impl("arc_eager_steps", arc_eager_steps);

@@ -801,6 +801,7 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
   SRB_CASE1(64, MODE_MNMN, EPI_ATOMIC_F32)
   SRB_CASE1(256, MODE_KK, EPI_ATOMIC_F32)
   SRB_CASE1(128, MODE_KK, EPI_ATOMIC_F32)
+  SRB_CASE1(64, MODE_KK, EPI_ATOMIC_F32)
   SRB_CASE(256, MODE_KMN, EPI_STORE)
   SRB_CASE1(192, MODE_KMN, EPI_STORE)
   SRB_CASE(128, MODE_KMN, EPI_STORE)

@@ -68,6 +68,9 @@ void launch_col2seq_residual(const void* dXw, const void* dY, const float* mask,
                              int add_residual, cudaStream_t s);
 
 // K6: row softmax + cross-entropy gradient + loss + argmax, logits fp32 or bf16 (Tp, nC).
+// logits: fp32 (Tp, ldl) WITHOUT bias (tcgen05 GEMM output); read, then left zeroed
+bool launch_softmax_xent_bias(float* logits, const void* b, const int64_t* labels, void* d_out, int64_t* guesses,
+                              float* loss, int Tp, int nC, int ldl, int ldd, cudaStream_t s);
 void launch_softmax_xent(const float* logits, const int64_t* labels, void* d_out /*bf16*/, int64_t* guesses,
                          float* loss, int Tp, int nC, cudaStream_t s);
 

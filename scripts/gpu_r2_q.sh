@@ -2,7 +2,7 @@
 # round 2, call Q (1 GPU): LayerNorm vec kernels for every width that is a multiple of 8: numerics + benches
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -q -x 2>&1 | tail -12
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -12
 run() { name=$1; shift
   timeout 300 python bench.py "$@" --steps 100 --warmup 10 --no-own-baseline > gpurun_out/r2q_$name.json 2> gpurun_out/r2q_$name.err
   python - "$name" <<'PY'
@@ -19,5 +19,5 @@ run flagship
 run tagger_w96 --config configs/tagger_w96.cfg
 run parser_w256 --config configs/parser_w256.cfg
 run multitask_w512 --config configs/multitask_w512.cfg
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --log-file gpurun_out/r2q_launches_tagger.csv python bench.py --config configs/tagger_w96.cfg --steps 3 --warmup 3 --no-e2e --no-own-baseline > gpurun_out/r2q_ncu_tagger.log 2>&1
-python scripts/launch_summary.py gpurun_out/r2q_launches_tagger.csv | head -24
+
+

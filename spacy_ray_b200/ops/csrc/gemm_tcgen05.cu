@@ -16,6 +16,7 @@
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_id % 4, column half = (warp_id - 2) / 4).
+#include <cstdlib>
 #include "common.cuh"
 #include "gate.cuh"
 #include "gemm_launch.h"
@@ -41,19 +42,30 @@ constexpr int kMaxBiasN = 4096;           // bias staged in smem as fp32 (16 KB)
 // correction (measured: base_offset must stay 0; setting it to the row phase gives wrong data).  That removes two
 // of the three A loads of these L2->SM-bound kernels; a stage then carries the B tiles of all
 // three shifts.
-template <int BLOCK_N, bool PAIR = false, bool HALO = false>
+// BRES (window forward, pair MMA, K <= 256): the B operand - the weights - stays RESIDENT in shared
+// memory for the whole kernel.  With a grid of clusters that is a multiple of the number of N tiles,
+// the persistent schedule (item = cluster + i * clusters, tile = m_group * n_tiles + n_tile) gives
+// every cluster ONE fixed N tile, i.e. one 192-row slice of W: 4 k-blocks x 3 shifts x 12 KB = 144 KB
+// per CTA, loaded once.  The ring then carries only the 17 KB activation tiles.  Before, every tile
+// re-fetched its 144 KB of weights from L2 (119 MB per layer against 53 MB of activations) and the
+// kernel sat at the L2 -> SM cap with the tensor pipe 68 % busy.
+template <int BLOCK_N, bool PAIR = false, bool HALO = false, bool BRES = false>
 struct Cfg {
   static constexpr int kTileB = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BK * 2;
   static constexpr int kBoxA = (HALO ? kHaloRows : BM) * BK * 2;             // bytes the A load delivers
   static constexpr int kStageA = HALO ? 17 * 1024 : BM * BK * 2;             // 1024-aligned
-  static constexpr int kStageB = (HALO ? 3 : 1) * kTileB;
+  static constexpr int kStageB = BRES ? 0 : (HALO ? 3 : 1) * kTileB;
+  static constexpr int kResKb = 4;                                           // k-blocks of 64 held resident (K <= 256)
+  static constexpr int kResB = BRES ? kResKb * 3 * kTileB : 0;
   static constexpr int kTxBytes = kBoxA + kStageB;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStagesRaw = kSmemBudget / kStage;
+  static constexpr int kBiasBytes = BRES ? 8192 : kMaxBiasN * 4;             // bias (+ LayerNorm gain/shift) as fp32
+  static constexpr int kStagesRaw = BRES ? 4 : kSmemBudget / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/ + kMaxBiasN * 4;
+  static constexpr int kSmemBytes = kStages * kStage + kResB + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -221,22 +233,25 @@ __device__ __forceinline__ void ln_finish(const GemmParams& p, const LnTile& t, 
 // stored AND fetched, which is what the L2 -> smem-bound single-CTA kernels were missing.  Both
 // CTAs run a TMA producer (completion bytes are signalled on the leader's barriers), only the
 // leader (cluster rank 0) runs the MMA issuer, both run their own epilogue.
-template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR, bool HALO = false>
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR, bool HALO = false, bool BRES = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   static_assert(!PAIR || CL == 2, "the pair MMA needs a 2-CTA cluster");
   static_assert(!HALO || (MODE != MODE_MNMN && (PAIR || CL == 1)), "halo: K-major A, single CTA or pair MMA");
-  using C = Cfg<BLOCK_N, PAIR, HALO>;
+  static_assert(!BRES || (HALO && PAIR && MODE == MODE_KK), "resident B: window forward with the pair MMA");
+  using C = Cfg<BLOCK_N, PAIR, HALO, BRES>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::kStages * C::kStageA;
-  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStage);
+  unsigned char* sBres = smem + C::kStages * C::kStage;       // BRES: the cluster's slice of the weights, all k-blocks
+  uint64_t* full_bar = (uint64_t*)(smem + C::kStages * C::kStage + C::kResB);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
-  float* bias_s = (float*)(smem + C::kStages * C::kStage + 256);
+  uint64_t* bres_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr = (uint32_t*)(bres_bar + 1);
+  float* bias_s = (float*)(smem + C::kStages * C::kStage + C::kResB + 256);
 
   pdl_trigger();          // the next kernel of the stream may be scheduled behind this one's CTAs (launch.h)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -267,6 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // collects the epilogue warps of BOTH CTAs
     for (int i = 0; i < C::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, PAIR ? 1 : CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, PAIR ? 16 : 8); }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_ptr); else tmem_alloc<C::kTmemCols>(tmem_ptr); }
@@ -300,6 +316,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================================ TMA producer =====================================
     if (elect_one()) {
       int stage = 0, phase = 0;
+      if (BRES && first_item < total_items) {
+        // my N tile never changes (grid of clusters = multiple of n_tiles): fetch its weights ONCE
+        const int n0r = (first_item % n_tiles) * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+        const uint32_t rb = map_to_cta(bres_bar, 0);
+        if (cta_rank == 0) mbar_arrive_expect_tx(bres_bar, 2 * total_kb * 3 * C::kTileB);
+        for (int kb = 0; kb < total_kb; ++kb)
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+            tma_load_2d_2sm(sBres + (kb * 3 + s) * C::kTileB, &tmB, rb, p.b_col_off[s] + kb * BK, n0r + p.b_row_off[s]);
+      }
       for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
         const int mg = tile / n_tiles;
@@ -317,6 +343,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (!PAIR || cta_rank == 0) mbar_arrive_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * C::kTxBytes);
             if (PAIR) tma_load_2d_2sm(a_dst, &tmA, fb, p.a_col_off[0] + kb * BK, m0 - 1);
             else tma_load_2d(a_dst, &tmA, full_bar + stage, p.a_col_off[0] + kb * BK, m0 - 1);
+            if (!BRES)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
               unsigned char* bs = b_dst + s * C::kTileB;
@@ -427,6 +454,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if ((!PAIR || cta_rank == 0) && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BLOCK_N, MODE == MODE_MNMN, MODE != MODE_KK);
       int stage = 0, phase = 0, it = 0;
+      if (BRES && first_item < total_items) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int w = first_item; w < total_items; w += item_stride) {
         const int tile = w / splits, split = w - tile * splits;
         const int mg = tile / n_tiles;
@@ -445,7 +473,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
               const uint32_t r = (uint32_t)(p.a_row_shift[s] + 1);           // 0, 1 or 2 rows into the halo tile
-              const uint32_t bs = b_addr + s * C::kTileB;
+              const uint32_t bs = BRES ? smem_u32(sBres) + ((kb - kb0) * 3 + s) * C::kTileB : b_addr + s * C::kTileB;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 const uint64_t adesc = make_smem_desc(a_addr + r * 128 + k * 32, 0, 1024);
@@ -523,9 +551,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float* vv = v + hh * 16;
               const int cc = c + hh * 16;
               if (n0 + cc >= p.N) break;                 // partial last N tile (N % 16 == 0): nothing to store
-              if (p.bias) {
+              if (p.bias) {                               // explicit ld.shared (the pointer is generic to the compiler)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) vv[i] += bias_s[n0 + cc + i];
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 bq = ld_shared_f4(bias_s + n0 + cc + i);
+                  vv[i] += bq.x; vv[i + 1] += bq.y; vv[i + 2] += bq.z; vv[i + 3] += bq.w;
+                }
               }
               if (p.add_src) {
                 const bf16x8* src = (const bf16x8*)(p.add_src + (size_t)row * p.ld_add + n0 + cc);
@@ -553,11 +584,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (row_ok) {
             bf16x8 h0, h1;
             __align__(16) uint8_t wh[16];
+            if (p.bias) {
+              // 48 consecutive bias values as 12 x ld.shared.v4 (the compiler only sees a generic pointer here:
+              // the scalar form compiled to 48 generic LD.E per chunk)
+#pragma unroll
+              for (int k = 0; k < 12; ++k) {
+                const float4 bq = ld_shared_f4(bias_s + n0 + c + 4 * k);
+                v[4 * k] += bq.x; v[4 * k + 1] += bq.y; v[4 * k + 2] += bq.z; v[4 * k + 3] += bq.w;
+              }
+            }
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              const int n = n0 + c + 3 * u;
-              float a = v[3 * u], b = v[3 * u + 1], d = v[3 * u + 2];
-              if (p.bias) { a += bias_s[n]; b += bias_s[n + 1]; d += bias_s[n + 2]; }
+              const float a = v[3 * u], b = v[3 * u + 1], d = v[3 * u + 2];
               float best = a; int bi = 0;
               if (b > best) { best = b; bi = 1; }
               if (d > best) { best = d; bi = 2; }
@@ -588,10 +626,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_wait_regs<48>(v);
           cur.wb[cc] = 0u;
           if (p.bias) {                                           // 48 consecutive bias values, 16-byte smem loads
-            const float4* b4 = (const float4*)(bias_s + n0 + cc * 48);
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
-              const float4 bq = b4[k];
+              const float4 bq = ld_shared_f4(bias_s + n0 + cc * 48 + 4 * k);
               v[4 * k] += bq.x; v[4 * k + 1] += bq.y; v[4 * k + 2] += bq.z; v[4 * k + 3] += bq.w;
             }
           }
@@ -713,12 +750,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR = false, bool HALO = false>
+template <int BLOCK_N, int MODE, int EPI, int CL, bool PAIR = false, bool HALO = false, bool BRES = false>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int num_sms, cudaStream_t s) {
-  using C = Cfg<BLOCK_N, PAIR, HALO>;
+  using C = Cfg<BLOCK_N, PAIR, HALO, BRES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO, BRES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -728,6 +765,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   const int items = m_groups * n_tiles * (p.splits > 0 ? p.splits : 1);
   int clusters = num_sms / CL;
   if (items < clusters) clusters = items;
+  if (BRES) clusters = clusters / n_tiles * n_tiles;      // every cluster keeps ONE N tile (see Cfg)
   if (clusters <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
@@ -741,7 +779,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO>, a, b, p);
+  return cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, EPI, CL, PAIR, HALO, BRES>, a, b, p);
 }
 
 int gemm_block_k() { return BK; }
@@ -768,6 +806,16 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const GemmPa
     if (block_n != 192 || mode != MODE_KK || cluster != 3) return cudaErrorInvalidValue;
     if (p.halo) return launch_one<192, MODE_KK, EPI_MAXOUT3_LN, 2, true, true>(a, b, p, num_sms, s);
     return launch_one<192, MODE_KK, EPI_MAXOUT3_LN, 2, true, false>(a, b, p, num_sms, s);
+  }
+  // window forward with the weights resident in shared memory (Cfg): K <= 256, bias (+ LayerNorm vectors) in 8 KB.
+  // Measured at parity / 0.3 % slower than re-fetching B per tile (1.3172 vs 1.3132 ms per flagship step,
+  // 72 instead of 74 clusters): the weight traffic is NOT what holds the tensor pipe at 68 % - the 4-k-block
+  // mainloop (2.5 us) is as short as the epilogue of the previous tile.  Off unless SRB_GEMM_BRES=1.
+  static const bool bres_on = std::getenv("SRB_GEMM_BRES") && std::getenv("SRB_GEMM_BRES")[0] == '1';
+  if (p.halo && bres_on && cluster == 3 && block_n == 192 && mode == MODE_KK && p.K <= 256 && p.N >= 192 &&
+      (num_sms / 2) >= p.N / 192) {
+    if (epi == EPI_MAXOUT3 && p.N <= 2048)
+      return launch_one<192, MODE_KK, EPI_MAXOUT3, 2, true, true, true>(a, b, p, num_sms, s);
   }
   if (p.halo) {
 #define SRB_HALO(BN, MD, EP)                                                                       \

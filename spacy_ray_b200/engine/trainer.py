@@ -380,7 +380,11 @@ class Trainer:
             stamp(0)                                        # trace: step start
         if self.exchange and hasattr(self.proxy, "begin_step"):
             self.proxy.begin_step(overlap=True)             # buckets are exchanged under the backward pass
-        self.ops.seed_dev.add_(7919)                        # fresh dropout masks on every replay
+        bump = getattr(getattr(self.ops, "k", None), "bump_i64", None)
+        if bump is not None and self.ops.seed_dev.is_cuda:
+            bump(self.ops.seed_dev, 7919)                   # fresh dropout masks on every replay (1-thread kernel)
+        else:
+            self.ops.seed_dev.add_(7919)
         shared = [c for _n, c, k in self.heads if k == "tok2vec"]
         n_heads = sum(1 for _n, _c, k in self.heads if k != "tok2vec")
         # heads that listen to ONE shared tok2vec are independent of each other: run each on its own

@@ -387,6 +387,11 @@ TORCH_LIBRARY(srb, m) {
     srb::g_pdl = on ? 1 : 0;
     return was;
   });
+  m.def("bump_i64(Tensor(a!) t, int by) -> ()", [](at::Tensor t, int64_t by) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kLong && t.numel() >= 1);
+    c10::cuda::CUDAGuard guard(t.device());
+    srb::launch_bump_i64(t.data_ptr<int64_t>(), by, at::cuda::getCurrentCUDAStream().stream());
+  });
   m.def("transition_scatter(Tensor d_hid, Tensor which, Tensor feats, Tensor dYf, Tensor dpad, Tensor db, int nF, int nP) -> ()");
   srb::register_gemm_ops(m);
   srb::register_comm_ops(m);

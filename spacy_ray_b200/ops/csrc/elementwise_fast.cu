@@ -636,4 +636,11 @@ void launch_arena_init(void* p, size_t n_zero_words, size_t n_ones_words, cudaSt
   launch_k(arena_init_kernel, (unsigned)blocks, 256, 0, s, (uint32_t*)p, n_zero_words, n_ones_words);
 }
 
+// the device-side dropout stream position: one thread of ours instead of a library elementwise kernel
+__global__ void bump_i64_kernel(int64_t* p, int64_t by) {
+  pdl_prologue();
+  *p += by;
+}
+void launch_bump_i64(int64_t* p, int64_t by, cudaStream_t s) { launch_k(bump_i64_kernel, 1, 1, 0, s, p, by); }
+
 }  // namespace srb

@@ -146,6 +146,7 @@ bool launch_arc_eager_steps(ArcArgs a, cudaStream_t s);
 int arc_eager_max_doc_len(int nO, int nP, int nA);
 extern int g_pdl;                                      // launch.h
 // words [0, n_zero) <- 0, [n_zero, n_zero + n_ones) <- 0xFFFFFFFF; both counts multiples of 4, p 16-byte aligned
+void launch_bump_i64(int64_t* p, int64_t by, cudaStream_t s);
 void launch_arena_init(void* p, size_t n_zero_words, size_t n_ones_words, cudaStream_t s);
 
 }  // namespace srb

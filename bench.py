@@ -309,8 +309,7 @@ def run_arm(args, impl: str, rank: int, world: int, local_rank: int):
     dev_inputs = []
     for ids in id_batches[:n_total]:
         trainer.prepare(ids)
-        stage, err = trainer._q_out.get()
-        assert err is None, err
+        stage = trainer._take()
         dev_inputs.append((stage["buf"].to(trainer.device), stage["rows"], stage["docs"], stage["words"]))
     torch.cuda.synchronize()
 
@@ -351,19 +350,30 @@ def run_arm(args, impl: str, rank: int, world: int, local_rank: int):
     # reads each loss one step late (it is logging data) so the device never waits for the host.
     e2e = None
     if args.e2e:
-        rest = id_batches[n_total: 2 * n_total + 1]
-        trainer.prepare(rest[0])
+        rest = id_batches[n_total: 2 * n_total + 2]
+        state = {"next": 0, "ahead": 0}
+
+        def top_up():
+            # the batch about to run + `trainer.prefetch_depth` more being collated behind it (the trainer
+            # raises the depth from 1 to its number of collate workers when the device waited for the host)
+            while state["ahead"] < trainer.prefetch_depth + 1 and state["next"] < len(rest):
+                trainer.prepare(rest[state["next"]])
+                state["next"] += 1
+                state["ahead"] += 1
+
         for i in range(warmup):
-            trainer.prepare(rest[i + 1])
+            top_up()
             trainer.train_step()
+            state["ahead"] -= 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         docs_local = 0
         with ClockSampler(local_rank) as clocks_e:
             barrier()
             e0.record()
             for i in range(warmup, n_total):
-                trainer.prepare(rest[i + 1])          # prefetch the NEXT batch while this one runs
+                top_up()                              # collate FUTURE batches while this one runs
                 loss_val = trainer.train_step()       # H2D + step + async D2H(loss); returns the previous step's
+                state["ahead"] -= 1
                 docs_local += trainer.last["docs"]
             loss_val = trainer.flush_loss()           # the last step's loss is read inside the timed region too
             e1.record()

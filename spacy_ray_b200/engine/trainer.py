@@ -26,8 +26,10 @@ their device kernels (``Trainer.unsupported_reason``).  Everything else uses the
 from __future__ import annotations
 
 import os
+import collections
 import queue
 import threading
+import time
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -245,7 +247,7 @@ class Trainer:
 
     def __init__(self, nlp, proxy, examples: Sequence[Any], *, docs_per_batch: int, dropout: float = 0.1,
                  component: Optional[str] = None, use_graphs: bool = True, bucket_rows: int = 256,
-                 prefetch: bool = True, n_stage: int = 3, exchange: bool = True):
+                 prefetch: bool = True, n_stage: int = 3, exchange: bool = True, prefetch_workers: int = 2):
         self.nlp, self.proxy = nlp, proxy
         # exchange=False: the captured step only ACCUMULATES gradients (accumulate_gradient > 1: the caller
         # runs proxy.step() once per full batch, after the last micro-batch)
@@ -281,6 +283,7 @@ class Trainer:
         self.use_graphs = use_graphs
         self.dev_buf = torch.zeros(self.lay.nbytes, dtype=torch.uint8, device=self.device)
         self.dv = _Views(self.lay, self.dev_buf)
+        n_stage = max(int(n_stage), (int(prefetch_workers) if prefetch else 1) + 2)
         self.stages = [make_stage(self.lay, self.store, pin=True) for _ in range(n_stage)]
         for stage in self.stages:
             # device landing buffer of this stage: the H2D copy runs on a side stream as soon as the
@@ -303,15 +306,33 @@ class Trainer:
         self._stage_i = 0
         self._prefetch = prefetch
         self._q_in: "queue.Queue" = queue.Queue()
-        self._q_out: "queue.Queue" = queue.Queue()
-        self._thread: Optional[threading.Thread] = None
+        # batches prepared but not yet consumed, in submission order (several collate workers may
+        # finish out of order; ``_take`` hands them out in the order ``prepare`` was called)
+        self._pending: "collections.deque" = collections.deque()
+        self._threads: List[threading.Thread] = []
+        # How many batches a caller should keep prepared ahead of the step it is about to run.  Starts at
+        # 1 (one collate in flight is enough when the device step is longer than a collate, and a second
+        # busy worker costs the launching thread ~2 % through the GIL / driver lock: flagship 99 % -> 97 %
+        # of device-timed); ``_take`` raises it to the number of workers when one collate costs more than
+        # half the period at which batches are consumed (tagger w96: 0.33 ms step, collate about as long:
+        # 82 % -> 96 % of device-timed).
+        self._workers = max(1, min(int(prefetch_workers), len(self.stages) - 2)) if prefetch else 1
+        self.prefetch_depth = 1
+        self._takes = 0
+        self._period = 0.0
+        self._cost = 0.0
+        self._last_take: Optional[float] = None
         self._side = torch.cuda.Stream(device=self.device)
         # the captured step runs at high stream priority: the backend's side-stream work (weight-
         # gradient GEMMs, default priority) then only takes SMs the dependent chain leaves idle
         self._hp = torch.cuda.Stream(device=self.device, priority=-1)
         if prefetch:
-            self._thread = threading.Thread(target=self._prefetch_loop, daemon=True)
-            self._thread.start()
+            # collation is native code called through ctypes (the GIL is released): two workers give
+            # two batches in flight, which the 0.33 ms tagger step needs (one collate takes about as long)
+            for _ in range(self._workers):
+                t = threading.Thread(target=self._prefetch_loop, daemon=True)
+                t.start()
+                self._threads.append(t)
 
     # ------------------------------------------------------------------ host side
     def _fill(self, stage: dict, ids: np.ndarray) -> None:
@@ -327,33 +348,65 @@ class Trainer:
             ev.record(self._side)
         stage["event"] = ev
 
+    def _produce(self, ticket: dict) -> None:
+        stage = ticket["stage"]
+        try:
+            ev = stage.get("event")
+            if ev is not None:
+                ev.synchronize()                # the previous H2D copy out of this pinned buffer has finished
+            t0 = time.perf_counter()
+            self._fill(stage, ticket["ids"])
+            self._upload(stage)
+            ticket["cost"] = time.perf_counter() - t0
+        except BaseException as e:              # surfaced in the training thread by _take()
+            ticket["err"] = e
+        ticket["done"].set()
+
     def _prefetch_loop(self) -> None:
         torch.cuda.set_device(self.device)
         while True:
-            item = self._q_in.get()
-            if item is None:
+            ticket = self._q_in.get()
+            if ticket is None:
                 return
-            stage, ids = item
-            try:
-                self._fill(stage, ids)
-                self._upload(stage)
-                self._q_out.put((stage, None))
-            except BaseException as e:          # surface in the training thread
-                self._q_out.put((stage, e))
+            self._produce(ticket)
 
     def prepare(self, ids: np.ndarray) -> None:
-        """Queue the collation of a future batch (returns immediately)."""
+        """Queue the collation of a future batch (returns immediately).  Up to ``prefetch_depth``
+        batches may be prepared ahead of the step that is about to run."""
         if self.max_doc_len is not None and len(ids) and int(self.store.lens[ids].max()) > self.max_doc_len:
             raise ValueError(f"batch contains a document longer than {self.max_doc_len} tokens; "
                              "use nlp.update (generic path) for it")
+        if len(self._pending) >= len(self.stages) - 1:
+            raise RuntimeError(f"{len(self._pending)} batches prepared and not consumed: the staging ring has "
+                               f"{len(self.stages)} buffers (prepare at most prefetch_depth = {self.prefetch_depth} ahead)")
         stage = self.stages[self._stage_i]
         self._stage_i = (self._stage_i + 1) % len(self.stages)
+        ticket = {"stage": stage, "ids": ids, "done": threading.Event(), "err": None}
+        self._pending.append(ticket)
         if self._prefetch:
-            self._q_in.put((stage, ids))
+            self._q_in.put(ticket)
         else:
-            self._fill(stage, ids)
-            self._upload(stage)
-            self._q_out.put((stage, None))
+            self._produce(ticket)
+
+    def _take(self) -> dict:
+        """The oldest prepared batch (its staging record), in the order ``prepare`` was called."""
+        ticket = self._pending.popleft()
+        ticket["done"].wait()
+        if self.prefetch_depth < self._workers:
+            # host-bound?  compare what a collate costs with the period at which batches are consumed
+            now = time.perf_counter()
+            if self._last_take is not None:
+                self._takes += 1
+                self._period += now - self._last_take
+                self._cost += ticket.get("cost", 0.0)
+                if self._takes >= 8:
+                    if self._cost > 0.5 * self._period:
+                        self.prefetch_depth = self._workers
+                    self._takes, self._period, self._cost = 0, 0.0, 0.0
+            self._last_take = now
+        if ticket["err"] is not None:
+            raise ticket["err"]
+        return ticket["stage"]
 
     # ------------------------------------------------------------------ device side
     def _batch_views(self, rows: int) -> tuple:
@@ -501,9 +554,7 @@ class Trainer:
     def step_async(self) -> torch.Tensor:
         """Consume the next prepared batch: H2D copy + (graph) step.  Returns the loss tensor
         (device); reading it is the caller's D2H sync."""
-        stage, err = self._q_out.get()
-        if err is not None:
-            raise err
+        stage = self._take()
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(stage["event"])                              # the packed H2D copy (side stream)
         self.dev_buf.copy_(stage["land"], non_blocking=True)        # D2D into the static graph input
@@ -588,9 +639,14 @@ class Trainer:
         stage = self.stages[self._stage_i]
         self._stage_i = (self._stage_i + 1) % len(self.stages)
         hist = np.zeros(int(adhoc.n_groups.sum()) + len(adhoc.n_groups), dtype=np.int32)
+        ev = stage.get("event")
+        if ev is not None:
+            ev.synchronize()
         fill_stage(adhoc, self.lay, stage, np.arange(len(examples), dtype=np.int64), hist=hist)
         self._upload(stage)
-        self._q_out.put((stage, None))
+        done = threading.Event()
+        done.set()
+        self._pending.append({"stage": stage, "ids": None, "done": done, "err": None})
         self.adhoc_batches += 1
         return self.step_async()
 
@@ -634,7 +690,8 @@ class Trainer:
         return out
 
     def close(self) -> None:
-        if self._thread is not None:
+        for _ in self._threads:
             self._q_in.put(None)
-            self._thread.join(timeout=5)
-            self._thread = None
+        for t in self._threads:
+            t.join(timeout=5)
+        self._threads = []

@@ -210,6 +210,41 @@ def test_train_step_reads_each_loss_one_step_late():
     assert last1 == pytest.approx(blocking[-1], rel=3e-2)
 
 
+def test_prepared_batches_are_consumed_in_submission_order_with_two_collate_workers():
+    """Two collate workers may finish out of order (a 4-doc batch behind a 64-doc one); ``step_async`` must
+    still run the batches in the order ``prepare`` was called, and preparing past the staging ring must raise."""
+    from conftest import multi_cfg
+    from spacy_ray_b200.config import Config
+    from spacy_ray_b200.engine import Trainer
+    from spacy_ray_b200.worker import Worker
+
+    text = multi_cfg(["ner"], width=64, depth=1, n_docs=256, max_len=16, hidden=64)
+    w = Worker(Config().from_str(text, interpolate=False), rank=0, num_workers=1, use_gpu=0, mode="sync", comm="auto")
+    w.set_proxy(None)
+    exs = list(w.train_corpus(w.nlp))
+    tr = Trainer(w.nlp, w.proxy, exs, docs_per_batch=64, dropout=0.0, prefetch=True, prefetch_workers=2)
+    assert len(tr._threads) == 2 and len(tr.stages) >= 4
+    sizes = [64, 4, 48, 2, 64, 8, 1, 33]
+    i = 0
+    while i < len(sizes):
+        pair = sizes[i:i + 2]
+        for n in pair:
+            tr.prepare(np.arange(n, dtype=np.int64))
+        for n in pair:
+            tr.step_async()
+            assert tr.last["docs"] == n, (sizes, i, tr.last)
+        i += 2
+    for n in (3, 5, 7):
+        tr.prepare(np.arange(n, dtype=np.int64))
+    with pytest.raises(RuntimeError):
+        tr.prepare(np.arange(2, dtype=np.int64))
+    for n in (3, 5, 7):
+        tr.step_async()
+        assert tr.last["docs"] == n
+    torch.cuda.synchronize()
+    tr.close()
+
+
 def test_learning_rate_changes_reach_the_captured_step():
     """The fused exchange kernel reads its hyper-parameters from a device tensor; a schedule that
     changes the learning rate between steps must take effect on CUDA-graph replays too."""

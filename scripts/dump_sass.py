@@ -19,15 +19,19 @@ OUT = ROOT / "profiles" / "sass"
 
 # demangled-name substrings of the kernels on the measured paths (template args as cuobjdump prints them)
 HOT = [
-    ("gemm_fwd_window_maxout_pair_halo", "gemm_kernelILi192ELi0ELi1ELi2ELb1ELb1E"),
-    ("gemm_fwd_plain_maxout_pair", "gemm_kernelILi192ELi0ELi1ELi2ELb1ELb0E"),
+    ("gemm_fwd_window_maxout_pair_halo", "gemm_kernelILi192ELi0ELi1ELi2ELb1ELb1ELb0E"),
+    ("gemm_fwd_window_maxout_pair_halo_resident_b", "gemm_kernelILi192ELi0ELi1ELi2ELb1ELb1ELb1E"),
+    ("gemm_fwd_window_maxout_ln_pair_halo", "gemm_kernelILi192ELi0ELi3ELi2ELb1ELb1ELb0E"),
+    ("gemm_fwd_plain_maxout_pair", "gemm_kernelILi192ELi0ELi1ELi2ELb1ELb0ELb0E"),
     ("gemm_dx_window_pair_halo", "gemm_kernelILi128ELi2ELi0ELi2ELb1ELb1E"),
     ("gemm_dx_plain_pair", "gemm_kernelILi256ELi2ELi0ELi2ELb1ELb0E"),
     ("gemm_dw_splitk_pair", "gemm_kernelILi256ELi1ELi2ELi2ELb1ELb0E"),
     ("gemm_linear_store_pair", "gemm_kernelILi192ELi0ELi0ELi2ELb1ELb0E"),
     ("gemm_linear_n64", "gemm_kernelILi64ELi0ELi0ELi1ELb0ELb0E"),
-    ("maxout_ln_fwd_vec", "maxout_ln_fwd_vec_kernelILi1ELi8ELi4E"),
-    ("maxout_ln_bwd_vec", "maxout_ln_bwd_vec_kernelILi3ELi8ELi2E"),
+    ("maxout_ln_fwd_vec", "maxout_ln_fwd_vec_kernelILi1ELi8ELi4ELi32ELb1E"),
+    ("maxout_ln_fwd_vec_w96", "maxout_ln_fwd_vec_kernelILi1ELi8ELi4ELi16ELb0E"),
+    ("maxout_ln_bwd_vec", "maxout_ln_bwd_vec_kernelILi3ELi8ELi2ELi32ELb1E"),
+    ("maxout_ln_bwd_vec_w96", "maxout_ln_bwd_vec_kernelILi3ELi8ELi2ELi16ELb0E"),
     ("hash_embed_fwd", "hash_embed_fwd_kernel"),
     ("hash_embed_bwd_sorted_i32", "hash_embed_bwd_sorted_kernelIiE"),
     ("biluo_block", "biluo_block_kernel"),
@@ -35,6 +39,8 @@ HOT = [
     ("arc_eager_steps", "arc_eager_steps_kernel"),
     ("transition_scatter", "transition_scatter_kernel"),
     ("linear_softmax_xent", "linear_softmax_xent_kernel"),
+    ("softmax_xent_bias", "softmax_xent_bias_kernel"),
+    ("arena_init", "arena_init_kernel"),
     ("bucket_signal", "bucket_signal_kernel"),
     ("bucket_wait", "bucket_wait_kernel"),
     ("bucket_reduce", "bucket_reduce_kernel"),

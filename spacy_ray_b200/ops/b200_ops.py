@@ -460,7 +460,9 @@ class B200Ops(TorchOps):
                 T, w = X.shape
                 n16 = (nC + 15) // 16 * 16
                 bn = 64 if n16 <= 64 else 128
-                logits = self._workspace("tag_logits", T, bn)
+                # (one scratch per head - keyed by its weights - because the heads of a multi-task pipeline run
+                # on concurrent streams; allocated by the eager first step, never under capture)
+                logits = self._workspace(f"tag_logits@{W.data_ptr():x}", T, bn)
                 self.tc_gemm(X, W.contiguous(), logits, mode=MODE_KK, epi=EPI_ATOMIC_F32, block_n=bn, M=T, N=n16, K=w,
                              splits=1, cluster=1)
                 out = self.k.softmax_xent_bias(logits, b.to(torch.bfloat16).contiguous(), labels.contiguous(), nC)
@@ -584,6 +586,9 @@ class B200Ops(TorchOps):
         (fp32, zeroed once) and the kernel-maintained [launch tag, finished CTAs, time-out flag] words.
         Persistent and sized once like ``_workspace`` (``max_rows_hint``)."""
         need = (rows + 255) // 256 * 256
+        # (one scratch per width class, allocated by the eager first step - never under capture; the fused
+        # epilogue therefore assumes the encoders of a pipeline run on ONE stream, which is how the engine
+        # schedules a shared tok2vec)
         key = ("ln_scratch", n_tiles)
         cur = self._ws.get(key)
         if cur is None or cur[2] < need:

@@ -128,20 +128,36 @@ class TorchDistComm:
     This is the baseline path ("B-nccl" in BASELINE.md), not the product."""
     name = "dist"
 
-    def __init__(self, rank: int, world_size: int, group=None):
+    def __init__(self, rank: int, world_size: int, group=None, grad_transport: str = "fp32"):
         import torch.distributed as dist
 
+        if grad_transport not in ("fp32", "bf16"):
+            raise ValueError(f"grad_transport must be 'fp32' or 'bf16', got {grad_transport!r}")
         self.dist = dist
         self.rank, self.world_size, self.group = rank, world_size, group
+        self.grad_transport = grad_transport
         self._rs_ok: Optional[bool] = None
         self._shard_buf: Optional[torch.Tensor] = None
+        self._bf16_buf: Optional[torch.Tensor] = None
 
     def reduce_scatter(self, grad_flat: torch.Tensor, layout: FlatLayout) -> torch.Tensor:
+        if self.grad_transport == "bf16" and grad_flat.dtype == torch.float32:
+            # bf16 on the wire (half the bytes; SURVEY 5.8 / BASELINE "cast/scale"): every rank rounds its
+            # local fp32 gradient once, the sum is formed by the collective in bf16 and handed back to the
+            # fp32 optimizer.  bf16 keeps fp32's exponent range, so no loss scaling is needed.
+            if self._bf16_buf is None or self._bf16_buf.shape != grad_flat.shape or self._bf16_buf.device != grad_flat.device:
+                self._bf16_buf = torch.empty_like(grad_flat, dtype=torch.bfloat16)
+            self._bf16_buf.copy_(grad_flat)
+            return self._reduce_scatter(self._bf16_buf, layout).to(torch.float32)
+        return self._reduce_scatter(grad_flat, layout)
+
+    def _reduce_scatter(self, grad_flat: torch.Tensor, layout: FlatLayout) -> torch.Tensor:
         cap = layout.shard_cap
         mine = grad_flat[self.rank * cap:(self.rank + 1) * cap]
         if self._rs_ok is not False:
             try:
-                if self._shard_buf is None or self._shard_buf.shape != mine.shape or self._shard_buf.device != mine.device:
+                if (self._shard_buf is None or self._shard_buf.shape != mine.shape or self._shard_buf.device != mine.device
+                        or self._shard_buf.dtype != mine.dtype):
                     self._shard_buf = torch.empty_like(mine)
                 self.dist.reduce_scatter_tensor(self._shard_buf, grad_flat, op=self.dist.ReduceOp.SUM, group=self.group)
                 self._rs_ok = True

@@ -7,7 +7,7 @@ including dotted config overrides from leftover args (``:44``) and loading the
 config un-interpolated (``:46``).  Unlike the reference, ``--output`` is wired
 (``:41`` is a TODO there).  Extra flags select the data plane:
 ``--mode sync|async``, ``--comm auto|dist|fused``, ``--quorum K``,
-``--shard-balance auto|nodes|bytes|lpt``, ``--resume PATH``.
+``--shard-balance auto|nodes|bytes|lpt``, ``--grad-transport fp32|bf16``, ``--resume PATH``.
 
 ``ray_train(config, *, ray_address, num_workers, use_gpu, code_path)`` keeps the
 reference's Python signature (``:56-63``) and control flow (create workers ->
@@ -85,6 +85,8 @@ def _add_train_args(p: argparse.ArgumentParser) -> None:
     p.add_argument("--comm", choices=["auto", "dist", "fused", "local"], default="auto")
     p.add_argument("--quorum", type=int, default=None, help="async mode: gradients per update (reference default 2)")
     p.add_argument("--shard-balance", choices=["auto", "nodes", "bytes", "lpt"], default="auto")
+    p.add_argument("--grad-transport", choices=["fp32", "bf16"], default="fp32",
+                   help="gradient dtype on the wire for --comm dist (library collectives); optimizer state stays fp32")
     p.add_argument("--resume", dest="resume_path", type=Path, default=None, help="Checkpoint dir to resume from")
     p.add_argument("--no-shard-data", dest="shard_data", action="store_false",
                    help="Give every rank the full corpus (reference behaviour)")
@@ -133,6 +135,7 @@ def ray_train_cli(args: argparse.Namespace, extra: Sequence[str]) -> None:
         comm=args.comm,
         quorum=args.quorum,
         shard_balance=args.shard_balance,
+        grad_transport=args.grad_transport,
         resume_path=args.resume_path,
         shard_data=args.shard_data,
         inject_fault=args.inject_fault,
@@ -151,6 +154,7 @@ def ray_train(
     comm: str = "auto",
     quorum: Optional[int] = None,
     shard_balance: str = "auto",
+    grad_transport: str = "fp32",
     resume_path: Optional[Path] = None,
     shard_data: bool = True,
     inject_fault: Optional[str] = None,
@@ -180,6 +184,7 @@ def ray_train(
             resume_path=resume_path,
             shard_data=shard_data,
             shard_balance=shard_balance,
+            grad_transport=grad_transport,
             dist_init=dist_init,
             inject_fault=inject_fault,
         )

@@ -75,6 +75,7 @@ class Worker:
         resume_path: Optional[Path] = None,
         shard_data: bool = True,
         shard_balance: str = "auto",
+        grad_transport: str = "fp32",
         dist_init: Optional[Dict[str, Any]] = None,
         fused_ops: bool = True,
         inject_fault: Optional[str] = None,
@@ -92,6 +93,7 @@ class Worker:
         self.resume_path = Path(resume_path) if resume_path else None
         self.shard_data = shard_data
         self.shard_balance = shard_balance
+        self.grad_transport = grad_transport
         self.dist_init = dict(dist_init or {})
         self.inject_fault = inject_fault
         self.gpu_id = self._resolve_gpu(use_gpu, fused_ops)
@@ -237,8 +239,11 @@ class Worker:
                 comm: Any = LocalComm(self.rank, self.num_workers)
             elif comm_name == "dist":
                 self._ensure_dist()
-                comm = TorchDistComm(self.rank, self.num_workers)
+                comm = TorchDistComm(self.rank, self.num_workers, grad_transport=self.grad_transport)
             elif comm_name == "fused":
+                if self.grad_transport != "fp32":
+                    logger.warning("--grad-transport %s applies to --comm dist; the fused peer-memory exchange "
+                                   "moves fp32 gradients", self.grad_transport)
                 if self.num_workers > 1:
                     self._ensure_dist()
                 from .parallel.fused_comm import FusedSymmComm

@@ -63,10 +63,14 @@ def build_parser() -> argparse.ArgumentParser:
     _add_train_args(train)
     plain = sub.add_parser("train", help="Single-process training (no workers).")
     _add_train_args(plain)
-    conv = sub.add_parser("convert", help="Convert a JSONL corpus to a DocBin (.spacy) file, like `spacy convert`.")
+    conv = sub.add_parser("convert", help="Convert a JSONL / CoNLL-U / IOB corpus to a DocBin (.spacy) file, like `spacy convert`.")
     conv.add_argument("input_path", type=Path)
     conv.add_argument("output_path", type=Path, help="output file (.spacy) or directory")
-    conv.add_argument("--limit", "-n", type=int, default=0)
+    conv.add_argument("--limit", "-L", type=int, default=0, help="stop after this many documents")
+    conv.add_argument("--converter", "-c", choices=["auto", "jsonl", "conllu", "iob"], default="auto")
+    conv.add_argument("--n-sents", "-n", type=int, default=1, help="sentences per document (CoNLL-U / IOB)")
+    conv.add_argument("--tag-column", choices=["xpos", "upos"], default="xpos", help="CoNLL-U column that becomes Doc.tags")
+    conv.add_argument("--lang", "-l", default=None, help="accepted for `spacy convert` compatibility (unused)")
     return parser
 
 
@@ -101,12 +105,14 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         parser.print_help()
         return 1
     if args.group == "convert":
-        from .training.docbin import convert_jsonl
+        from .training.docbin import convert
 
         out = args.output_path
         if out.suffix != ".spacy":
+            out.mkdir(parents=True, exist_ok=True)
             out = out / (args.input_path.stem + ".spacy")
-        n = convert_jsonl(args.input_path, out, limit=args.limit)
+        n = convert(args.input_path, out, converter=args.converter, n_sents=args.n_sents, limit=args.limit,
+                    tag_column=args.tag_column)
         print(f"✔ Generated output file ({n} documents): {out}")
         return 0
     try:

@@ -283,3 +283,147 @@ def convert_jsonl(src: Union[str, Path], dst: Union[str, Path], *, limit: int = 
                 break
     db.to_disk(dst)
     return len(db)
+
+
+# ----------------------------------------------------------------------------------------------
+# `spacy convert` for the treebank / NER column formats (what real tagger / parser / NER corpora
+# ship as): CoNLL-U and IOB / CoNLL-2003.  Output: Docs with words, spaces, tags, heads, deps, ents.
+# ----------------------------------------------------------------------------------------------
+def _biluo_or_iob_to_spans(tags: Sequence[str]) -> List[tuple]:
+    """Entity spans ``(start, end_exclusive, label)`` from IOB / IOB2 / BILUO token tags."""
+    spans, start, label = [], None, None
+
+    def close(i):
+        nonlocal start, label
+        if start is not None:
+            spans.append((start, i, label))
+        start, label = None, None
+
+    for i, t in enumerate(tags):
+        t = t or "O"
+        if t in ("O", "-", "_", ""):
+            close(i)
+            continue
+        prefix, _, lab = t.partition("-")
+        if not lab:                      # bare label without a prefix: treat as I-
+            prefix, lab = "I", t
+        if prefix in ("B", "U") or (prefix in ("I", "L") and (start is None or lab != label)):
+            close(i)
+            start, label = i, lab
+        if prefix in ("L", "U"):
+            close(i + 1)
+    close(len(tags))
+    return spans
+
+
+def read_conllu(src: Union[str, Path], *, n_sents: int = 1, tag_column: str = "xpos", merge_subtokens: bool = False):
+    """Docs from a CoNLL-U treebank (ID FORM LEMMA UPOS XPOS FEATS HEAD DEPREL DEPS MISC).  ``n_sents``
+    sentences are concatenated per Doc (heads re-based, every sentence root heads itself - the parser's
+    sentence boundaries come from that); multi-word-token ranges (``3-4``) and empty nodes (``5.1``) are
+    skipped (``merge_subtokens`` is accepted for CLI compatibility and not implemented); NER tags in MISC
+    (``NER=B-ORG``/``name=B-ORG``, as `spacy convert` reads them) become ``ents``."""
+    col = {"upos": 3, "xpos": 4}[tag_column]
+    sents, cur = [], []
+    with Path(src).open("r", encoding="utf8") as fh:
+        for line in list(fh) + [""]:
+            line = line.rstrip("\n")
+            if not line.strip():
+                if cur:
+                    sents.append(cur)
+                    cur = []
+                continue
+            if line.startswith("#"):
+                continue
+            parts = line.split("\t")
+            if len(parts) < 8 or "-" in parts[0] or "." in parts[0]:
+                continue
+            cur.append(parts)
+    docs = []
+    for i in range(0, len(sents), max(1, n_sents)):
+        words, spaces, tags, heads, deps, ner = [], [], [], [], [], []
+        any_ner = False
+        for sent in sents[i:i + max(1, n_sents)]:
+            base = len(words)
+            for parts in sent:
+                tid = int(parts[0]) - 1
+                head = int(parts[6]) if parts[6].isdigit() else 0
+                misc = parts[9] if len(parts) > 9 else "_"
+                words.append(parts[1])
+                spaces.append("SpaceAfter=No" not in misc)
+                tag = parts[col] if parts[col] != "_" else parts[3]
+                tags.append(tag)
+                heads.append(base + (tid if head == 0 else head - 1))
+                deps.append("ROOT" if head == 0 else parts[7])
+                t = "O"
+                for kv in misc.split("|"):
+                    k, _, v = kv.partition("=")
+                    if k in ("NER", "name") and v:
+                        t, any_ner = v, True
+                ner.append(t)
+        if words:
+            docs.append(Doc(words, spaces, tags=tags, heads=heads, deps=deps,
+                            ents=_biluo_or_iob_to_spans(ner) if any_ner else None))
+    return docs
+
+
+def read_iob(src: Union[str, Path], *, n_sents: int = 1):
+    """Docs from the NER column formats `spacy convert` takes: CoNLL-2003 style (one token per line,
+    whitespace-separated columns, word first, NER tag last, POS tag second if there are >= 3 columns,
+    blank line = sentence, ``-DOCSTART-`` = document) or spaCy's ``.iob`` (one sentence per line,
+    ``word|tag|ner`` or ``word|ner`` tokens)."""
+    sents, cur = [], []
+    with Path(src).open("r", encoding="utf8") as fh:
+        lines = [ln.rstrip("\n") for ln in fh]
+    pipe_format = any("|" in ln and len(ln.split()) > 1 and all("|" in t for t in ln.split()) for ln in lines if ln.strip())
+    if pipe_format:
+        for ln in lines:
+            toks = ln.split()
+            if not toks:
+                continue
+            rows = []
+            for t in toks:
+                f = t.split("|")
+                rows.append((f[0], f[1] if len(f) >= 3 else None, f[-1]))
+            sents.append(rows)
+    else:
+        for ln in lines + [""]:
+            if not ln.strip() or ln.startswith("-DOCSTART-"):
+                if cur:
+                    sents.append(cur)
+                    cur = []
+                continue
+            f = ln.split()
+            cur.append((f[0], f[1] if len(f) >= 3 else None, f[-1]))
+    docs = []
+    for i in range(0, len(sents), max(1, n_sents)):
+        words, tags, ner = [], [], []
+        for sent in sents[i:i + max(1, n_sents)]:
+            for w, tag, t in sent:
+                words.append(w)
+                tags.append(tag)
+                ner.append(t)
+        if words:
+            docs.append(Doc(words, tags=tags if all(t is not None for t in tags) else None,
+                            ents=_biluo_or_iob_to_spans(ner)))
+    return docs
+
+
+def convert(src: Union[str, Path], dst: Union[str, Path], *, converter: str = "auto", n_sents: int = 1,
+            limit: int = 0, tag_column: str = "xpos") -> int:
+    """``spacy convert``: ``.jsonl`` / ``.conllu`` (``.conll``) / ``.iob`` (``.ner``) -> DocBin."""
+    src = Path(src)
+    kind = converter
+    if kind == "auto":
+        ext = src.suffix.lower().lstrip(".")
+        kind = {"jsonl": "jsonl", "json": "jsonl", "conllu": "conllu", "conll": "conllu", "iob": "iob", "ner": "iob"}.get(ext)
+        if kind is None:
+            raise ValueError(f"cannot guess the converter for {src.name!r}; pass --converter jsonl|conllu|iob")
+    if kind == "jsonl":
+        return convert_jsonl(src, dst, limit=limit)
+    docs = read_conllu(src, n_sents=n_sents, tag_column=tag_column) if kind == "conllu" else read_iob(src, n_sents=n_sents)
+    db = DocBin()
+    for d in docs[: limit or None]:
+        db.add(d)
+    db.to_disk(dst)
+    return len(db)
+

@@ -87,3 +87,59 @@ def test_corpus_reader_reads_spacy_files_and_convert_cli(tmp_path):
     assert convert_jsonl(src, tmp_path / "two.spacy", limit=2) == 2
     with pytest.raises(ValueError):
         DocBin().from_bytes(b"not a docbin")
+
+
+CONLLU = """# sent_id = 1
+# text = The cat sat.
+1\tThe\tthe\tDET\tDT\t_\t2\tdet\t_\t_
+2\tcat\tcat\tNOUN\tNN\t_\t3\tnsubj\t_\t_
+3\tsat\tsit\tVERB\tVBD\t_\t0\troot\t_\tSpaceAfter=No
+4\t.\t.\tPUNCT\t.\t_\t3\tpunct\t_\t_
+
+# sent_id = 2
+1-2\tdon't\t_\t_\t_\t_\t_\t_\t_\t_
+1\tdo\tdo\tAUX\tVBP\t_\t3\taux\t_\t_
+2\tn't\tnot\tPART\tRB\t_\t3\tadvmod\t_\t_
+3\tgo\tgo\tVERB\tVB\t_\t0\troot\t_\tNER=O
+3.1\tghost\t_\t_\t_\t_\t_\t_\t_\t_
+4\tParis\tParis\tPROPN\tNNP\t_\t3\tobl\t_\tNER=B-GPE
+"""
+
+
+def test_convert_conllu_reads_tags_heads_deps_sentences_and_misc_ner(tmp_path):
+    from spacy_ray_b200.training.docbin import DocBin, convert, read_conllu
+
+    src = tmp_path / "tb.conllu"
+    src.write_text(CONLLU, encoding="utf8")
+    docs = read_conllu(src, n_sents=1)
+    assert [d.words for d in docs] == [["The", "cat", "sat", "."], ["do", "n't", "go", "Paris"]]
+    assert docs[0].tags == ["DT", "NN", "VBD", "."] and docs[0].heads == [1, 2, 2, 2]
+    assert docs[0].deps == ["det", "nsubj", "ROOT", "punct"] and docs[0].spaces == [True, True, False, True]
+    assert docs[1].ents == [(3, 4, "GPE")] and not docs[0].has_ents_annotation
+    both = read_conllu(src, n_sents=2, tag_column="upos")
+    assert len(both) == 1 and both[0].heads == [1, 2, 2, 2, 6, 6, 6, 6] and both[0].tags[:2] == ["DET", "NOUN"]
+    n = convert(src, tmp_path / "tb.spacy", n_sents=2)
+    assert n == 1
+    back = list(DocBin().from_disk(tmp_path / "tb.spacy").get_docs())
+    assert back[0].words == both[0].words and back[0].heads == both[0].heads and back[0].deps[2] == "ROOT"
+
+
+def test_convert_iob_formats(tmp_path):
+    from spacy_ray_b200.training.docbin import _biluo_or_iob_to_spans, convert, read_iob
+
+    assert _biluo_or_iob_to_spans(["O", "B-PER", "I-PER", "O", "I-LOC", "B-LOC", "U-ORG", "B-X", "L-X"]) == [
+        (1, 3, "PER"), (4, 5, "LOC"), (5, 6, "LOC"), (6, 7, "ORG"), (7, 9, "X")]
+    conll = tmp_path / "ner.conll"
+    conll.write_text("-DOCSTART- -X- O O\n\nJohn NNP B-NP B-PER\nSmith NNP I-NP I-PER\nsleeps VBZ B-VP O\n\nParis NNP B-NP B-LOC\n",
+                     encoding="utf8")
+    docs = read_iob(conll)
+    assert [d.words for d in docs] == [["John", "Smith", "sleeps"], ["Paris"]]
+    assert docs[0].ents == [(0, 2, "PER")] and docs[0].tags == ["NNP", "NNP", "VBZ"] and docs[1].ents == [(0, 1, "LOC")]
+    iob = tmp_path / "ner.iob"
+    iob.write_text("I|PRP|O like|VBP|O London|NNP|B-GPE .|.|O\nBerlin|B-GPE rocks|O\n", encoding="utf8")
+    docs = read_iob(iob, n_sents=2)
+    assert len(docs) == 1 and docs[0].words[2] == "London" and docs[0].ents == [(2, 3, "GPE"), (4, 5, "GPE")]
+    assert docs[0].tags is None                       # the second sentence has no tag column
+    assert convert(iob, tmp_path / "ner.spacy") == 2
+    with pytest.raises(ValueError):
+        convert(tmp_path / "x.unknown", tmp_path / "x.spacy")

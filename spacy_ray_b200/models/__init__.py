@@ -5,11 +5,12 @@ an upstream ``.cfg`` resolves unchanged:
 
 ``spacy.Tok2Vec.v2``, ``spacy.MultiHashEmbed.v2``, ``spacy.MaxoutWindowEncoder.v2``,
 ``spacy.HashEmbedCNN.v2``, ``spacy.Tok2VecListener.v1``, ``spacy.Tagger.v1/v2``,
-``spacy.TransitionBasedParser.v2``.
+``spacy.TransitionBasedParser.v2``, ``spacy.TextCatCNN.v1/v2``, ``spacy.TextCatReduce.v1``.
 """
 from ..config import registry
 from ..nn import layers as L
 from .tagger import build_tagger_model
+from .textcat import build_textcat_model
 from .transition_model import build_transition_model, TransitionModelOutput
 
 for _v in ("v1", "v2"):
@@ -19,7 +20,9 @@ for _v in ("v1", "v2"):
     registry.architectures.register(f"spacy.HashEmbedCNN.{_v}", L.HashEmbedCNN)
     registry.architectures.register(f"spacy.Tagger.{_v}", build_tagger_model)
 registry.architectures.register("spacy.Tok2VecListener.v1", L.Tok2VecListener)
+for _n in ("spacy.TextCatCNN.v1", "spacy.TextCatCNN.v2", "spacy.TextCatReduce.v1"):
+    registry.architectures.register(_n, build_textcat_model)
 for _v in ("v1", "v2", "v3"):
     registry.architectures.register(f"spacy.TransitionBasedParser.{_v}", build_transition_model)
 
-__all__ = ["build_tagger_model", "build_transition_model", "TransitionModelOutput"]
+__all__ = ["build_tagger_model", "build_textcat_model", "build_transition_model", "TransitionModelOutput"]

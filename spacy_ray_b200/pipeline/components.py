@@ -247,6 +247,121 @@ class Tagger(TrainablePipe):
 
 
 # ============================================================================
+class SentenceRecognizer(Tagger):
+    """``senter``: a two-label token tagger (``I`` / ``S``) whose ``S`` marks the first token of a sentence.
+    Gold comes from ``Doc.sent_starts`` or, for treebank docs, from the roots of the dependency tree."""
+    default_score_weights = {"sents_f": 1.0, "sents_p": 0.0, "sents_r": 0.0}
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        for l in ("I", "S"):
+            self.add_label(l)
+        self._after_labels()
+        self.model.initialize()
+
+    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
+        arr = np.full((batch.n_rows,), -1, dtype=np.int64)
+        for eg, s in zip(examples, batch.starts):
+            ref = eg.reference
+            ids = ref.user_data.get(("senter_ids", self.name))
+            if ids is None:
+                starts = ref.gold_sent_starts()
+                if starts is None:
+                    ids = np.full((len(ref),), -1, dtype=np.int64)
+                else:
+                    ids = np.array([-1 if v is None else int(bool(v)) for v in starts], dtype=np.int64)
+                ref.user_data[("senter_ids", self.name)] = ids
+            arr[s:s + len(ids)] = ids
+        from ..nn.batch import to_device
+
+        return to_device(arr, batch.device)
+
+    def set_annotations(self, docs, preds) -> None:
+        host = preds.to("cpu").tolist()
+        row = 1
+        for doc in docs:
+            n = len(doc)
+            starts = [bool(v == 1) for v in host[row:row + n]]
+            if starts:
+                starts[0] = True
+            doc.sent_starts = starts
+            row += n + 1
+
+    def score(self, examples):
+        return S.score_sents(examples)
+
+
+class Morphologizer(Tagger):
+    """``morphologizer``: one label per (morphological features, UPOS) combination seen in training,
+    written the way spaCy does (``"Case=Nom|Number=Sing|POS=NOUN"``); predicts ``Doc.pos`` and ``Doc.morphs``."""
+    default_score_weights = {"pos_acc": 0.5, "morph_acc": 0.5}
+
+    @staticmethod
+    def _label_of(pos: Optional[str], morph: Optional[str]) -> Optional[str]:
+        if not pos and not morph:
+            return None
+        feats = [f for f in (morph or "").split("|") if f and f != "_" and not f.startswith("POS=")]
+        if pos:
+            feats.append(f"POS={pos}")
+        return "|".join(sorted(feats))
+
+    @staticmethod
+    def _split(label: str):
+        feats = [f for f in label.split("|") if f]
+        pos = next((f[4:] for f in feats if f.startswith("POS=")), None)
+        return pos, "|".join(f for f in feats if not f.startswith("POS="))
+
+    def _ref_labels(self, ref: Doc) -> List[Optional[str]]:
+        n = len(ref)
+        pos = ref.pos or [None] * n
+        morphs = ref.morphs or [None] * n
+        return [self._label_of(p, m) for p, m in zip(pos, morphs)]
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                seen.update(l for l in self._ref_labels(eg.reference) if l)
+            for l in sorted(seen):
+                self.add_label(l)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no POS / morphological annotation found in the training data")
+        self._after_labels()
+        self.model.initialize()
+
+    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
+        index = {l: i for i, l in enumerate(self._labels)}
+        arr = np.full((batch.n_rows,), -1, dtype=np.int64)
+        for eg, s in zip(examples, batch.starts):
+            ref = eg.reference
+            ids = ref.user_data.get(("morph_ids", self.name))
+            if ids is None:
+                ids = np.array([index.get(l, -1) if l else -1 for l in self._ref_labels(ref)], dtype=np.int64)
+                ref.user_data[("morph_ids", self.name)] = ids
+            arr[s:s + len(ids)] = ids
+        from ..nn.batch import to_device
+
+        return to_device(arr, batch.device)
+
+    def set_annotations(self, docs, preds) -> None:
+        host = preds.to("cpu").tolist()
+        row = 1
+        for doc in docs:
+            n = len(doc)
+            pairs = [self._split(self._labels[i]) for i in host[row:row + n]]
+            doc.pos = [p for p, _ in pairs]
+            doc.morphs = [m for _, m in pairs]
+            row += n + 1
+
+    def score(self, examples):
+        out = S.score_token_attr(examples, "pos", "pos_acc")
+        out.update(S.score_token_attr(examples, "morphs", "morph_acc"))
+        return out
+
+
+# ============================================================================
 class EntityRecognizer(TrainablePipe):
     default_score_weights = {"ents_f": 1.0, "ents_p": 0.0, "ents_r": 0.0, "ents_per_type": None}
 
@@ -451,6 +566,81 @@ class DependencyParser(TrainablePipe):
         return S.score_deps(examples)
 
 
+# ============================================================================
+class TextCategorizer(TrainablePipe):
+    """``textcat`` (mutually exclusive classes) / ``textcat_multilabel``: document categories in ``Doc.cats``.
+    Labels come from the keys of the training docs' ``cats``; a label missing from a doc's ``cats`` is
+    ignored for that doc (spaCy's ``not_missing`` mask).  Loss reported = mean squared error, as upstream."""
+    default_score_weights = {"cats_score": 1.0, "cats_macro_f": 0.0, "cats_micro_f": 0.0, "cats_macro_p": None,
+                             "cats_macro_r": None, "cats_micro_p": None, "cats_micro_r": None, "cats_f_per_type": None}
+    multi_label = False
+
+    def _after_labels(self) -> None:
+        if self.model.has_dim("nO") is None and self._labels:
+            self.model.set_dim("nO", len(self._labels))
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                seen.update((eg.reference.cats or {}).keys())
+            for l in sorted(seen):
+                self.add_label(l)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no document categories (Doc.cats) found in the training data")
+        if not self.multi_label and len(self._labels) < 2:
+            raise ValueError(f"[{self.name}] mutually exclusive classes need at least two labels; "
+                             "use textcat_multilabel for a single yes/no category")
+        exclusive = self.model.attrs.get("exclusive_classes")
+        if exclusive is not None and bool(exclusive) == self.multi_label:
+            raise ValueError(f"[{self.name}] the model's exclusive_classes = {exclusive} does not fit the "
+                             f"{'textcat_multilabel' if self.multi_label else 'textcat'} component")
+        self._after_labels()
+        self.model.initialize()
+
+    def _truths(self, examples, device):
+        n, k = len(examples), len(self._labels)
+        truths = np.zeros((n, k), dtype=np.float32)
+        known = np.zeros((n, k), dtype=np.float32)
+        for i, eg in enumerate(examples):
+            cats = eg.reference.cats or {}
+            for j, l in enumerate(self._labels):
+                if l in cats:
+                    truths[i, j] = float(cats[l])
+                    known[i, j] = 1.0
+        return torch.from_numpy(truths).to(device), torch.from_numpy(known).to(device)
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        set_dropout_rate(self.model, drop)
+        scores, backprop = self.model(batch, True)
+        truths, known = self._truths(examples, scores.device)
+        diff = (scores - truths) * known
+        backprop(diff / max(len(examples), 1))
+        if sgd not in (None, False):
+            self.finish_update(sgd)
+        _add_loss(losses, self.name, (diff * diff).mean())
+        return losses
+
+    def predict(self, docs, batch):
+        return self.model.predict(batch)
+
+    def set_annotations(self, docs, scores) -> None:
+        host = scores.to("cpu").tolist()
+        for doc, row in zip(docs, host):
+            doc.cats = {l: float(v) for l, v in zip(self._labels, row)}
+
+    def score(self, examples):
+        return S.score_cats(examples, self._labels, multi_label=self.multi_label,
+                            threshold=float(self.cfg.get("threshold", 0.5)))
+
+
+class MultiLabelTextCategorizer(TextCategorizer):
+    multi_label = True
+
+
 # ---- factories ----------------------------------------------------------------
 @registry.factories("tok2vec")
 def make_tok2vec(nlp, name: str, model: Model) -> Tok2VecComponent:
@@ -460,6 +650,26 @@ def make_tok2vec(nlp, name: str, model: Model) -> Tok2VecComponent:
 @registry.factories("tagger")
 def make_tagger(nlp, name: str, model: Model, **cfg) -> Tagger:
     return Tagger(name, model, **cfg)
+
+
+@registry.factories("senter")
+def make_senter(nlp, name: str, model: Model, **cfg) -> SentenceRecognizer:
+    return SentenceRecognizer(name, model, **cfg)
+
+
+@registry.factories("morphologizer")
+def make_morphologizer(nlp, name: str, model: Model, **cfg) -> Morphologizer:
+    return Morphologizer(name, model, **cfg)
+
+
+@registry.factories("textcat")
+def make_textcat(nlp, name: str, model: Model, **cfg) -> TextCategorizer:
+    return TextCategorizer(name, model, **cfg)
+
+
+@registry.factories("textcat_multilabel")
+def make_textcat_multilabel(nlp, name: str, model: Model, **cfg) -> MultiLabelTextCategorizer:
+    return MultiLabelTextCategorizer(name, model, **cfg)
 
 
 @registry.factories("ner")
@@ -479,6 +689,26 @@ DEFAULT_MODEL_CONFIGS: Dict[str, Dict[str, Any]] = {
     },
     "tagger": {
         "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "senter": {
+        "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 12, "depth": 1, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 2, "subword_features": True, "pretrained_vectors": None},
+    },
+    "morphologizer": {
+        "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "textcat": {
+        "@architectures": "spacy.TextCatCNN.v2", "exclusive_classes": True,
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "textcat_multilabel": {
+        "@architectures": "spacy.TextCatCNN.v2", "exclusive_classes": False,
         "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
                     "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
     },

@@ -99,11 +99,14 @@ def featurize_words(words: Sequence[str]) -> np.ndarray:
 class Doc:
     """A tokenised text with optional gold annotations.
 
-    ``tags``: per-token strings; ``ents``: ``(start, end_exclusive, label)`` token
-    spans; ``heads``: absolute head index per token (root points at itself);
-    ``deps``: per-token dependency label."""
+    ``tags``: per-token fine-grained tags; ``pos`` / ``morphs`` / ``lemmas``: per-token UPOS, FEATS strings
+    (``"Case=Nom|Number=Sing"``) and lemmas; ``ents``: ``(start, end_exclusive, label)`` token spans;
+    ``heads``: absolute head index per token (root points at itself); ``deps``: per-token dependency
+    label; ``sent_starts``: per-token True / False / None (unknown); ``cats``: ``{label: score}``
+    document categories."""
 
-    __slots__ = ("words", "spaces", "tags", "ents", "heads", "deps", "_attrs", "user_data", "has_ents_annotation")
+    __slots__ = ("words", "spaces", "tags", "ents", "heads", "deps", "_attrs", "user_data", "has_ents_annotation",
+                 "pos", "morphs", "lemmas", "sent_starts", "cats")
 
     def __init__(
         self,
@@ -115,6 +118,11 @@ class Doc:
         heads: Optional[Sequence[int]] = None,
         deps: Optional[Sequence[str]] = None,
         attrs: Optional[np.ndarray] = None,
+        pos: Optional[Sequence[Optional[str]]] = None,
+        morphs: Optional[Sequence[Optional[str]]] = None,
+        lemmas: Optional[Sequence[Optional[str]]] = None,
+        sent_starts: Optional[Sequence[Optional[bool]]] = None,
+        cats: Optional[Dict[str, float]] = None,
     ):
         self.words = list(words)
         self.spaces = list(spaces) if spaces is not None else [True] * len(self.words)
@@ -123,8 +131,38 @@ class Doc:
         self.has_ents_annotation = ents is not None
         self.heads = list(heads) if heads is not None else None
         self.deps = list(deps) if deps is not None else None
+        self.pos = list(pos) if pos is not None else None
+        self.morphs = list(morphs) if morphs is not None else None
+        self.lemmas = list(lemmas) if lemmas is not None else None
+        self.sent_starts = list(sent_starts) if sent_starts is not None else None
+        self.cats = dict(cats) if cats else {}
         self._attrs = attrs
         self.user_data: Dict = {}
+        for name in ("tags", "heads", "deps", "pos", "morphs", "lemmas", "sent_starts"):
+            v = getattr(self, name)
+            if v is not None and len(v) != len(self.words):
+                raise ValueError(f"Doc: {name} has {len(v)} entries for {len(self.words)} tokens")
+
+    def gold_sent_starts(self) -> Optional[List[Optional[bool]]]:
+        """Sentence starts: the explicit annotation, else derived from the dependency tree (first token
+        of every root's subtree), else None."""
+        if self.sent_starts is not None:
+            return self.sent_starts
+        if self.heads is None:
+            return None
+        n = len(self.words)
+        root_of = list(range(n))
+        for i in range(n):
+            j, guard = i, 0
+            while 0 <= self.heads[j] < n and self.heads[j] != j and guard <= n:
+                j, guard = self.heads[j], guard + 1
+            root_of[i] = j
+        seen, out = set(), [False] * n
+        for i in range(n):
+            if root_of[i] not in seen:
+                seen.add(root_of[i])
+                out[i] = True
+        return out
 
     def __len__(self) -> int:
         return len(self.words)
@@ -152,22 +190,31 @@ class Doc:
             d["heads"] = self.heads
         if self.deps is not None:
             d["deps"] = self.deps
+        for name in ("pos", "morphs", "lemmas", "sent_starts"):
+            if getattr(self, name) is not None:
+                d[name] = getattr(self, name)
+        if self.cats:
+            d["cats"] = self.cats
         return d
 
     @classmethod
     def from_dict(cls, d: Dict) -> "Doc":
         words = d.get("words")
+        cats = d.get("cats")
+        if cats is None and isinstance(d.get("label"), str) and "answer" in d:       # Prodigy textcat rows
+            cats = {d["label"]: 1.0 if d.get("answer") == "accept" else 0.0}
         if words is None:
             words, spans = _tokenize_with_offsets(d.get("text", ""))
             ents = None
             if "spans" in d or "entities" in d:
                 ents = _char_spans_to_token_spans(spans, d.get("spans") or d.get("entities") or [])
-            return cls(words, ents=ents)
+            return cls(words, ents=ents, cats=cats)
         ents = d.get("ents")
         return cls(
             words, d.get("spaces"), tags=d.get("tags"),
             ents=[tuple(e) for e in ents] if ents is not None else None,
-            heads=d.get("heads"), deps=d.get("deps"),
+            heads=d.get("heads"), deps=d.get("deps"), pos=d.get("pos"), morphs=d.get("morphs"),
+            lemmas=d.get("lemmas"), sent_starts=d.get("sent_starts"), cats=cats,
         )
 
     def __repr__(self) -> str:

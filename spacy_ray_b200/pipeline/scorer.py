@@ -92,6 +92,81 @@ def score_deps(examples: Iterable) -> Dict[str, Any]:
     return {"dep_uas": unl.fscore, "dep_las": lab.fscore}
 
 
+def score_token_attr(examples: Iterable, attr: str, key: str) -> Dict[str, Any]:
+    """Token accuracy of a per-token string attribute of ``Doc`` (``pos``, ``morphs``, ``lemmas``)."""
+    right = total = 0
+    for eg in examples:
+        gold = getattr(eg.reference, attr)
+        pred = getattr(eg.predicted, attr)
+        if gold is None:
+            continue
+        for i, g in enumerate(gold):
+            if g is None:
+                continue
+            total += 1
+            if pred is not None and i < len(pred) and (pred[i] or "") == (g or ""):
+                right += 1
+    return {key: (right / total) if total else None}
+
+
+def score_sents(examples: Iterable) -> Dict[str, Any]:
+    """Sentence spans (start, end) P/R/F, as spaCy's ``Scorer.score_spans(..., "sents")``."""
+    prf = PRF()
+    seen = False
+
+    def spans(starts):
+        idx = [i for i, v in enumerate(starts) if v] or [0]
+        if idx[0] != 0:
+            idx = [0] + idx
+        return {(a, b) for a, b in zip(idx, idx[1:] + [len(starts)])}
+
+    for eg in examples:
+        gold = eg.reference.gold_sent_starts()
+        if gold is None or any(v is None for v in gold):
+            continue
+        seen = True
+        pred = eg.predicted.sent_starts
+        prf.score_set(spans(pred) if pred is not None else set(), spans(gold))
+    if not seen:
+        return {"sents_p": None, "sents_r": None, "sents_f": None}
+    return {"sents_p": prf.precision, "sents_r": prf.recall, "sents_f": prf.fscore}
+
+
+def score_cats(examples: Iterable, labels: Sequence[str], *, multi_label: bool, threshold: float = 0.5) -> Dict[str, Any]:
+    """Document categories: per-label P/R/F (argmax for exclusive classes, ``threshold`` otherwise), macro and
+    micro averages; ``cats_score`` = macro F (spaCy's default for exclusive classes)."""
+    per = {l: PRF() for l in labels}
+    seen = False
+    for eg in examples:
+        gold = eg.reference.cats
+        if not gold:
+            continue
+        seen = True
+        pred = eg.predicted.cats or {}
+        if multi_label:
+            pos_pred = {l for l in labels if pred.get(l, 0.0) >= threshold}
+        else:
+            pos_pred = {max(labels, key=lambda l: pred.get(l, 0.0))} if pred else set()
+        for l in labels:
+            if l not in gold:
+                continue
+            g, p = gold[l] >= 0.5, l in pos_pred
+            per[l].tp += int(g and p)
+            per[l].fp += int(p and not g)
+            per[l].fn += int(g and not p)
+    if not seen:
+        return {"cats_score": None, "cats_macro_f": None, "cats_micro_f": None, "cats_f_per_type": None}
+    micro = PRF()
+    for v in per.values():
+        micro.tp += v.tp; micro.fp += v.fp; micro.fn += v.fn
+    macro_f = sum(v.fscore for v in per.values()) / max(len(per), 1)
+    return {"cats_score": macro_f, "cats_macro_f": macro_f,
+            "cats_macro_p": sum(v.precision for v in per.values()) / max(len(per), 1),
+            "cats_macro_r": sum(v.recall for v in per.values()) / max(len(per), 1),
+            "cats_micro_p": micro.precision, "cats_micro_r": micro.recall, "cats_micro_f": micro.fscore,
+            "cats_f_per_type": {k: v.to_dict() for k, v in per.items()}}
+
+
 def weighted_score(scores: Dict[str, Any], weights: Dict[str, Any]) -> float:
     """Main score = sum_k w_k * scores[k] (missing / None scores count as 0),
     the same combination ``create_evaluation_callback`` uses upstream."""

@@ -118,9 +118,18 @@ class DocBin:
         strs("ORTH", doc.words)
         if doc.tags is not None:
             strs("TAG", doc.tags)
+        if doc.pos is not None:
+            strs("POS", doc.pos)
+        if doc.morphs is not None:
+            strs("MORPH", doc.morphs)
+        if doc.lemmas is not None:
+            strs("LEMMA", doc.lemmas)
         if doc.heads is not None:
             put("HEAD", [(h - i) if (h is not None and h >= 0) else 0 for i, h in enumerate(doc.heads)])
             strs("DEP", doc.deps if doc.deps is not None else [None] * n)
+        if doc.sent_starts is not None:
+            put("SENT_START", [0 if v is None else (1 if v else -1) for v in doc.sent_starts])
+        elif doc.heads is not None:
             # one sentence per doc unless the tree has several roots
             roots = [i for i, h in enumerate(doc.heads) if h == i]
             starts = set(_sentence_starts(doc.heads)) if len(roots) > 1 else {0}
@@ -136,7 +145,7 @@ class DocBin:
             strs("ENT_TYPE", etype)
         self.tokens.append(arr)
         self.spaces.append(np.asarray(doc.spaces, dtype=bool).reshape(n, 1))
-        self.cats.append({})
+        self.cats.append({str(k): float(v) for k, v in (doc.cats or {}).items()})
         self.flags.append({"has_unknown_spaces": False})
 
     def to_bytes(self) -> bytes:
@@ -220,7 +229,8 @@ class DocBin:
                     out.append(s)
             return out
 
-        for arr, sp in zip(self.tokens, self.spaces):
+        cats_list = list(self.cats) + [{}] * (len(self.tokens) - len(self.cats))
+        for arr, sp, cats in zip(self.tokens, self.spaces, cats_list):
             n = len(arr)
             words = strings_of(column(arr, "ORTH"), "ORTH")
             if any(w is None for w in words):
@@ -246,7 +256,17 @@ class DocBin:
                         start = None
                     if t < n and tag == 3 or (t < n and tag == 1 and start is None and et[t]):
                         start = t
-            yield Doc(words, [bool(x) for x in sp.reshape(-1).tolist()], tags=tag_s, ents=ents, heads=heads, deps=deps)
+            def opt_strings(name):
+                vals = column(arr, name)
+                return strings_of(vals, name) if vals is not None and any(vals) else None
+
+            ss = column(arr, "SENT_START")
+            sent_starts = None
+            if ss is not None and any(ss):
+                sent_starts = [None if _i64(v) == 0 else (_i64(v) > 0) for v in ss]
+            yield Doc(words, [bool(x) for x in sp.reshape(-1).tolist()], tags=tag_s, ents=ents, heads=heads, deps=deps,
+                      pos=opt_strings("POS"), morphs=opt_strings("MORPH"), lemmas=opt_strings("LEMMA"),
+                      sent_starts=sent_starts, cats=cats or None)
 
 
 def _sentence_starts(heads: Sequence[int]) -> List[int]:
@@ -341,10 +361,15 @@ def read_conllu(src: Union[str, Path], *, n_sents: int = 1, tag_column: str = "x
     docs = []
     for i in range(0, len(sents), max(1, n_sents)):
         words, spaces, tags, heads, deps, ner = [], [], [], [], [], []
+        pos, morphs, lemmas, starts = [], [], [], []
         any_ner = False
         for sent in sents[i:i + max(1, n_sents)]:
             base = len(words)
             for parts in sent:
+                pos.append(parts[3] if parts[3] != "_" else None)
+                morphs.append(parts[5] if parts[5] != "_" else "")
+                lemmas.append(parts[2] if parts[2] != "_" else None)
+                starts.append(len(words) == base)
                 tid = int(parts[0]) - 1
                 head = int(parts[6]) if parts[6].isdigit() else 0
                 misc = parts[9] if len(parts) > 9 else "_"
@@ -362,7 +387,9 @@ def read_conllu(src: Union[str, Path], *, n_sents: int = 1, tag_column: str = "x
                 ner.append(t)
         if words:
             docs.append(Doc(words, spaces, tags=tags, heads=heads, deps=deps,
-                            ents=_biluo_or_iob_to_spans(ner) if any_ner else None))
+                            ents=_biluo_or_iob_to_spans(ner) if any_ner else None,
+                            pos=pos if any(pos) else None, morphs=morphs if any(pos) else None,
+                            lemmas=lemmas if any(lemmas) else None, sent_starts=starts))
     return docs
 
 

@@ -1,0 +1,252 @@
+"""``senter`` and ``morphologizer`` (token taggers with their own gold / annotation) and the Doc / DocBin
+fields behind them (pos, morphs, lemmas, sent_starts, cats)."""
+import random
+
+import pytest
+
+from spacy_ray_b200.config import Config
+from spacy_ray_b200.pipeline.doc import Doc, Example
+
+CFG = """
+[nlp]
+lang = "en"
+pipeline = ["tok2vec", "senter", "morphologizer"]
+
+[components]
+
+[components.tok2vec]
+factory = "tok2vec"
+
+[components.tok2vec.model]
+@architectures = "spacy.HashEmbedCNN.v2"
+width = 32
+depth = 2
+embed_size = 300
+window_size = 1
+maxout_pieces = 3
+subword_features = true
+pretrained_vectors = null
+
+[components.senter]
+factory = "senter"
+
+[components.senter.model]
+@architectures = "spacy.Tagger.v2"
+
+[components.senter.model.tok2vec]
+@architectures = "spacy.Tok2VecListener.v1"
+width = 32
+upstream = "*"
+
+[components.morphologizer]
+factory = "morphologizer"
+
+[components.morphologizer.model]
+@architectures = "spacy.Tagger.v2"
+
+[components.morphologizer.model.tok2vec]
+@architectures = "spacy.Tok2VecListener.v1"
+width = 32
+upstream = "*"
+
+[corpora]
+
+[corpora.train]
+@readers = "spacy_ray_b200.SyntheticCorpus.v1"
+n_docs = 4
+
+[corpora.dev]
+@readers = "spacy_ray_b200.SyntheticCorpus.v1"
+n_docs = 4
+
+[training]
+max_steps = 1
+"""
+
+NOUNS = ["cat", "dog", "tree", "house", "river", "stone"]
+VERBS = ["sees", "likes", "finds", "paints"]
+DETS = ["the", "a"]
+
+
+def _sentence(rng):
+    words, pos, morphs = [], [], []
+    for role in ("subj", "obj"):
+        plural = rng.random() < 0.4
+        noun = rng.choice(NOUNS) + ("s" if plural else "")
+        if role == "subj":
+            words.append(rng.choice(DETS).capitalize())
+        else:
+            words.append(rng.choice(VERBS))
+            pos.append("VERB")
+            morphs.append("Tense=Pres")
+            words.append(rng.choice(DETS))
+        pos.append("DET")
+        morphs.append("")
+        words.append(noun)
+        pos.append("NOUN")
+        morphs.append("Number=Plur" if plural else "Number=Sing")
+    words.append(".")
+    pos.append("PUNCT")
+    morphs.append("")
+    return words, pos, morphs
+
+
+def _docs(n, seed):
+    rng = random.Random(seed)
+    docs = []
+    for _ in range(n):
+        words, pos, morphs, starts = [], [], [], []
+        for _s in range(rng.randint(1, 3)):
+            w, p, m = _sentence(rng)
+            starts += [True] + [False] * (len(w) - 1)
+            words += w
+            pos += p
+            morphs += m
+        docs.append(Doc(words, pos=pos, morphs=morphs, sent_starts=starts))
+    return docs
+
+
+def test_senter_and_morphologizer_learn_on_a_toy_grammar(tmp_path):
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline.language import Language
+
+    fix_random_seed(0)
+    nlp = Language.from_config(Config().from_str(CFG, interpolate=False))
+    train = [Example.from_doc(d) for d in _docs(200, 0)]
+    dev = [Example.from_doc(d) for d in _docs(40, 1)]
+    nlp.initialize(lambda: train)
+    morph = nlp.get_pipe("morphologizer")
+    assert "Number=Plur|POS=NOUN" in morph.labels and "POS=DET" in morph.labels and "POS=PUNCT" in morph.labels
+    assert nlp.get_pipe("senter").labels == ["I", "S"]
+    opt = nlp.create_optimizer()
+    first = last = None
+    for step in range(60):
+        losses = {}
+        lo = (step * 16) % (len(train) - 16)
+        nlp.update(train[lo:lo + 16], drop=0.0, sgd=opt, losses=losses)
+        if step == 0:
+            first = dict(losses)
+        last = dict(losses)
+    assert float(last["senter"]) < 0.5 * float(first["senter"])
+    assert float(last["morphologizer"]) < 0.5 * float(first["morphologizer"])
+    scores = nlp.evaluate(dev)
+    assert scores["sents_f"] > 0.9 and scores["pos_acc"] > 0.9 and scores["morph_acc"] > 0.8, scores
+    doc = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
+    assert doc.sent_starts[0] is True and len(doc.pos) == len(doc) and len(doc.morphs) == len(doc)
+    # checkpoint round trip keeps labels and predictions
+    from spacy_ray_b200.pipeline import load
+
+    nlp.to_disk(tmp_path / "m")
+    nlp2 = load(tmp_path / "m")
+    doc2 = next(iter(nlp2.pipe([dev[0].reference.copy_unannotated()])))
+    assert (doc2.pos, doc2.morphs, doc2.sent_starts) == (doc.pos, doc.morphs, doc.sent_starts)
+
+
+def test_senter_gold_falls_back_to_the_dependency_roots():
+    d = Doc(["a", "b", "c", "d"], heads=[1, 1, 3, 3], deps=["x", "ROOT", "x", "ROOT"])
+    assert d.gold_sent_starts() == [True, False, True, False]
+    assert Doc(["a"]).gold_sent_starts() is None
+    with pytest.raises(ValueError):
+        Doc(["a", "b"], pos=["X"])
+
+
+def test_docbin_round_trips_the_new_fields(tmp_path):
+    from spacy_ray_b200.training.docbin import DocBin
+
+    d = Doc(["Cats", "sleep", "."], pos=["NOUN", "VERB", "PUNCT"], morphs=["Number=Plur", "Tense=Pres", ""],
+            lemmas=["cat", "sleep", "."], sent_starts=[True, False, False], cats={"POSITIVE": 1.0, "NEGATIVE": 0.0})
+    db = DocBin(docs=[d, Doc(["x"])])
+    db.to_disk(tmp_path / "c.spacy")
+    a, b = list(DocBin().from_disk(tmp_path / "c.spacy").get_docs())
+    assert a.pos == d.pos and a.lemmas == d.lemmas and a.sent_starts == d.sent_starts and a.cats == d.cats
+    assert a.morphs == ["Number=Plur", "Tense=Pres", None]
+    assert b.pos is None and b.cats == {} and b.sent_starts is None
+    assert Doc.from_dict(d.to_dict()).to_dict() == d.to_dict()
+
+
+TEXTCAT_CFG = """
+[nlp]
+lang = "en"
+pipeline = ["{factory}"]
+
+[components]
+
+[components.{factory}]
+factory = "{factory}"
+threshold = 0.5
+
+[components.{factory}.model]
+@architectures = "spacy.TextCatCNN.v2"
+exclusive_classes = {exclusive}
+{extra}
+
+[components.{factory}.model.tok2vec]
+@architectures = "spacy.HashEmbedCNN.v2"
+width = 32
+depth = 1
+embed_size = 300
+window_size = 1
+maxout_pieces = 3
+subword_features = true
+pretrained_vectors = null
+"""
+
+GOOD = ["great", "lovely", "superb", "fine"]
+BAD = ["awful", "dreadful", "poor", "bad"]
+FILL = ["the", "film", "was", "really", "and", "plot", "acting", "music"]
+
+
+def _review(rng, multilabel):
+    pos = rng.random() < 0.5
+    words = [rng.choice(FILL) for _ in range(rng.randint(3, 8))]
+    words.insert(rng.randrange(len(words) + 1), rng.choice(GOOD if pos else BAD))
+    long = len(words) >= 7
+    if multilabel:
+        cats = {"POSITIVE": float(pos), "LONG": float(long)}
+    else:
+        cats = {"POSITIVE": float(pos), "NEGATIVE": float(not pos)}
+    return Doc(words, cats=cats)
+
+
+@pytest.mark.parametrize("factory,exclusive,extra", [("textcat", "true", ""),
+                                                     ("textcat_multilabel", "false", "use_reduce_max = true")])
+def test_textcat_learns(factory, exclusive, extra, tmp_path):
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline import load
+    from spacy_ray_b200.pipeline.language import Language
+
+    fix_random_seed(0)
+    cfg = TEXTCAT_CFG.format(factory=factory, exclusive=exclusive, extra=extra)
+    nlp = Language.from_config(Config().from_str(cfg, interpolate=False))
+    rng = random.Random(3)
+    train = [Example.from_doc(_review(rng, factory != "textcat")) for _ in range(300)]
+    dev = [Example.from_doc(_review(rng, factory != "textcat")) for _ in range(60)]
+    nlp.initialize(lambda: train)
+    pipe = nlp.get_pipe(factory)
+    assert pipe.labels == sorted(train[0].reference.cats)
+    opt = nlp.create_optimizer()
+    hist = []
+    for step in range(80 if factory == "textcat" else 160):
+        losses = {}
+        lo = (step * 16) % (len(train) - 16)
+        nlp.update(train[lo:lo + 16], drop=0.0, sgd=opt, losses=losses)
+        hist.append(float(losses[factory]))
+    assert sum(hist[-5:]) < 0.5 * sum(hist[:5]), hist
+    scores = nlp.evaluate(dev)
+    assert scores["cats_score"] > (0.9 if factory == "textcat" else 0.85), scores
+    doc = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
+    assert set(doc.cats) == set(pipe.labels) and all(0.0 <= v <= 1.0 for v in doc.cats.values())
+    if factory == "textcat":
+        assert abs(sum(doc.cats.values()) - 1.0) < 1e-3
+    nlp.to_disk(tmp_path / "m")
+    doc2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
+    assert doc2.cats == pytest.approx(doc.cats)
+
+
+def test_textcat_rejects_a_model_of_the_other_kind():
+    from spacy_ray_b200.pipeline.language import Language
+
+    cfg = TEXTCAT_CFG.format(factory="textcat", exclusive="false", extra="")
+    nlp = Language.from_config(Config().from_str(cfg, interpolate=False))
+    with pytest.raises(ValueError):
+        nlp.initialize(lambda: [Example.from_doc(Doc(["a"], cats={"A": 1.0, "B": 0.0}))])

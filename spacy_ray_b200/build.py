@@ -91,6 +91,9 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
         objs.append(obj)
         jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", abi, *torch_inc, f"-I{cuda_home / 'include'}",
                      "-DTORCH_EXTENSION_NAME=_srb_cuda", "-c", str(CSRC / f), "-o", str(obj)])
+    for old in OBJ_DIR.glob("*.o"):                     # objects of sources that no longer exist
+        if old not in objs:
+            old.unlink()
     with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         list(ex.map(_run, jobs))
     torch_lib = Path(torch.__file__).parent / "lib"

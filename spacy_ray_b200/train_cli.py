@@ -63,6 +63,12 @@ def build_parser() -> argparse.ArgumentParser:
     _add_train_args(train)
     plain = sub.add_parser("train", help="Single-process training (no workers).")
     _add_train_args(plain)
+    ev = sub.add_parser("evaluate", help="Score a saved pipeline (model-best / model-last) on a corpus, like `spacy evaluate`.")
+    ev.add_argument("model", type=Path, help="directory written by --output (model-best / model-last)")
+    ev.add_argument("data_path", type=Path, help=".spacy (DocBin) or .jsonl corpus with gold annotations")
+    ev.add_argument("--output", "-o", type=Path, default=None, help="write the scores as JSON")
+    ev.add_argument("--gpu-id", "-g", dest="use_gpu", type=int, default=-1)
+    ev.add_argument("--batch-size", type=int, default=256)
     conv = sub.add_parser("convert", help="Convert a JSONL / CoNLL-U / IOB corpus to a DocBin (.spacy) file, like `spacy convert`.")
     conv.add_argument("input_path", type=Path)
     conv.add_argument("output_path", type=Path, help="output file (.spacy) or directory")
@@ -104,6 +110,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     if args.group is None or (args.group == "ray" and args.command is None):
         parser.print_help()
         return 1
+    if args.group == "evaluate":
+        return evaluate_cli(args)
     if args.group == "convert":
         from .training.docbin import convert
 
@@ -120,6 +128,36 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     except ConfigValidationError as e:
         print(f"\n✘ Config validation error ({args.config_path})\n{e}", file=sys.stderr)
         return 1
+    return 0
+
+
+def evaluate_cli(args: argparse.Namespace) -> int:
+    """``spacy evaluate``: load a saved pipeline, annotate the corpus, print the components' scores."""
+    import json
+
+    from .pipeline import load
+    from .training.corpus import JsonlCorpus
+
+    if not args.model.exists():
+        print(f"\u2718 Model directory not found: {args.model}", file=sys.stderr)
+        return 1
+    if not args.data_path.exists():
+        print(f"\u2718 Evaluation data not found: {args.data_path}", file=sys.stderr)
+        return 1
+    setup_gpu(args.use_gpu)
+    nlp = load(args.model)
+    examples = list(JsonlCorpus(str(args.data_path))(nlp))
+    scores = nlp.evaluate(examples, batch_size=args.batch_size)
+    flat = {k: v for k, v in scores.items() if isinstance(v, (int, float)) and v is not None}
+    width = max((len(k) for k in flat), default=5)
+    print(f"\n================== Results ({len(examples)} docs) ==================\n")
+    for k, v in flat.items():
+        shown = f"{v:.0f}" if k == "speed" else f"{100 * v:.2f}"
+        print(f"{k.upper():<{width}}   {shown}")
+    if args.output is not None:
+        args.output.parent.mkdir(parents=True, exist_ok=True)
+        args.output.write_text(json.dumps(scores, indent=2, default=str))
+        print(f"\n\u2714 Saved results to {args.output}")
     return 0
 
 

@@ -73,3 +73,28 @@ def test_stock_spacy_generated_config_runs_unchanged(tmp_path):
         cwd=ROOT, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "LOSS TOK2VEC" in r.stdout and "LOSS NER" in r.stdout and "ENTS_F" in r.stdout
+
+
+def test_evaluate_subcommand_scores_a_saved_pipeline(tmp_path, capsys):
+    import json
+
+    from spacy_ray_b200.config import Config, resolve_dot_names
+    from spacy_ray_b200.train_cli import main
+    from spacy_ray_b200.training import init_nlp
+    from spacy_ray_b200.training.docbin import DocBin
+
+    cfg = ROOT / "configs" / "tagger_w96.cfg"
+    out = tmp_path / "out"
+    small = ["--training.max_steps", "6", "--training.eval_frequency", "3", "--corpora.train.n_docs", "60",
+             "--corpora.dev.n_docs", "20"]
+    assert main(["ray", "train", str(cfg), "-w", "1", "-o", str(out), *small]) == 0
+    nlp = init_nlp(Config().from_disk(cfg, overrides={"corpora.train.n_docs": 60, "corpora.dev.n_docs": 20}))
+    (dev,) = resolve_dot_names(nlp.config.interpolate(), ["corpora.dev"])
+    DocBin(docs=[eg.reference for eg in dev(nlp)]).to_disk(tmp_path / "dev.spacy")
+    capsys.readouterr()
+    assert main(["evaluate", str(out / "model-best"), str(tmp_path / "dev.spacy"), "-o", str(tmp_path / "s.json")]) == 0
+    shown = capsys.readouterr().out
+    assert "TAG_ACC" in shown and "SPEED" in shown
+    scores = json.loads((tmp_path / "s.json").read_text())
+    assert 0.0 <= scores["tag_acc"] <= 1.0
+    assert main(["evaluate", str(tmp_path / "nope"), str(tmp_path / "dev.spacy")]) == 1

@@ -1,5 +1,5 @@
-"""A small single-node actor runtime with Ray's surface (``init``, ``remote``,
-``get``, ``shutdown``, handles with ``.method.remote(...)``).
+"""A small actor runtime with Ray's surface (``init``, ``remote``, ``get``, ``shutdown``, handles with
+``.method.remote(...)``): one node here, more nodes over TCP through ``cluster.py``.
 
 The reference's only inter-process transport is Ray actor RPC;
 ``ray>=0.8,<1.0`` cannot be installed here, and on one 8xB200 box the data
@@ -73,6 +73,7 @@ class _Runtime:
         self.mailbox_thread: Optional[int] = None
         self.extra_env = dict(extra_env or {})
         self.alive = True
+        self.cluster: Any = None       # cluster.Head in the driver of a multi-node run
 
     # -- sending ------------------------------------------------------------
     def send_call(self, target: int, method: str, args, kwargs, want_reply: bool) -> Optional[ObjectRef]:
@@ -151,18 +152,25 @@ def is_initialized() -> bool:
 
 
 def init(address: Optional[str] = None, ignore_reinit_error: bool = True, **kwargs) -> None:
-    """Start the runtime in the driver.  ``address`` is accepted for CLI
-    compatibility (``--address``); joining a remote cluster is not supported -
-    this runtime is single-node by design."""
+    """Start the runtime in the driver.  Without ``address`` (or ``auto`` / ``local``): single node.  With
+    ``address="HOST:PORT"`` and ``nodes=N`` the driver becomes the head of an N-node cluster: it listens there
+    and waits for N-1 agents (``python -m spacy_ray_b200 ray node --address HOST:PORT``), see ``cluster.py``."""
     global _rt
     if _rt is not None:
         if ignore_reinit_error:
             return
         raise RuntimeError("actor runtime already initialised")
-    if address not in (None, "", "auto", "local"):
-        raise NotImplementedError(
-            f"--address {address!r}: multi-node clusters are not supported by the built-in actor runtime"
-        )
+    nodes = int(kwargs.get("nodes") or os.environ.get("SRB_NODES", "1") or 1)
+    if address not in (None, "", "auto", "local") and nodes > 1:
+        from . import cluster
+
+        head = cluster.Head(address, nodes, _POOL_SIZE, _CTX, accept_timeout=float(kwargs.get("accept_timeout", 300.0)))
+        _rt = _Runtime(head.pool, 0, extra_env=kwargs.get("env"))
+        _rt.cluster = head
+        return
+    if address not in (None, "", "auto", "local") and nodes <= 1:
+        # Ray semantics would be "join the cluster at ADDRESS"; with one node there is nothing to join
+        pass
     pool = [_CTX.Queue() for _ in range(_POOL_SIZE)]
     _rt = _Runtime(pool, 0, extra_env=kwargs.get("env"))
 
@@ -183,6 +191,8 @@ def shutdown() -> None:
         if proc.is_alive():
             proc.terminate()
             proc.join(timeout=2)
+    if rt.cluster is not None:
+        rt.cluster.shutdown()
     _rt = None
 
 
@@ -246,16 +256,26 @@ class _RemoteClass:
         rt = _require_rt()
         if rt.my_index != 0:
             raise RuntimeError("actors can only be created from the driver process")
-        index = rt.next_actor
-        if index >= len(rt.pool):
-            raise RuntimeError(f"actor pool exhausted ({len(rt.pool) - 1} actors)")
-        rt.next_actor += 1
+        head = rt.cluster
+        want_gpu = int(self._options.get("num_gpus", 0) or 0) > 0
+        if head is not None:
+            node = head.place(int(want_gpu))
+            index = head.new_index(node)
+        else:
+            node = 0
+            index = rt.next_actor
+            if index >= len(rt.pool):
+                raise RuntimeError(f"actor pool exhausted ({len(rt.pool) - 1} actors)")
+            rt.next_actor += 1
         env = dict(rt.extra_env)
-        if int(self._options.get("num_gpus", 0) or 0) > 0:
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if want_gpu:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES") if node == 0 else None
             devices = visible.split(",") if visible else None
-            gpu = rt.gpu_cursor
-            rt.gpu_cursor += 1
+            if head is not None:
+                gpu = head.next_gpu(node)
+            else:
+                gpu = rt.gpu_cursor
+                rt.gpu_cursor += 1
             if self._options.get("isolate_gpu", False):
                 # Ray-style isolation: the actor sees exactly one device (index 0)
                 env["CUDA_VISIBLE_DEVICES"] = devices[gpu % len(devices)] if devices else str(gpu)
@@ -264,10 +284,11 @@ class _RemoteClass:
                 # rank to address a *distinct* device ordinal); the actor is told which one is its own.
                 env["SRB_ASSIGNED_GPU"] = str(gpu % len(devices) if devices else gpu)
         payload = pickle.dumps((self._cls, args, kwargs))
-        proc = _CTX.Process(
-            target=_actor_main, args=(rt.pool, index, payload, env), daemon=True,
-            name=f"srb-actor-{self._cls.__name__}-{index}",
-        )
+        name = f"srb-actor-{self._cls.__name__}-{index}"
+        if node != 0:
+            rt.procs[index] = head.spawn_remote(node, index, payload, env, name)
+            return ActorHandle(index, self._cls.__name__)
+        proc = _CTX.Process(target=_actor_main, args=(rt.pool, index, payload, env), daemon=True, name=name)
         proc.start()
         rt.procs[index] = proc
         return ActorHandle(index, self._cls.__name__)

@@ -61,6 +61,9 @@ def build_parser() -> argparse.ArgumentParser:
     ray_sub = ray.add_subparsers(dest="command")
     train = ray_sub.add_parser("train", help="Train a pipeline in parallel.")
     _add_train_args(train)
+    node = ray_sub.add_parser("node", help="Join a multi-node run as a node agent (the driver's --address is the head).")
+    node.add_argument("--address", "-a", required=True, help="HOST:PORT the driver listens on (its --address)")
+    node.add_argument("--num-gpus", type=int, default=None, help="GPUs this node offers (informational)")
     plain = sub.add_parser("train", help="Single-process training (no workers).")
     _add_train_args(plain)
     ev = sub.add_parser("evaluate", help="Score a saved pipeline (model-best / model-last) on a corpus, like `spacy evaluate`.")
@@ -87,7 +90,10 @@ def _add_train_args(p: argparse.ArgumentParser) -> None:
     p.add_argument("--output", "--output-path", "-o", dest="output_path", type=Path, default=None,
                    help="Output directory for the trained pipeline (model-best / model-last)")
     p.add_argument("--n-workers", "-w", dest="num_workers", type=int, default=1, help="Number of workers")
-    p.add_argument("--address", "-a", dest="ray_address", default=None, help="Address of cluster (single node only)")
+    p.add_argument("--address", "-a", dest="ray_address", default=None,
+                   help="HOST:PORT this driver listens on as the head of a multi-node run (with --nodes > 1)")
+    p.add_argument("--nodes", type=int, default=1,
+                   help="machines in the run: the driver's plus N-1 started with `ray node --address HOST:PORT`")
     p.add_argument("--gpu-id", "-g", dest="use_gpu", type=int, default=-1, help="GPU ID or -1 for CPU")
     p.add_argument("--verbose", "-V", "-VV", dest="verbose", action="store_true", help="Debug logging")
     p.add_argument("--mode", choices=["sync", "async"], default="sync",
@@ -110,6 +116,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     if args.group is None or (args.group == "ray" and args.command is None):
         parser.print_help()
         return 1
+    if args.group == "ray" and args.command == "node":
+        from .parallel.cluster import agent_main
+
+        return agent_main(args.address, args.num_gpus)
     if args.group == "evaluate":
         return evaluate_cli(args)
     if args.group == "convert":
@@ -180,6 +190,7 @@ def ray_train_cli(args: argparse.Namespace, extra: Sequence[str]) -> None:
         quorum=args.quorum,
         shard_balance=args.shard_balance,
         grad_transport=args.grad_transport,
+        nodes=getattr(args, "nodes", 1),
         resume_path=args.resume_path,
         shard_data=args.shard_data,
         inject_fault=args.inject_fault,
@@ -199,6 +210,7 @@ def ray_train(
     quorum: Optional[int] = None,
     shard_balance: str = "auto",
     grad_transport: str = "fp32",
+    nodes: int = 1,
     resume_path: Optional[Path] = None,
     shard_data: bool = True,
     inject_fault: Optional[str] = None,
@@ -208,11 +220,27 @@ def ray_train(
     """Driver: same sequence as the reference (``train_cli.py:66-91``)."""
     if ray is None:
         from .parallel import actors as ray
+    master_addr = "127.0.0.1"
     if ray_address is not None:
-        ray.init(address=ray_address)
+        if nodes > 1:
+            # this driver is the head: node agents connect to ray_address, torch.distributed meets there too;
+            # the peer-memory exchange cannot span machines, so "auto" means the library collectives
+            ray.init(address=ray_address, nodes=nodes)
+            host = ray_address.rpartition(":")[0]
+            if host in ("", "*", "0.0.0.0"):
+                import socket
+
+                host = socket.gethostbyname(socket.gethostname())
+            master_addr = host
+            if comm == "auto":
+                comm = "dist"
+            elif comm == "fused":
+                raise ValueError("--comm fused is single-node (NVLink peer memory); use --comm dist across machines")
+        else:
+            ray.init(address=ray_address)
     else:
         ray.init(ignore_reinit_error=True)
-    dist_init = {"master_addr": "127.0.0.1", "master_port": _free_port()}
+    dist_init = {"master_addr": master_addr, "master_port": _free_port()}
     RemoteWorker = ray.remote(Worker).options(num_gpus=int(use_gpu >= 0), num_cpus=2)
     workers = [
         RemoteWorker.remote(

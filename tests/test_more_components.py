@@ -250,3 +250,106 @@ def test_textcat_rejects_a_model_of_the_other_kind():
     nlp = Language.from_config(Config().from_str(cfg, interpolate=False))
     with pytest.raises(ValueError):
         nlp.initialize(lambda: [Example.from_doc(Doc(["a"], cats={"A": 1.0, "B": 0.0}))])
+
+
+BOW_CFG = """
+[nlp]
+lang = "en"
+pipeline = ["textcat"]
+
+[components]
+
+[components.textcat]
+factory = "textcat"
+
+[components.textcat.model]
+@architectures = "spacy.TextCatBOW.v2"
+exclusive_classes = true
+ngram_size = 2
+no_output_layer = false
+nO = null
+"""
+
+ENSEMBLE_CFG = """
+[nlp]
+lang = "en"
+pipeline = ["textcat"]
+
+[components]
+
+[components.textcat]
+factory = "textcat"
+
+[components.textcat.model]
+@architectures = "spacy.TextCatEnsemble.v2"
+nO = null
+
+[components.textcat.model.linear_model]
+@architectures = "spacy.TextCatBOW.v2"
+exclusive_classes = true
+ngram_size = 1
+no_output_layer = false
+
+[components.textcat.model.tok2vec]
+@architectures = "spacy.Tok2Vec.v2"
+
+[components.textcat.model.tok2vec.embed]
+@architectures = "spacy.MultiHashEmbed.v2"
+width = 32
+rows = [500, 250, 250, 250]
+attrs = ["NORM", "PREFIX", "SUFFIX", "SHAPE"]
+include_static_vectors = false
+
+[components.textcat.model.tok2vec.encode]
+@architectures = "spacy.MaxoutWindowEncoder.v2"
+width = 32
+window_size = 1
+maxout_pieces = 3
+depth = 1
+"""
+
+
+@pytest.mark.parametrize("cfg_text", [BOW_CFG, ENSEMBLE_CFG], ids=["bow", "ensemble"])
+def test_stock_textcat_architectures_train(cfg_text, tmp_path):
+    """The two architectures `spacy init config` writes for textcat (efficiency: TextCatBOW, accuracy:
+    TextCatEnsemble) resolve and learn."""
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline import load
+    from spacy_ray_b200.pipeline.language import Language
+
+    fix_random_seed(0)
+    nlp = Language.from_config(Config().from_str(cfg_text, interpolate=False))
+    rng = random.Random(5)
+    train = [Example.from_doc(_review(rng, False)) for _ in range(300)]
+    dev = [Example.from_doc(_review(rng, False)) for _ in range(60)]
+    nlp.initialize(lambda: train)
+    opt = nlp.create_optimizer()
+    hist = []
+    for step in range(300):                      # the sparse rows see few updates each: slower than the CNN
+        losses = {}
+        lo = (step * 16) % (len(train) - 16)
+        nlp.update(train[lo:lo + 16], drop=0.0, sgd=opt, losses=losses)
+        hist.append(float(losses["textcat"]))
+    assert sum(hist[-5:]) < 0.6 * sum(hist[:5]), (hist[:5], hist[-5:])
+    scores = nlp.evaluate(dev)
+    assert scores["cats_score"] > 0.9, scores
+    nlp.to_disk(tmp_path / "m")
+    d1 = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
+    d2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
+    assert d2.cats == pytest.approx(d1.cats)
+
+
+def test_bow_ngrams_stay_inside_their_doc():
+    import numpy as np
+    import torch
+
+    from spacy_ray_b200.models.textcat import _ngram_features
+    from spacy_ray_b200.pipeline.language import Language
+
+    nlp = Language.from_config(Config().from_str(BOW_CFG, interpolate=False))
+    docs = [Doc(["a", "b", "c"]), Doc(["d"]), Doc(["e", "f"])]
+    batch = nlp.make_batch(docs)
+    f, d = _ngram_features(batch, 2, 1 << 18)
+    counts = np.bincount(d.numpy(), minlength=3).tolist()
+    assert counts == [3 + 2, 1 + 0, 2 + 1]            # unigrams + bigrams per doc, none across a boundary
+    assert int(f.min()) >= 0 and int(f.max()) < (1 << 18)

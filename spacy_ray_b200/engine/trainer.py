@@ -47,7 +47,14 @@ def _align(x: int, a: int = 256) -> int:
 
 
 def _kind(comp) -> Optional[str]:
-    return {"Tok2VecComponent": "tok2vec", "Tagger": "tagger", "EntityRecognizer": "ner",
+    """Which device-side step serves a component.  Every token tagger (``Tagger`` and its subclasses
+    ``SentenceRecognizer`` / ``Morphologizer``: same model, same kernels, only the gold ids differ) is a
+    "tagger"."""
+    from ..pipeline.components import Tagger
+
+    if isinstance(comp, Tagger):
+        return "tagger"
+    return {"Tok2VecComponent": "tok2vec", "EntityRecognizer": "ner",
             "DependencyParser": "parser"}.get(comp.__class__.__name__)
 
 
@@ -86,12 +93,10 @@ class ExampleStore:
                 self.slots[name + ".heads"] = (cat([h for h, _ in g]), self.doc_off, False)
                 self.slots[name + ".labels"] = (cat([l for _, l in g]), self.doc_off, False)
             elif kind == "tagger":
-                index = {l: i for i, l in enumerate(comp.labels)}
                 end = np.array([-1], dtype=np.int32)
                 parts = []
                 for eg in examples:
-                    tags = eg.reference.tags or [None] * len(eg.reference)
-                    parts.append(np.array([index.get(t, -1) if t else -1 for t in tags], dtype=np.int32))
+                    parts.append(comp.gold_ids(eg.reference).astype(np.int32))
                     parts.append(end)
                 self.slots[name] = (cat(parts), self.doc_off_padded, True)
         self.lens = lens

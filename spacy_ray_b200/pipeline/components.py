@@ -206,16 +206,26 @@ class Tagger(TrainablePipe):
         self._after_labels()
         self.model.initialize()
 
-    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
+    def gold_ids(self, ref: Doc) -> np.ndarray:
+        """Per-token gold label ids of one reference doc (int64, -1 = no gold); cached on the doc.  This is
+        the one thing the token-tagging components differ in - the generic update and the device-resident
+        engine (``engine.ExampleStore``) both read it."""
+        key = ("gold_ids", self.name)
+        ids = ref.user_data.get(key)
+        if ids is None:
+            ids = np.asarray(self._compute_gold_ids(ref), dtype=np.int64)
+            ref.user_data[key] = ids
+        return ids
+
+    def _compute_gold_ids(self, ref: Doc):
         index = {l: i for i, l in enumerate(self._labels)}
+        tags = ref.tags or [None] * len(ref)
+        return [index.get(t, -1) if t else -1 for t in tags]
+
+    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
         arr = np.full((batch.n_rows,), -1, dtype=np.int64)
         for eg, s in zip(examples, batch.starts):
-            ref = eg.reference
-            ids = ref.user_data.get(("tag_ids", self.name))
-            if ids is None:
-                tags = ref.tags or [None] * len(ref)
-                ids = np.array([index.get(t, -1) if t else -1 for t in tags], dtype=np.int64)
-                ref.user_data[("tag_ids", self.name)] = ids
+            ids = self.gold_ids(eg.reference)
             arr[s:s + len(ids)] = ids
         from ..nn.batch import to_device
 
@@ -258,22 +268,11 @@ class SentenceRecognizer(Tagger):
         self._after_labels()
         self.model.initialize()
 
-    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
-        arr = np.full((batch.n_rows,), -1, dtype=np.int64)
-        for eg, s in zip(examples, batch.starts):
-            ref = eg.reference
-            ids = ref.user_data.get(("senter_ids", self.name))
-            if ids is None:
-                starts = ref.gold_sent_starts()
-                if starts is None:
-                    ids = np.full((len(ref),), -1, dtype=np.int64)
-                else:
-                    ids = np.array([-1 if v is None else int(bool(v)) for v in starts], dtype=np.int64)
-                ref.user_data[("senter_ids", self.name)] = ids
-            arr[s:s + len(ids)] = ids
-        from ..nn.batch import to_device
-
-        return to_device(arr, batch.device)
+    def _compute_gold_ids(self, ref: Doc):
+        starts = ref.gold_sent_starts()
+        if starts is None:
+            return [-1] * len(ref)
+        return [-1 if v is None else int(bool(v)) for v in starts]
 
     def set_annotations(self, docs, preds) -> None:
         host = preds.to("cpu").tolist()
@@ -331,19 +330,9 @@ class Morphologizer(Tagger):
         self._after_labels()
         self.model.initialize()
 
-    def _gold_labels(self, examples, batch: TokenBatch) -> torch.Tensor:
+    def _compute_gold_ids(self, ref: Doc):
         index = {l: i for i, l in enumerate(self._labels)}
-        arr = np.full((batch.n_rows,), -1, dtype=np.int64)
-        for eg, s in zip(examples, batch.starts):
-            ref = eg.reference
-            ids = ref.user_data.get(("morph_ids", self.name))
-            if ids is None:
-                ids = np.array([index.get(l, -1) if l else -1 for l in self._ref_labels(ref)], dtype=np.int64)
-                ref.user_data[("morph_ids", self.name)] = ids
-            arr[s:s + len(ids)] = ids
-        from ..nn.batch import to_device
-
-        return to_device(arr, batch.device)
+        return [index.get(l, -1) if l else -1 for l in self._ref_labels(ref)]
 
     def set_annotations(self, docs, preds) -> None:
         host = preds.to("cpu").tolist()

@@ -353,3 +353,34 @@ def test_bow_ngrams_stay_inside_their_doc():
     counts = np.bincount(d.numpy(), minlength=3).tolist()
     assert counts == [3 + 2, 1 + 0, 2 + 1]            # unigrams + bigrams per doc, none across a boundary
     assert int(f.min()) >= 0 and int(f.max()) < (1 << 18)
+
+
+def test_engine_staging_serves_the_tagger_subclasses():
+    """``engine.Trainer`` treats every token tagger as a "tagger": the packed staging buffer must carry exactly
+    the gold ids the generic update would use for senter / morphologizer (host side only; no GPU needed)."""
+    import numpy as np
+
+    from spacy_ray_b200.engine.trainer import ExampleStore, Trainer, _kind, _Layout, fill_stage, make_stage
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline.language import Language
+
+    fix_random_seed(0)
+    nlp = Language.from_config(Config().from_str(CFG, interpolate=False))
+    examples = [Example.from_doc(d) for d in _docs(40, 2)]
+    nlp.initialize(lambda: examples)
+    heads = [(n, c, _kind(c)) for n, c in nlp.pipeline if getattr(c, "is_trainable", False)]
+    assert [k for _, _, k in heads] == ["tok2vec", "tagger", "tagger"]
+    assert Trainer.unsupported_reason(nlp) in (None, "") or "CUDA" in str(Trainer.unsupported_reason(nlp))
+    store = ExampleStore(examples, heads)
+    lay = _Layout(rows=512, docs=8, lmax=64, slots=tuple(store.slots))
+    stage = make_stage(lay, store, pin=False)
+    ids = np.array([1, 5, 8, 13, 21, 30, 33, 39])
+    fill_stage(store, lay, stage, ids)
+    chosen = [examples[i] for i in ids]
+    batch = nlp.make_batch([eg.predicted for eg in chosen])
+    rows = stage["rows"]
+    assert rows == batch.n_rows
+    for name in ("senter", "morphologizer"):
+        want = nlp.get_pipe(name)._gold_labels(chosen, batch).numpy()
+        np.testing.assert_array_equal(stage["np"]["gold"][name][:rows], want)
+        assert (want >= 0).sum() == sum(len(eg) for eg in chosen)

@@ -351,6 +351,78 @@ class Morphologizer(Tagger):
 
 
 # ============================================================================
+class TrainableLemmatizer(Tagger):
+    """``trainable_lemmatizer``: lemmatisation as token classification over EDIT RULES learned from the
+    training data (upstream's ``EditTreeLemmatizer`` classifies over edit trees with the same ``spacy.Tagger``
+    model; the rule here is the suffix form of such a tree): a rule ``(case, k, suffix)`` lower-cases the form if
+    ``case`` says so, strips its last ``k`` characters and appends ``suffix``.  Rules seen fewer than
+    ``min_tree_freq`` times are dropped; tokens whose gold rule is unknown train nothing; with ``backoff =
+    "orth"`` an unknown / inapplicable prediction falls back to the form itself."""
+    default_score_weights = {"lemma_acc": 1.0}
+
+    @staticmethod
+    def rule_of(form: str, lemma: str) -> str:
+        case = "L" if (lemma == lemma.lower() and form != form.lower()) else "K"
+        base = form.lower() if case == "L" else form
+        p = 0
+        while p < len(base) and p < len(lemma) and base[p] == lemma[p]:
+            p += 1
+        return f"{case}|{len(base) - p}|{lemma[p:]}"
+
+    @staticmethod
+    def apply_rule(form: str, rule: str) -> Optional[str]:
+        case, k, suffix = rule.split("|", 2)
+        base = form.lower() if case == "L" else form
+        k = int(k)
+        if k > len(base):
+            return None
+        return base[: len(base) - k] + suffix
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            from collections import Counter
+
+            counts: Counter = Counter()
+            for eg in get_examples():
+                ref = eg.reference
+                for w, lem in zip(ref.words, ref.lemmas or []):
+                    if lem:
+                        counts[self.rule_of(w, lem)] += 1
+            min_freq = int(self.cfg.get("min_tree_freq", 3))
+            for rule, n in sorted(counts.items(), key=lambda kv: (-kv[1], kv[0])):
+                if n >= min_freq:
+                    self.add_label(rule)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no lemma annotation (Doc.lemmas) found in the training data")
+        self._after_labels()
+        self.model.initialize()
+
+    def _compute_gold_ids(self, ref: Doc):
+        index = {l: i for i, l in enumerate(self._labels)}
+        lemmas = ref.lemmas or [None] * len(ref)
+        return [index.get(self.rule_of(w, lem), -1) if lem else -1 for w, lem in zip(ref.words, lemmas)]
+
+    def set_annotations(self, docs, preds) -> None:
+        host = preds.to("cpu").tolist()
+        backoff = self.cfg.get("backoff", "orth")
+        row = 1
+        for doc in docs:
+            n = len(doc)
+            out = []
+            for w, i in zip(doc.words, host[row:row + n]):
+                lem = self.apply_rule(w, self._labels[i])
+                out.append(lem if lem else (w if backoff == "orth" else None))
+            doc.lemmas = out
+            row += n + 1
+
+    def score(self, examples):
+        return S.score_token_attr(examples, "lemmas", "lemma_acc")
+
+
+# ============================================================================
 class EntityRecognizer(TrainablePipe):
     default_score_weights = {"ents_f": 1.0, "ents_p": 0.0, "ents_r": 0.0, "ents_per_type": None}
 
@@ -646,6 +718,11 @@ def make_senter(nlp, name: str, model: Model, **cfg) -> SentenceRecognizer:
     return SentenceRecognizer(name, model, **cfg)
 
 
+@registry.factories("trainable_lemmatizer")
+def make_trainable_lemmatizer(nlp, name: str, model: Model, **cfg) -> TrainableLemmatizer:
+    return TrainableLemmatizer(name, model, **cfg)
+
+
 @registry.factories("morphologizer")
 def make_morphologizer(nlp, name: str, model: Model, **cfg) -> Morphologizer:
     return Morphologizer(name, model, **cfg)
@@ -685,6 +762,11 @@ DEFAULT_MODEL_CONFIGS: Dict[str, Dict[str, Any]] = {
         "@architectures": "spacy.Tagger.v2",
         "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 12, "depth": 1, "embed_size": 2000,
                     "window_size": 1, "maxout_pieces": 2, "subword_features": True, "pretrained_vectors": None},
+    },
+    "trainable_lemmatizer": {
+        "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
     },
     "morphologizer": {
         "@architectures": "spacy.Tagger.v2",

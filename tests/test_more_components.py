@@ -384,3 +384,57 @@ def test_engine_staging_serves_the_tagger_subclasses():
         want = nlp.get_pipe(name)._gold_labels(chosen, batch).numpy()
         np.testing.assert_array_equal(stage["np"]["gold"][name][:rows], want)
         assert (want >= 0).sum() == sum(len(eg) for eg in chosen)
+
+
+def test_trainable_lemmatizer_learns_suffix_rules(tmp_path):
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline import load
+    from spacy_ray_b200.pipeline.components import TrainableLemmatizer as TL
+    from spacy_ray_b200.pipeline.language import Language
+
+    assert TL.rule_of("Cats", "cat") == "L|1|" and TL.apply_rule("Cats", "L|1|") == "cat"
+    assert TL.rule_of("running", "run") == "K|4|" and TL.rule_of("was", "be") == "K|3|be"
+    assert TL.apply_rule("is", "K|3|be") is None and TL.rule_of("Paris", "Paris") == "K|0|"
+    cfg = CFG.replace('pipeline = ["tok2vec", "senter", "morphologizer"]', 'pipeline = ["tok2vec", "trainable_lemmatizer"]')
+    cfg = cfg[: cfg.index("[components.senter]")] + """[components.trainable_lemmatizer]
+factory = "trainable_lemmatizer"
+min_tree_freq = 2
+backoff = "orth"
+
+[components.trainable_lemmatizer.model]
+@architectures = "spacy.Tagger.v2"
+
+[components.trainable_lemmatizer.model.tok2vec]
+@architectures = "spacy.Tok2VecListener.v1"
+width = 32
+upstream = "*"
+""" + cfg[cfg.index("[corpora]"):]
+    fix_random_seed(0)
+    nlp = Language.from_config(Config().from_str(cfg, interpolate=False))
+
+    def lemma(w):
+        lw = w.lower()
+        if lw.endswith("s") and lw[:-1] in NOUNS:
+            return lw[:-1]
+        if lw in VERBS:
+            return lw[:-1]                      # sees -> see, likes -> like ...
+        return lw if lw in DETS else w
+
+    docs = _docs(200, 0) + _docs(40, 1)
+    for d in docs:
+        d.lemmas = [lemma(w) for w in d.words]
+    train = [Example.from_doc(d) for d in docs[:200]]
+    dev = [Example.from_doc(d) for d in docs[200:]]
+    nlp.initialize(lambda: train)
+    pipe = nlp.get_pipe("trainable_lemmatizer")
+    assert "K|1|" in pipe.labels and "K|0|" in pipe.labels and "L|0|" in pipe.labels
+    opt = nlp.create_optimizer()
+    for step in range(60):
+        lo = (step * 16) % (len(train) - 16)
+        nlp.update(train[lo:lo + 16], drop=0.0, sgd=opt, losses={})
+    scores = nlp.evaluate(dev)
+    assert scores["lemma_acc"] > 0.95, scores
+    nlp.to_disk(tmp_path / "m")
+    d1 = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
+    d2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
+    assert d1.lemmas == d2.lemmas and len(d1.lemmas) == len(d1)

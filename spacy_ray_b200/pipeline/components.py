@@ -702,6 +702,87 @@ class MultiLabelTextCategorizer(TextCategorizer):
     multi_label = True
 
 
+# ============================================================================
+class SpanCategorizer(TrainablePipe):
+    """``spancat``: label candidate token spans (overlapping, multi-label) of ``Doc.spans[spans_key]``.
+    Candidates come from the ``suggester`` (default: all 1-3-grams); a candidate's target is 1 for every gold
+    label it carries.  Prediction keeps the labels whose score reaches ``threshold`` (at most ``max_positive``
+    per span)."""
+
+    def __init__(self, name, model, **cfg):
+        super().__init__(name, model, **cfg)
+        self.spans_key = str(cfg.get("spans_key", "sc"))
+        sug = cfg.get("suggester")
+        if sug is None:
+            from ..models.spancat import ngram_suggester
+
+            sug = ngram_suggester([1, 2, 3])
+        self.suggester = sug
+        k = f"spans_{self.spans_key}"
+        self.default_score_weights = {f"{k}_f": 1.0, f"{k}_p": 0.0, f"{k}_r": 0.0}
+
+    def _after_labels(self) -> None:
+        if self.model.has_dim("nO") is None and self._labels:
+            self.model.set_dim("nO", len(self._labels))
+
+    def initialize(self, get_examples, *, nlp=None, labels=None) -> None:
+        if labels is not None:
+            for l in labels:
+                self.add_label(l)
+        else:
+            seen = set()
+            for eg in get_examples():
+                seen.update(l for _s, _e, l in eg.reference.spans.get(self.spans_key, []))
+            for l in sorted(seen):
+                self.add_label(l)
+        if not self._labels:
+            raise ValueError(f"[{self.name}] no spans under Doc.spans[{self.spans_key!r}] in the training data")
+        self._after_labels()
+        self.model.initialize()
+
+    def update(self, examples, *, batch, drop=0.0, sgd=None, losses=None):
+        set_dropout_rate(self.model, drop)
+        cands = self.suggester(batch.lengths)
+        scores, backprop = self.model((batch, cands), True)
+        index = {l: i for i, l in enumerate(self._labels)}
+        target = np.zeros((len(cands), len(self._labels)), dtype=np.float32)
+        where = {c: i for i, c in enumerate(cands)}
+        for d, eg in enumerate(examples):
+            for s_, e_, lab in eg.reference.spans.get(self.spans_key, []):
+                i = where.get((d, s_, e_))
+                if i is not None and lab in index:
+                    target[i, index[lab]] = 1.0
+        diff = scores - torch.from_numpy(target).to(scores.device)
+        backprop(diff / max(len(examples), 1))
+        if sgd not in (None, False):
+            self.finish_update(sgd)
+        _add_loss(losses, self.name, (diff * diff).sum() / max(len(examples), 1))
+        return losses
+
+    def predict(self, docs, batch):
+        cands = self.suggester(batch.lengths)
+        scores = self.model.predict((batch, cands))
+        return cands, scores
+
+    def set_annotations(self, docs, preds) -> None:
+        cands, scores = preds
+        host = scores.to("cpu").numpy() if len(cands) else np.zeros((0, len(self._labels)), dtype=np.float32)
+        thr = float(self.cfg.get("threshold", 0.5))
+        max_pos = self.cfg.get("max_positive")
+        out = [[] for _ in docs]
+        for (d, s_, e_), row in zip(cands, host):
+            keep = [j for j in np.argsort(-row) if row[j] >= thr]
+            if max_pos:
+                keep = keep[: int(max_pos)]
+            for j in keep:
+                out[d].append((int(s_), int(e_), self._labels[j]))
+        for doc, spans in zip(docs, out):
+            doc.spans[self.spans_key] = sorted(spans)
+
+    def score(self, examples):
+        return S.score_spans(examples, self.spans_key)
+
+
 # ---- factories ----------------------------------------------------------------
 @registry.factories("tok2vec")
 def make_tok2vec(nlp, name: str, model: Model) -> Tok2VecComponent:
@@ -726,6 +807,11 @@ def make_trainable_lemmatizer(nlp, name: str, model: Model, **cfg) -> TrainableL
 @registry.factories("morphologizer")
 def make_morphologizer(nlp, name: str, model: Model, **cfg) -> Morphologizer:
     return Morphologizer(name, model, **cfg)
+
+
+@registry.factories("spancat")
+def make_spancat(nlp, name: str, model: Model, **cfg) -> SpanCategorizer:
+    return SpanCategorizer(name, model, **cfg)
 
 
 @registry.factories("textcat")
@@ -770,6 +856,11 @@ DEFAULT_MODEL_CONFIGS: Dict[str, Dict[str, Any]] = {
     },
     "morphologizer": {
         "@architectures": "spacy.Tagger.v2",
+        "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
+                    "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
+    },
+    "spancat": {
+        "@architectures": "spacy.SpanCategorizer.v1", "hidden_size": 128,
         "tok2vec": {"@architectures": "spacy.HashEmbedCNN.v2", "width": 96, "depth": 4, "embed_size": 2000,
                     "window_size": 1, "maxout_pieces": 3, "subword_features": True, "pretrained_vectors": None},
     },

@@ -103,10 +103,10 @@ class Doc:
     (``"Case=Nom|Number=Sing"``) and lemmas; ``ents``: ``(start, end_exclusive, label)`` token spans;
     ``heads``: absolute head index per token (root points at itself); ``deps``: per-token dependency
     label; ``sent_starts``: per-token True / False / None (unknown); ``cats``: ``{label: score}``
-    document categories."""
+    document categories; ``spans``: named groups of labelled, possibly overlapping token spans."""
 
     __slots__ = ("words", "spaces", "tags", "ents", "heads", "deps", "_attrs", "user_data", "has_ents_annotation",
-                 "pos", "morphs", "lemmas", "sent_starts", "cats")
+                 "pos", "morphs", "lemmas", "sent_starts", "cats", "spans")
 
     def __init__(
         self,
@@ -123,6 +123,7 @@ class Doc:
         lemmas: Optional[Sequence[Optional[str]]] = None,
         sent_starts: Optional[Sequence[Optional[bool]]] = None,
         cats: Optional[Dict[str, float]] = None,
+        spans: Optional[Dict[str, Sequence[Tuple[int, int, str]]]] = None,
     ):
         self.words = list(words)
         self.spaces = list(spaces) if spaces is not None else [True] * len(self.words)
@@ -136,6 +137,8 @@ class Doc:
         self.lemmas = list(lemmas) if lemmas is not None else None
         self.sent_starts = list(sent_starts) if sent_starts is not None else None
         self.cats = dict(cats) if cats else {}
+        # named groups of (possibly overlapping) labelled token spans: {"sc": [(start, end_exclusive, label), ...]}
+        self.spans = {str(k): [tuple(x) for x in v] for k, v in (spans or {}).items()}
         self._attrs = attrs
         self.user_data: Dict = {}
         for name in ("tags", "heads", "deps", "pos", "morphs", "lemmas", "sent_starts"):
@@ -195,6 +198,8 @@ class Doc:
                 d[name] = getattr(self, name)
         if self.cats:
             d["cats"] = self.cats
+        if self.spans:
+            d["spans"] = {k: [list(x) for x in v] for k, v in self.spans.items()}
         return d
 
     @classmethod
@@ -214,7 +219,7 @@ class Doc:
             words, d.get("spaces"), tags=d.get("tags"),
             ents=[tuple(e) for e in ents] if ents is not None else None,
             heads=d.get("heads"), deps=d.get("deps"), pos=d.get("pos"), morphs=d.get("morphs"),
-            lemmas=d.get("lemmas"), sent_starts=d.get("sent_starts"), cats=cats,
+            lemmas=d.get("lemmas"), sent_starts=d.get("sent_starts"), cats=cats, spans=d.get("spans"),
         )
 
     def __repr__(self) -> str:

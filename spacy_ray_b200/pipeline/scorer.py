@@ -167,6 +167,22 @@ def score_cats(examples: Iterable, labels: Sequence[str], *, multi_label: bool, 
             "cats_f_per_type": {k: v.to_dict() for k, v in per.items()}}
 
 
+def score_spans(examples: Iterable, spans_key: str) -> Dict[str, Any]:
+    """Labelled span P/R/F of one span group (spaCy's ``spans_{key}_p/r/f``)."""
+    prf = PRF()
+    seen = False
+    for eg in examples:
+        gold = eg.reference.spans.get(spans_key)
+        if gold is None:
+            continue
+        seen = True
+        prf.score_set({tuple(x) for x in eg.predicted.spans.get(spans_key, [])}, {tuple(x) for x in gold})
+    k = f"spans_{spans_key}"
+    if not seen:
+        return {f"{k}_p": None, f"{k}_r": None, f"{k}_f": None}
+    return {f"{k}_p": prf.precision, f"{k}_r": prf.recall, f"{k}_f": prf.fscore}
+
+
 def weighted_score(scores: Dict[str, Any], weights: Dict[str, Any]) -> float:
     """Main score = sum_k w_k * scores[k] (missing / None scores count as 0),
     the same combination ``create_evaluation_callback`` uses upstream."""

@@ -89,6 +89,7 @@ class DocBin:
         self.tokens: List[np.ndarray] = []
         self.spaces: List[np.ndarray] = []
         self.cats: List[dict] = []
+        self.span_groups: List[bytes] = []
         self.flags: List[dict] = []
         self.strings: set = set()
         self.store_user_data = store_user_data
@@ -146,6 +147,7 @@ class DocBin:
         self.tokens.append(arr)
         self.spaces.append(np.asarray(doc.spaces, dtype=bool).reshape(n, 1))
         self.cats.append({str(k): float(v) for k, v in (doc.cats or {}).items()})
+        self.span_groups.append(_pack_spans(doc.spans))
         self.flags.append({"has_unknown_spaces": False})
 
     def to_bytes(self) -> bytes:
@@ -158,7 +160,8 @@ class DocBin:
             "version": self.version, "attrs": list(self.attrs),
             "tokens": tokens.astype("<u8").tobytes("C"), "spaces": spaces.tobytes("C"),
             "lengths": lengths.astype("<i4").tobytes("C"), "strings": sorted(self.strings),
-            "cats": self.cats, "flags": self.flags, "span_groups": [b"" for _ in self.tokens],
+            "cats": self.cats, "flags": self.flags,
+            "span_groups": list(self.span_groups) + [b""] * (len(self.tokens) - len(self.span_groups)),
         }
         return zlib.compress(msgpack.packb(msg, use_bin_type=True))
 
@@ -194,6 +197,7 @@ class DocBin:
             self.spaces.append(spaces[pos:pos + n])
             pos += n
         self.cats = list(msg.get("cats") or [{} for _ in self.tokens])
+        self.span_groups = list(msg.get("span_groups") or [b"" for _ in self.tokens])
         self.flags = list(msg.get("flags") or [{} for _ in self.tokens])
         return self
 
@@ -206,6 +210,7 @@ class DocBin:
         self.tokens.extend(other.tokens)
         self.spaces.extend(other.spaces)
         self.cats.extend(other.cats)
+        self.span_groups.extend(other.span_groups)
         self.flags.extend(other.flags)
         self.strings.update(other.strings)
 
@@ -230,7 +235,8 @@ class DocBin:
             return out
 
         cats_list = list(self.cats) + [{}] * (len(self.tokens) - len(self.cats))
-        for arr, sp, cats in zip(self.tokens, self.spaces, cats_list):
+        groups_list = list(self.span_groups) + [b""] * (len(self.tokens) - len(self.span_groups))
+        for arr, sp, cats, groups in zip(self.tokens, self.spaces, cats_list, groups_list):
             n = len(arr)
             words = strings_of(column(arr, "ORTH"), "ORTH")
             if any(w is None for w in words):
@@ -266,7 +272,30 @@ class DocBin:
                 sent_starts = [None if _i64(v) == 0 else (_i64(v) > 0) for v in ss]
             yield Doc(words, [bool(x) for x in sp.reshape(-1).tolist()], tags=tag_s, ents=ents, heads=heads, deps=deps,
                       pos=opt_strings("POS"), morphs=opt_strings("MORPH"), lemmas=opt_strings("LEMMA"),
-                      sent_starts=sent_starts, cats=cats or None)
+                      sent_starts=sent_starts, cats=cats or None, spans=_unpack_spans(groups))
+
+
+_SPAN_MAGIC = b"srb-spans-1"
+
+
+def _pack_spans(spans: Optional[Dict]) -> bytes:
+    """Span groups of one doc in DocBin's per-doc ``span_groups`` bytes slot.  (spaCy stores its own
+    ``SpanGroup.to_bytes`` blobs there, which need a Vocab to decode; ours carry a magic prefix + msgpack
+    ``{name: [[start, end, label], ...]}`` and anything else is ignored on read.)"""
+    if not spans:
+        return b""
+    import msgpack
+
+    return _SPAN_MAGIC + msgpack.packb({str(k): [[int(a), int(b), str(l)] for a, b, l in v] for k, v in spans.items()},
+                                       use_bin_type=True)
+
+
+def _unpack_spans(blob) -> Optional[Dict]:
+    if not blob or not isinstance(blob, (bytes, bytearray)) or not bytes(blob).startswith(_SPAN_MAGIC):
+        return None
+    import msgpack
+
+    return {k: [tuple(x) for x in v] for k, v in msgpack.unpackb(bytes(blob)[len(_SPAN_MAGIC):], raw=False).items()}
 
 
 def _sentence_starts(heads: Sequence[int]) -> List[int]:

@@ -438,3 +438,91 @@ upstream = "*"
     d1 = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
     d2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
     assert d1.lemmas == d2.lemmas and len(d1.lemmas) == len(d1)
+
+
+SPANCAT_CFG = """
+[nlp]
+lang = "en"
+pipeline = ["spancat"]
+
+[components]
+
+[components.spancat]
+factory = "spancat"
+spans_key = "sc"
+threshold = 0.5
+max_positive = null
+
+[components.spancat.suggester]
+@misc = "spacy.ngram_suggester.v1"
+sizes = [1, 2, 3]
+
+[components.spancat.model]
+@architectures = "spacy.SpanCategorizer.v1"
+
+[components.spancat.model.reducer]
+@layers = "spacy.mean_max_reducer.v1"
+hidden_size = 64
+
+[components.spancat.model.scorer]
+@layers = "spacy.LinearLogistic.v1"
+nO = null
+nI = null
+
+[components.spancat.model.tok2vec]
+@architectures = "spacy.HashEmbedCNN.v2"
+width = 32
+depth = 2
+embed_size = 300
+window_size = 1
+maxout_pieces = 3
+subword_features = true
+pretrained_vectors = null
+"""
+
+
+def _span_doc(rng):
+    """"<det> <noun>" is an NP, a noun alone is also a THING (overlapping spans), "<verb> <det> <noun>" is a VP."""
+    words, spans = [], []
+    for _ in range(rng.randint(1, 2)):
+        s0 = len(words)
+        words += [rng.choice(DETS), rng.choice(NOUNS), rng.choice(VERBS), rng.choice(DETS), rng.choice(NOUNS), "."]
+        spans += [(s0, s0 + 2, "NP"), (s0 + 1, s0 + 2, "THING"), (s0 + 3, s0 + 5, "NP"), (s0 + 4, s0 + 5, "THING"),
+                  (s0 + 2, s0 + 5, "VP")]
+    return Doc(words, spans={"sc": spans})
+
+
+def test_spancat_learns_overlapping_spans(tmp_path):
+    from spacy_ray_b200.models.spancat import ngram_suggester
+    from spacy_ray_b200.nn.layers import fix_random_seed
+    from spacy_ray_b200.pipeline import load
+    from spacy_ray_b200.pipeline.language import Language
+    from spacy_ray_b200.training.docbin import DocBin
+
+    assert ngram_suggester([1, 2])([3, 1]) == [(0, 0, 1), (0, 1, 2), (0, 2, 3), (0, 0, 2), (0, 1, 3), (1, 0, 1)]
+    fix_random_seed(0)
+    nlp = Language.from_config(Config().from_str(SPANCAT_CFG, interpolate=False))
+    rng = random.Random(7)
+    train = [Example.from_doc(_span_doc(rng)) for _ in range(200)]
+    dev = [Example.from_doc(_span_doc(rng)) for _ in range(40)]
+    nlp.initialize(lambda: train)
+    assert nlp.get_pipe("spancat").labels == ["NP", "THING", "VP"]
+    opt = nlp.create_optimizer()
+    hist = []
+    for step in range(120):
+        losses = {}
+        lo = (step * 16) % (len(train) - 16)
+        nlp.update(train[lo:lo + 16], drop=0.0, sgd=opt, losses=losses)
+        hist.append(float(losses["spancat"]))
+    assert sum(hist[-5:]) < 0.3 * sum(hist[:5]), (hist[:5], hist[-5:])
+    scores = nlp.evaluate(dev)
+    assert scores["spans_sc_f"] > 0.9, scores
+    doc = next(iter(nlp.pipe([dev[0].reference.copy_unannotated()])))
+    assert any(l == "THING" for _s, _e, l in doc.spans["sc"]) and any(l == "VP" for _s, _e, l in doc.spans["sc"])
+    # span groups survive DocBin and the checkpoint
+    DocBin(docs=[dev[0].reference]).to_disk(tmp_path / "s.spacy")
+    back = next(iter(DocBin().from_disk(tmp_path / "s.spacy").get_docs()))
+    assert back.spans == dev[0].reference.spans
+    nlp.to_disk(tmp_path / "m")
+    doc2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
+    assert doc2.spans == doc.spans

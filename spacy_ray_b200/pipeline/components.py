@@ -783,6 +783,62 @@ class SpanCategorizer(TrainablePipe):
         return S.score_spans(examples, self.spans_key)
 
 
+# ============================================================================
+class Sentencizer:
+    """``sentencizer``: rule-based sentence boundaries (a token after sentence-final punctuation starts a
+    sentence) - spaCy's non-trainable alternative to ``senter``.  Not trainable: ``nlp.update`` skips it."""
+    is_trainable = False
+    default_score_weights = {"sents_f": 1.0, "sents_p": 0.0, "sents_r": 0.0}
+    default_punct_chars = ["!", ".", "?", "\u0589", "\u061f", "\u06d4", "\u0700", "\u0701", "\u0702", "\u0964", "\u3002",
+                           "\uff01", "\uff0e", "\uff1f", "\uff61", "\u2026"]
+
+    def __init__(self, name: str, punct_chars: Optional[Sequence[str]] = None, overwrite: bool = False, **cfg):
+        self.name = name
+        self.punct_chars = set(punct_chars) if punct_chars else set(self.default_punct_chars)
+        self.overwrite = bool(overwrite)
+        self.cfg = dict(cfg)
+
+    @property
+    def labels(self) -> List[str]:
+        return []
+
+    def predict(self, docs: Sequence[Doc], batch=None):
+        out = []
+        for doc in docs:
+            starts = [False] * len(doc)
+            if starts:
+                starts[0] = True
+            seen_period = False
+            for i, w in enumerate(doc.words):
+                is_punct = w in self.punct_chars
+                if seen_period and not is_punct:
+                    starts[i] = True
+                    seen_period = False
+                elif is_punct:
+                    seen_period = True
+            out.append(starts)
+        return out
+
+    def set_annotations(self, docs: Sequence[Doc], preds) -> None:
+        for doc, starts in zip(docs, preds):
+            if doc.sent_starts is None or self.overwrite:
+                doc.sent_starts = list(starts)
+
+    def score(self, examples):
+        return S.score_sents(examples)
+
+    def to_disk(self, path: Path) -> None:
+        path = Path(path)
+        path.mkdir(parents=True, exist_ok=True)
+        (path / "cfg").write_text(json.dumps({"punct_chars": sorted(self.punct_chars), "overwrite": self.overwrite}))
+
+    def from_disk(self, path: Path) -> "Sentencizer":
+        meta = json.loads((Path(path) / "cfg").read_text())
+        self.punct_chars = set(meta.get("punct_chars") or self.default_punct_chars)
+        self.overwrite = bool(meta.get("overwrite", False))
+        return self
+
+
 # ---- factories ----------------------------------------------------------------
 @registry.factories("tok2vec")
 def make_tok2vec(nlp, name: str, model: Model) -> Tok2VecComponent:
@@ -807,6 +863,11 @@ def make_trainable_lemmatizer(nlp, name: str, model: Model, **cfg) -> TrainableL
 @registry.factories("morphologizer")
 def make_morphologizer(nlp, name: str, model: Model, **cfg) -> Morphologizer:
     return Morphologizer(name, model, **cfg)
+
+
+@registry.factories("sentencizer")
+def make_sentencizer(nlp, name: str, punct_chars: Optional[Sequence[str]] = None, overwrite: bool = False, **cfg) -> Sentencizer:
+    return Sentencizer(name, punct_chars=punct_chars, overwrite=overwrite, **cfg)
 
 
 @registry.factories("spancat")

@@ -526,3 +526,28 @@ def test_spancat_learns_overlapping_spans(tmp_path):
     nlp.to_disk(tmp_path / "m")
     doc2 = next(iter(load(tmp_path / "m").pipe([dev[0].reference.copy_unannotated()])))
     assert doc2.spans == doc.spans
+
+
+def test_sentencizer_is_a_non_trainable_pipe(tmp_path):
+    from spacy_ray_b200.pipeline import load
+    from spacy_ray_b200.pipeline.language import Language
+
+    cfg = """
+[nlp]
+lang = "en"
+pipeline = ["sentencizer"]
+
+[components]
+
+[components.sentencizer]
+factory = "sentencizer"
+"""
+    nlp = Language.from_config(Config().from_str(cfg, interpolate=False))
+    nlp.initialize()
+    doc = nlp(Doc(["Hello", "world", ".", "How", "are", "you", "?", "!", "Fine"]))
+    assert doc.sent_starts == [True, False, False, True, False, False, False, False, True]
+    egs = [Example.from_doc(d) for d in _docs(10, 4)]
+    assert nlp.update(egs, losses={}) == {}                      # nothing to train
+    assert nlp.evaluate(egs)["sents_f"] == pytest.approx(1.0)    # the toy docs end every sentence with "."
+    nlp.to_disk(tmp_path / "m")
+    assert load(tmp_path / "m")(Doc(["A", ".", "B"])).sent_starts == [True, False, True]

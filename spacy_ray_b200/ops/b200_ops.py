@@ -15,13 +15,18 @@ What this replaces: the reference itself ships no kernels; under
 thinc's ``CupyOps`` - NVRTC scalar kernels + cuBLAS fp32 - one launch per op.  Op map:
 K1 ``multi_hash_embed*`` -> ``hash_embed_fwd_kernel`` / ``hash_embed_bwd_sorted_kernel``;
 K2-K5 ``maxout_block*`` -> tcgen05 ``gemm_kernel`` (window, bias, maxout epilogue; dX from the weights
-as stored; split-K dW) + ``maxout_ln_{fwd,bwd}_vec_kernel``; K6 ``softmax_xent`` ->
-``linear_softmax_xent_kernel``; K7 ``transition_steps`` -> ``biluo_steps_kernel`` /
-``arc_eager_steps_kernel``; K8 lives in the fused exchange kernel (``parallel/fused_comm.py``).
+as stored; split-K dW) + ``maxout_ln_{fwd,bwd}_vec_kernel``; K6 ``softmax_xent`` -> tcgen05 logits GEMM +
+``softmax_xent_bias_kernel``; K7 ``transition_steps`` -> ``biluo_block_kernel`` / ``biluo_steps_kernel`` /
+``arc_eager_steps_kernel``; K8 lives in the bucketed exchange kernels (``parallel/fused_comm.py``).
 
-Environment switches (all default to the fast path): ``SRB_USE_TC``, ``SRB_TC_DW``,
-``SRB_GEMM_CLUSTER`` (1 / 2 multicast / 3 pair MMA), ``SRB_GEMM_HALO``, ``SRB_DX_BN``,
-``SRB_SIDE_DW``, ``SRB_SORTED_EMBED``.
+Environment switches.  Defaults are the measured-fastest path; the "off" ones are complete, tested
+alternatives that lost the measurement (``profiles/r2_*experiments*.md``, ``r2_fused_ln.md``):
+``SRB_USE_TC``, ``SRB_TC_DW``, ``SRB_GEMM_CLUSTER`` (1 / 2 multicast / 3 pair MMA), ``SRB_GEMM_HALO``, ``SRB_DX_BN``,
+``SRB_SIDE_DW``, ``SRB_SORTED_EMBED``, ``SRB_HOST_GROUP``, ``SRB_HEAD_STREAMS``, ``SRB_TAG_HEAD_TC`` (1),
+``SRB_BILUO_BLOCK`` (1), ``SRB_FUSED_LN`` (0: LayerNorm in the GEMM epilogue), ``SRB_GEMM_BRES`` (0: weights
+resident in shared memory), ``SRB_PDL`` / ``SRB_PDL_SIDE`` (0: programmatic dependent launch);
+exchange: ``SRB_COMM_BUCKETS`` (4), ``SRB_COMM_OVERLAP``, ``SRB_COMM_PRIO``, ``SRB_NVLS`` (auto: from 4 ranks),
+``SRB_GATE_ALWAYS``, ``SRB_COMM_TRACE``; engine: ``SRB_FAST_PATH*``.
 """
 from __future__ import annotations
 

@@ -167,6 +167,8 @@ class Head:
                 index, msg = self.uplink.get(timeout=0.2)
             except queue.Empty:
                 continue
+            except (OSError, ValueError, EOFError):      # the queue was torn down under us (interpreter exit)
+                return
             self.route(index, msg)
 
     def _reader(self, node_id: int, conn: socket.socket) -> None:
@@ -271,6 +273,8 @@ def agent_main(address: str, num_gpus: Optional[int] = None, connect_timeout: fl
                 index, msg = uplink.get(timeout=0.2)
             except queue.Empty:
                 continue
+            except (OSError, ValueError, EOFError):
+                return
             if index // pool_size == node_id:
                 local[index % pool_size].put(msg)
             else:

@@ -6,6 +6,9 @@
 set -euo pipefail
 out=${OUT_DIR:-data}
 mkdir -p "$out"
+# works from any directory, installed or not: put the repository root on the module path
+repo="$(cd "$(dirname "$0")/.." && pwd)"
+export PYTHONPATH="$repo${PYTHONPATH:+:$PYTHONPATH}"
 if [ $# -ge 2 ] && command -v wget >/dev/null; then
   wget -q -O "$out/train.jsonl" "$1"
   wget -q -O "$out/dev.jsonl" "$2"
